@@ -1,0 +1,918 @@
+// api.cu — context, orchestration of the device pipeline and the C ABI of include/asgart_b200.h.
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "automaton.cuh"
+#include "common.cuh"
+#include "sa_build.cuh"
+#include "search.cuh"
+
+namespace ab200 {
+thread_local LaunchCounter* g_launch_counter = nullptr;
+
+struct Index32 { DevBuf<u32> sa, lut_lo, lut_hi; };
+struct Index64 { DevBuf<u64> sa, lut_lo, lut_hi; };
+
+struct ChunkPlan {
+    std::vector<ChunkDev> host;
+    DevBuf<ChunkDev> dev;
+    u64 total_probes = 0;
+    u32 k = 0, s = 0;
+    int mode = PACK_DIRECT;
+    AutoParams ap{};
+};
+
+struct StageA {
+    u64 p_begin = 0, p_end = 0, n_events = 0, n_matches = 0;
+    DevBuf<u32> bits;
+    DevBuf<u64> ev_probe, ev_moff, matches;
+    DevBuf<u32> ev_cnt;
+};
+}  // namespace ab200
+
+using namespace ab200;
+
+struct asgart_b200_result {
+    std::vector<u64> fam_off;
+    std::vector<asgart_b200_protosd> sds;
+};
+
+struct asgart_b200_partial {
+    u64 p_begin = 0, p_end = 0;
+    std::vector<u32> bits;
+    std::vector<u64> ev_probe;
+    std::vector<u32> ev_cnt;
+    std::vector<u64> matches;
+};
+
+struct asgart_b200_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    u64 n1 = 0;
+    bool have_strand = false, have_index = false;
+    int want_bits = 0, idx_bits = 0;
+    DevBuf<u8> d_text;
+    DevBuf<u64> d_pt, d_pn;
+    int pn_mode = -1;
+    Index32 ix32;
+    Index64 ix64;
+    asgart_b200_stats st{};
+    FamilyTimer t_sort, t_gather, t_rank, t_probe, t_emit;
+    LaunchCounter launches;
+};
+
+namespace ab200 { namespace detail {
+
+const u64 kPartialMagic = 0x4132303050415254ull;  // "A200PART"
+
+struct ApiGuard {
+    asgart_b200_ctx* c;
+    explicit ApiGuard(asgart_b200_ctx* ctx) : c(ctx) {
+        g_launch_counter = &ctx->launches;
+        CUDA_CHECK(cudaSetDevice(ctx->device));
+    }
+    ~ApiGuard() { g_launch_counter = nullptr; }
+};
+
+template <typename F>
+int32_t guarded(asgart_b200_ctx* ctx, F f) {
+    if (!ctx) return ASGART_B200_EINVAL;
+    try {
+        ApiGuard g(ctx);
+        return f();
+    } catch (const CudaError& e) {
+        ctx->err = e.what();
+        cudaGetLastError();
+        return e.code;
+    } catch (const std::bad_alloc&) {
+        ctx->err = "host allocation failed";
+        return ASGART_B200_ENOMEM;
+    } catch (const std::exception& e) {
+        ctx->err = e.what();
+        return ASGART_B200_ECUDA;
+    }
+}
+
+int fail(asgart_b200_ctx* ctx, int code, const char* msg) {
+    ctx->err = msg;
+    return code;
+}
+
+u64 packed_words(u64 n1) { return ceil_div(n1, 16) + 4; }
+
+void pack_image(asgart_b200_ctx* ctx, int mode, DevBuf<u64>& out, u32* d_err) {
+    const u64 words = packed_words(ctx->n1);
+    out.alloc(words, ctx->stream);
+    pack_text_kernel<<<unsigned(ceil_div(words, 256)), 256, 0, ctx->stream>>>(ctx->d_text.p, ctx->n1, mode, out.p, words, d_err);
+    KERNEL_CHECK();
+    count_launch();
+}
+
+template <typename IdxT> struct IxOf;
+template <> struct IxOf<u32> { static Index32& get(asgart_b200_ctx* c) { return c->ix32; } };
+template <> struct IxOf<u64> { static Index64& get(asgart_b200_ctx* c) { return c->ix64; } };
+
+int pick_bits(const asgart_b200_ctx* ctx) {
+    if (ctx->want_bits == 32 || ctx->want_bits == 64) return ctx->want_bits;
+    return (ctx->n1 < 0xFFFFFFFEull) ? 32 : 64;
+}
+
+template <typename IdxT>
+void build_lut(asgart_b200_ctx* ctx) {
+    auto& ix = IxOf<IdxT>::get(ctx);
+    ix.lut_lo.alloc(kLutSize, ctx->stream);
+    ix.lut_hi.alloc(kLutSize, ctx->stream);
+    ix.lut_lo.zero();
+    ix.lut_hi.zero();
+    lut_build_kernel<IdxT><<<unsigned(ceil_div(ctx->n1, 256)), 256, 0, ctx->stream>>>(ctx->d_pt.p, ix.sa.p, ctx->n1, ix.lut_lo.p,
+                                                                                      ix.lut_hi.p);
+    KERNEL_CHECK();
+    count_launch();
+}
+
+template <typename IdxT>
+void build_index_t(asgart_b200_ctx* ctx) {
+    auto& ix = IxOf<IdxT>::get(ctx);
+    EventTimer tsa(ctx->stream), tlut(ctx->stream);
+    tsa.start();
+    ix.sa.alloc(ctx->n1, ctx->stream);
+    {
+        DevBuf<IdxT> rank(ctx->n1, ctx->stream);
+        SaStats ss;
+        ss.sort = &ctx->t_sort; ss.gather = &ctx->t_gather; ss.rank = &ctx->t_rank;
+        build_suffix_array<IdxT>(ctx->d_text.p, ctx->n1, ix.sa.p, rank.p, ctx->stream, &ss);
+        ctx->st.sa_rounds = ss.rounds;
+    }
+    tsa.stop();
+    tlut.start();
+    build_lut<IdxT>(ctx);
+    tlut.stop();
+    ctx->st.ms_sa_build = tsa.ms();
+    ctx->st.ms_lut = tlut.ms();
+}
+
+template <typename T>
+__global__ void widen_to_i64_kernel(const T* __restrict__ in, i64* __restrict__ out, u64 n) {
+    const u64 i = u64(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = i64(in[i]);
+}
+template <typename T>
+__global__ void narrow_from_i64_kernel(const i64* __restrict__ in, T* __restrict__ out, u64 n) {
+    const u64 i = u64(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = T(in[i]);
+}
+
+template <typename T>
+void download_as_i64(const T* d, i64* h, u64 n, cudaStream_t s) {
+    const u64 chunk = u64(1) << 26;
+    DevBuf<i64> stage(std::min(n, chunk), s);
+    for (u64 o = 0; o < n; o += chunk) {
+        const u64 m = std::min(chunk, n - o);
+        widen_to_i64_kernel<T><<<unsigned(ceil_div(m, 256)), 256, 0, s>>>(d + o, stage.p, m);
+        KERNEL_CHECK();
+        count_launch();
+        CUDA_CHECK(cudaMemcpyAsync(h + o, stage.p, m * sizeof(i64), cudaMemcpyDeviceToHost, s));
+        CUDA_CHECK(cudaStreamSynchronize(s));
+    }
+}
+template <typename T>
+void upload_from_i64(const i64* h, T* d, u64 n, cudaStream_t s) {
+    const u64 chunk = u64(1) << 26;
+    DevBuf<i64> stage(std::min(n, chunk), s);
+    for (u64 o = 0; o < n; o += chunk) {
+        const u64 m = std::min(chunk, n - o);
+        CUDA_CHECK(cudaMemcpyAsync(stage.p, h + o, m * sizeof(i64), cudaMemcpyHostToDevice, s));
+        narrow_from_i64_kernel<T><<<unsigned(ceil_div(m, 256)), 256, 0, s>>>(stage.p, d + o, m);
+        KERNEL_CHECK();
+        count_launch();
+        CUDA_CHECK(cudaStreamSynchronize(s));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- chunk plan
+int make_plan(asgart_b200_ctx* ctx, const asgart_b200_chunk* chunks, i64 n_chunks, const asgart_b200_settings* st, ChunkPlan& plan) {
+    if (!chunks || n_chunks < 0 || !st) return fail(ctx, ASGART_B200_EINVAL, "null chunks/settings");
+    if (st->probe_size < 8) return fail(ctx, ASGART_B200_EINVAL, "probe_size must be >= 8 (the reference indexes the first 8 bases, src/searcher.rs:95-97)");
+    if (st->probe_size > 4096) return fail(ctx, ASGART_B200_EINVAL, "probe_size > 4096 not supported");
+    const u64 n = ctx->n1 - 1;
+    plan.k = u32(st->probe_size);
+    plan.s = u32(st->probe_size / 2);
+    plan.mode = (st->reverse ? 2 : 0) | (st->complement ? 1 : 0);
+    plan.host.clear();
+    u64 base = 0;
+    for (i64 c = 0; c < n_chunks; ++c) {
+        ChunkDev d{};
+        d.c0 = chunks[c].start; d.len = chunks[c].length;
+        if (d.c0 > n || d.len > n - d.c0) return fail(ctx, ASGART_B200_EINVAL, "chunk outside the strand");
+        d.n_probes = probes_in_chunk(d.len, plan.k, plan.s, st->min_duplication_length);
+        d.probe_base = base;
+        d.needle_start = st->reverse ? (n - d.c0 - d.len) : d.c0;
+        base += d.n_probes;
+        plan.host.push_back(d);
+    }
+    plan.total_probes = base;
+    if (plan.host.empty()) plan.host.push_back(ChunkDev{});
+    plan.dev.alloc(plan.host.size(), ctx->stream);
+    CUDA_CHECK(cudaMemcpyAsync(plan.dev.p, plan.host.data(), plan.host.size() * sizeof(ChunkDev), cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    AutoParams& ap = plan.ap;
+    ap.k = plan.k; ap.s = plan.s; ap.G = st->max_gap_size; ap.min_len = st->min_duplication_length;
+    const u64 q = (ap.G + ap.s - 1) / ap.s;
+    ap.q_ext = std::max<u64>(1, q);
+    ap.q_new = q > 0 ? q - 1 : 0;
+    ap.reverse = st->reverse ? 1 : 0;
+    return ASGART_B200_OK;
+}
+
+void ensure_needle(asgart_b200_ctx* ctx, int mode) {
+    if (mode == PACK_DIRECT) return;
+    if (ctx->pn_mode == mode && ctx->d_pn.p) return;
+    DevBuf<u32> d_err(1, ctx->stream);
+    d_err.zero();
+    pack_image(ctx, mode, ctx->d_pn, d_err.p);
+    ctx->pn_mode = mode;
+}
+
+// ---------------------------------------------------------------------------------------------- stage A
+template <typename IdxT>
+void run_stage_a(asgart_b200_ctx* ctx, const ChunkPlan& plan, const asgart_b200_settings* st, u64 p_begin, u64 p_end, StageA& A) {
+    auto& ix = IxOf<IdxT>::get(ctx);
+    cudaStream_t s = ctx->stream;
+    A.p_begin = p_begin; A.p_end = p_end;
+    const u64 np = p_end - p_begin;
+    const u64 words = ceil_div(np, 32);
+    A.bits.alloc(words, s);
+    if (np == 0) return;
+    DevBuf<IdxT> out_lo(np, s), out_raw(np, s);
+    DevBuf<u32> out_surv(np, s);
+    DevBuf<unsigned long long> counters(CTR_COUNT, s);
+    counters.zero();
+    ProbeParams<IdxT> P{};
+    P.PT = ctx->d_pt.p;
+    P.PN = plan.mode == PACK_DIRECT ? ctx->d_pt.p : ctx->d_pn.p;
+    P.SA = ix.sa.p; P.lut_lo = ix.lut_lo.p; P.lut_hi = ix.lut_hi.p;
+    P.chunks = plan.dev.p; P.n_chunks = u32(plan.host.size());
+    P.n1 = ctx->n1; P.k = plan.k; P.s = plan.s; P.reverse = st->reverse ? 1 : 0; P.max_card = st->max_cardinality;
+    P.p_begin = p_begin; P.p_end = p_end;
+    P.out_lo = out_lo.p; P.out_raw = out_raw.p; P.out_surv = out_surv.p; P.proc_bits = A.bits.p; P.counters = counters.p;
+    ctx->t_probe.begin();
+    probe_search_kernel<IdxT><<<unsigned(ceil_div(np, 256)), 256, 0, s>>>(P);
+    KERNEL_CHECK();
+    count_launch();
+    unsigned long long h_ctr[CTR_COUNT];
+    CUDA_CHECK(cudaMemcpyAsync(h_ctr, counters.p, sizeof h_ctr, cudaMemcpyDeviceToHost, s));
+    CUDA_CHECK(cudaStreamSynchronize(s));
+    ctx->t_probe.end(1, h_ctr[CTR_ALG_BYTES]);
+    ctx->st.n_probes += np;
+    ctx->st.n_searched += h_ctr[CTR_SEARCHED];
+    ctx->st.n_skipped_n += h_ctr[CTR_SKIP_N];
+    ctx->st.n_skipped_card += h_ctr[CTR_SKIP_CARD];
+    ctx->st.n_matches += h_ctr[CTR_MATCHES];
+
+    // match offsets + event list + emission, fused into one scan
+    ctx->t_emit.begin();
+    const u32* surv = out_surv.p;
+    auto in = [surv] __device__(u64 o) { const u32 v = surv[o]; return Sum2(u64(v), v ? 1ull : 0ull); };
+    DevBuf<Sum2> d_total(1, s);
+    ScanPlan<Sum2, Sum2Op> scan;
+    scan.prepare(in, np, d_total.p, s);
+    Sum2 tot;
+    CUDA_CHECK(cudaMemcpyAsync(&tot, d_total.p, sizeof tot, cudaMemcpyDeviceToHost, s));
+    CUDA_CHECK(cudaStreamSynchronize(s));
+    A.n_matches = tot.a; A.n_events = tot.b;
+    A.ev_probe.alloc(A.n_events, s); A.ev_cnt.alloc(A.n_events, s); A.ev_moff.alloc(A.n_events, s);
+    A.matches.alloc(A.n_matches, s);
+    {
+        u64* ev_probe = A.ev_probe.p; u32* ev_cnt = A.ev_cnt.p; u64* ev_moff = A.ev_moff.p; u64* matches = A.matches.p;
+        const IdxT* lo = out_lo.p; const IdxT* raw = out_raw.p; const IdxT* SA = ix.sa.p;
+        const ChunkDev* chunks = plan.dev.p; const u32 n_chunks = u32(plan.host.size());
+        const u32 sstep = plan.s; const bool rev = st->reverse != 0;
+        scan.finish(in, [=] __device__(u64 o, const Sum2& exc, const Sum2&) {
+            const u32 v = surv[o];
+            if (!v) return;
+            const u64 g = p_begin + o;
+            ev_probe[exc.b] = g; ev_cnt[exc.b] = v; ev_moff[exc.b] = exc.a;
+            const ChunkDev ch = chunks[chunk_of_probe(chunks, n_chunks, g)];
+            const u64 i = (g - ch.probe_base + 1) * sstep;
+            const u64 b = u64(lo[o]), e = b + u64(raw[o]);
+            u64 w = exc.a;
+            for (u64 j = b; j < e; ++j) {
+                const u64 x = u64(SA[j]);
+                if (match_survives(x, i, ch.c0, ch.len, rev)) matches[w++] = x;
+            }
+        });
+    }
+    ctx->t_emit.end(3, 0);
+}
+
+// ---------------------------------------------------------------------------------------------- post-steps
+// d_sds / d_off are replaced by the post-processed families
+void run_post(asgart_b200_ctx* ctx, DevBuf<asgart_b200_protosd>& d_sds, DevBuf<u64>& d_off, u64& n_fam, u64& n_sds, u32 post_mask) {
+    cudaStream_t s = ctx->stream;
+    if (n_fam == 0 || post_mask == 0) return;
+    DevBuf<u8> keep(n_sds, s);
+    if (post_mask & ASGART_B200_POST_FILTER_NS) {
+        n_content_kernel<<<unsigned(ceil_div(n_sds * 32, 256)), 256, 0, s>>>(ctx->d_text.p, d_sds.p, n_sds, keep.p);
+        KERNEL_CHECK();
+        count_launch();
+    }
+    DevBuf<u64> new_count(n_fam, s);
+    post_family_kernel<<<unsigned(ceil_div(n_fam, 64)), 64, 0, s>>>(d_sds.p, d_off.p, n_fam, keep.p, post_mask, new_count.p);
+    KERNEL_CHECK();
+    count_launch();
+    const u64* nc = new_count.p;
+    auto in = [nc] __device__(u64 f) { const u64 v = nc[f]; return Sum2(v, v ? 1ull : 0ull); };
+    DevBuf<Sum2> d_total(1, s);
+    ScanPlan<Sum2, Sum2Op> scan;
+    scan.prepare(in, n_fam, d_total.p, s);
+    Sum2 tot;
+    CUDA_CHECK(cudaMemcpyAsync(&tot, d_total.p, sizeof tot, cudaMemcpyDeviceToHost, s));
+    CUDA_CHECK(cudaStreamSynchronize(s));
+    DevBuf<asgart_b200_protosd> out_sds(tot.a, s);
+    DevBuf<u64> out_off(tot.b + 1, s);
+    {
+        const asgart_b200_protosd* src = d_sds.p; const u64* off = d_off.p;
+        asgart_b200_protosd* dst = out_sds.p; u64* ooff = out_off.p;
+        scan.finish(in, [=] __device__(u64 f, const Sum2& exc, const Sum2&) {
+            const u64 v = nc[f];
+            if (!v) return;
+            ooff[exc.b] = exc.a;
+            const u64 b = off[f];
+            for (u64 r = 0; r < v; ++r) dst[exc.a + r] = src[b + r];
+        });
+    }
+    CUDA_CHECK(cudaMemcpyAsync(out_off.p + tot.b, &tot.a, sizeof(u64), cudaMemcpyHostToDevice, s));
+    CUDA_CHECK(cudaStreamSynchronize(s));
+    d_sds = std::move(out_sds);
+    d_off = std::move(out_off);
+    n_sds = tot.a;
+    n_fam = tot.b;
+}
+
+void download_result(asgart_b200_ctx* ctx, const DevBuf<asgart_b200_protosd>& d_sds, const DevBuf<u64>& d_off, u64 n_fam, u64 n_sds,
+                     asgart_b200_result* r) {
+    r->fam_off.assign(n_fam + 1, 0);
+    r->sds.resize(n_sds);
+    EventTimer t(ctx->stream);
+    t.start();
+    if (n_fam) CUDA_CHECK(cudaMemcpyAsync(r->fam_off.data(), d_off.p, (n_fam + 1) * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+    if (n_sds) CUDA_CHECK(cudaMemcpyAsync(r->sds.data(), d_sds.p, n_sds * sizeof(asgart_b200_protosd), cudaMemcpyDeviceToHost, ctx->stream));
+    t.stop();
+    ctx->st.ms_d2h += t.ms();
+    ctx->st.d2h_bytes += (n_fam + 1) * sizeof(u64) + n_sds * sizeof(asgart_b200_protosd);
+}
+
+// ---------------------------------------------------------------------------------------------- stage B
+__global__ void chunk_tc_kernel(const ChunkDev* __restrict__ chunks, u32 n_chunks, const u32* __restrict__ bits,
+                                const u64* __restrict__ wpre, u64* __restrict__ tc) {
+    const u32 c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_chunks) return;
+    const u64 b = chunks[c].probe_base;
+    tc[c] = processed_before(bits, wpre, b + chunks[c].n_probes) - processed_before(bits, wpre, b);
+}
+
+// bits: processed bitmask over all probes; events sorted by probe; ev_moff = exclusive scan of ev_cnt
+void run_stage_b(asgart_b200_ctx* ctx, const ChunkPlan& plan, const asgart_b200_settings* st, const u32* d_bits, u64 n_events,
+                 const u64* ev_probe, const u32* ev_cnt, const u64* ev_moff, const u64* matches, u64 n_matches, u32 post_mask,
+                 asgart_b200_result* result) {
+    cudaStream_t s = ctx->stream;
+    EventTimer tauto(s), tpost(s);
+    tauto.start();
+    ctx->st.n_events = n_events;
+    u64 n_fam = 0, n_sds = 0;
+    DevBuf<asgart_b200_protosd> d_sds;
+    DevBuf<u64> d_off;
+    if (n_events > 0) {
+        const u64 words = ceil_div(plan.total_probes, 32);
+        DevBuf<u64> wpre(words + 1, s);
+        {
+            u64* wp = wpre.p;
+            device_scan<u64, SumOp>([d_bits] __device__(u64 w) { return u64(__popc(d_bits[w])); },
+                                    [wp] __device__(u64 w, u64 exc, u64) { wp[w] = exc; }, words, wpre.p + words, s);
+        }
+        const u32 n_chunks = u32(plan.host.size());
+        DevBuf<u64> tc(n_chunks, s);
+        chunk_tc_kernel<<<ceil_div_i(n_chunks, 128), 128, 0, s>>>(plan.dev.p, n_chunks, d_bits, wpre.p, tc.p);
+        KERNEL_CHECK();
+        DevBuf<u64> ev_i(n_events, s), ev_t(n_events, s);
+        DevBuf<u32> ev_chunk(n_events, s);
+        DevBuf<u8> ev_head(n_events, s);
+        event_info_kernel<<<unsigned(ceil_div(n_events, 256)), 256, 0, s>>>(ev_probe, n_events, plan.dev.p, n_chunks, d_bits, wpre.p,
+                                                                          plan.s, plan.ap.q_ext, ev_i.p, ev_t.p, ev_chunk.p, ev_head.p);
+        KERNEL_CHECK();
+        count_launch(2);
+        // segments
+        const u8* hd = ev_head.p;
+        auto in_seg = [hd] __device__(u64 e) { return u64(hd[e]); };
+        DevBuf<u64> d_nseg(1, s);
+        ScanPlan<u64, SumOp> seg_scan;
+        seg_scan.prepare(in_seg, n_events, d_nseg.p, s);
+        u64 n_seg = 0;
+        CUDA_CHECK(cudaMemcpyAsync(&n_seg, d_nseg.p, sizeof n_seg, cudaMemcpyDeviceToHost, s));
+        CUDA_CHECK(cudaStreamSynchronize(s));
+        ctx->st.n_segments = n_seg;
+        DevBuf<u64> seg_first(n_seg + 1, s);
+        {
+            u64* sf = seg_first.p;
+            seg_scan.finish(in_seg, [hd, sf] __device__(u64 e, u64 exc, u64) { if (hd[e]) sf[exc] = e; });
+            CUDA_CHECK(cudaMemcpyAsync(seg_first.p + n_seg, &n_events, sizeof(u64), cudaMemcpyHostToDevice, s));
+        }
+        // automaton
+        DevBuf<i64> op_target(n_matches, s);
+        DevBuf<u64> a_ls(n_matches, s), a_le(n_matches, s), a_rs(n_matches, s), a_re(n_matches, s), a_death(n_matches, s);
+        DevBuf<asgart_b200_protosd> out_sd(n_matches, s);
+        DevBuf<u8> out_flag(n_matches, s);
+        out_flag.zero();
+        AutoBuffers B{};
+        B.ev_i = ev_i.p; B.ev_t = ev_t.p; B.ev_moff = ev_moff; B.ev_cnt = ev_cnt; B.ev_chunk = ev_chunk.p;
+        B.seg_first = seg_first.p; B.matches = matches; B.op_target = op_target.p;
+        B.a_ls = a_ls.p; B.a_le = a_le.p; B.a_rs = a_rs.p; B.a_re = a_re.p; B.a_death = a_death.p;
+        B.out_sd = out_sd.p; B.out_flag = out_flag.p; B.chunk_tc = tc.p; B.chunks = plan.dev.p;
+        automaton_kernel<<<unsigned(ceil_div(n_seg, 64)), 64, 0, s>>>(B, plan.ap, n_seg, st->reverse ? 1 : 0, st->complement ? 1 : 0);
+        KERNEL_CHECK();
+        count_launch();
+        // compaction into CSR families
+        const u8* fl = out_flag.p;
+        auto in_c = [fl] __device__(u64 j) { const u8 f = fl[j]; return Sum2(f ? 1ull : 0ull, f == 3 ? 1ull : 0ull); };
+        DevBuf<Sum2> d_tot(1, s);
+        ScanPlan<Sum2, Sum2Op> cscan;
+        cscan.prepare(in_c, n_matches, d_tot.p, s);
+        Sum2 tot;
+        CUDA_CHECK(cudaMemcpyAsync(&tot, d_tot.p, sizeof tot, cudaMemcpyDeviceToHost, s));
+        CUDA_CHECK(cudaStreamSynchronize(s));
+        n_sds = tot.a; n_fam = tot.b;
+        d_sds.alloc(n_sds, s);
+        d_off.alloc(n_fam + 1, s);
+        {
+            const asgart_b200_protosd* src = out_sd.p; asgart_b200_protosd* dst = d_sds.p; u64* off = d_off.p;
+            cscan.finish(in_c, [=] __device__(u64 j, const Sum2& exc, const Sum2&) {
+                const u8 f = fl[j];
+                if (!f) return;
+                dst[exc.a] = src[j];
+                if (f == 3) off[exc.b] = exc.a;
+            });
+            CUDA_CHECK(cudaMemcpyAsync(d_off.p + n_fam, &n_sds, sizeof(u64), cudaMemcpyHostToDevice, s));
+            CUDA_CHECK(cudaStreamSynchronize(s));
+        }
+    }
+    tauto.stop();
+    tpost.start();
+    run_post(ctx, d_sds, d_off, n_fam, n_sds, post_mask);
+    tpost.stop();
+    ctx->st.ms_automaton += tauto.ms();
+    ctx->st.ms_post += tpost.ms();
+    download_result(ctx, d_sds, d_off, n_fam, n_sds, result);
+}
+
+void shard_range(u64 total, int shard, int n_shards, u64& b, u64& e) {
+    u64 per = ceil_div(ceil_div(total, u64(n_shards)), 32) * 32;
+    if (per == 0) per = 32;
+    b = std::min(total, u64(shard) * per);
+    e = std::min(total, u64(shard + 1) * per);
+}
+
+void fold_family_timers(asgart_b200_ctx* ctx) {
+    ctx->t_sort.drain(); ctx->t_gather.drain(); ctx->t_rank.drain(); ctx->t_probe.drain(); ctx->t_emit.drain();
+    asgart_b200_stats& S = ctx->st;
+    S.ms_sa_sort = ctx->t_sort.total_ms; S.launches_sa_sort = ctx->t_sort.launches; S.bytes_sa_sort = ctx->t_sort.bytes;
+    S.ms_sa_gather = ctx->t_gather.total_ms; S.launches_sa_gather = ctx->t_gather.launches; S.bytes_sa_gather = ctx->t_gather.bytes;
+    S.ms_sa_rank = ctx->t_rank.total_ms;
+    S.ms_probe = ctx->t_probe.total_ms; S.launches_probe = ctx->t_probe.launches; S.bytes_probe = ctx->t_probe.bytes;
+    S.ms_emit = ctx->t_emit.total_ms;
+    S.launches_total = ctx->launches.total;
+    S.sa_index_bits = u64(ctx->idx_bits);
+}
+
+} }  // namespace ab200::detail
+using namespace ab200::detail;
+
+// ================================================================================================ C ABI
+extern "C" {
+
+const char* asgart_b200_version(void) { return "asgart_b200 0.1.0 (sm_100a; prefix-doubling SA, lock-step probe search)"; }
+
+int32_t asgart_b200_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int32_t asgart_b200_ctx_create(int32_t device, asgart_b200_ctx** out) {
+    if (!out) return ASGART_B200_EINVAL;
+    *out = nullptr;
+    int n = asgart_b200_device_count();
+    if (n <= 0) return ASGART_B200_ENODEVICE;
+    if (device < 0 || device >= n) return ASGART_B200_EINVAL;
+    asgart_b200_ctx* ctx = new (std::nothrow) asgart_b200_ctx();
+    if (!ctx) return ASGART_B200_ENOMEM;
+    ctx->device = device;
+    try {
+        CUDA_CHECK(cudaSetDevice(device));
+        CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        cudaMemPool_t pool;
+        CUDA_CHECK(cudaDeviceGetDefaultMemPool(&pool, device));
+        u64 thr = ~u64(0);
+        CUDA_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+        ctx->t_sort.init(ctx->stream); ctx->t_gather.init(ctx->stream); ctx->t_rank.init(ctx->stream);
+        ctx->t_probe.init(ctx->stream); ctx->t_emit.init(ctx->stream);
+    } catch (const CudaError& e) {
+        int code = e.code;
+        delete ctx;
+        cudaGetLastError();
+        return code;
+    }
+    *out = ctx;
+    return ASGART_B200_OK;
+}
+
+void asgart_b200_ctx_destroy(asgart_b200_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    ctx->t_sort.destroy(); ctx->t_gather.destroy(); ctx->t_rank.destroy(); ctx->t_probe.destroy(); ctx->t_emit.destroy();
+    ctx->d_text.release(); ctx->d_pt.release(); ctx->d_pn.release();
+    ctx->ix32.sa.release(); ctx->ix32.lut_lo.release(); ctx->ix32.lut_hi.release();
+    ctx->ix64.sa.release(); ctx->ix64.lut_lo.release(); ctx->ix64.lut_hi.release();
+    cudaStreamSynchronize(ctx->stream);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* asgart_b200_ctx_last_error(const asgart_b200_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int32_t asgart_b200_ctx_set_index_bits(asgart_b200_ctx* ctx, int32_t bits) {
+    if (!ctx || (bits != 0 && bits != 32 && bits != 64)) return ASGART_B200_EINVAL;
+    ctx->want_bits = bits;
+    return ASGART_B200_OK;
+}
+
+int32_t asgart_b200_ctx_load_strand(asgart_b200_ctx* ctx, const uint8_t* T, int64_t n_plus_1) {
+    return guarded(ctx, [&]() -> int32_t {
+        if (!T || n_plus_1 < 1) return fail(ctx, ASGART_B200_EINVAL, "null strand or n_plus_1 < 1");
+        ctx->have_strand = ctx->have_index = false;
+        ctx->pn_mode = -1;
+        ctx->n1 = u64(n_plus_1);
+        EventTimer th(ctx->stream), tp(ctx->stream);
+        th.start();
+        ctx->d_text.alloc(ctx->n1, ctx->stream);
+        CUDA_CHECK(cudaMemcpyAsync(ctx->d_text.p, T, ctx->n1, cudaMemcpyHostToDevice, ctx->stream));
+        th.stop();
+        tp.start();
+        DevBuf<u32> d_err(1, ctx->stream);
+        d_err.zero();
+        pack_image(ctx, PACK_DIRECT, ctx->d_pt, d_err.p);
+        tp.stop();
+        u32 h_err = 0;
+        CUDA_CHECK(cudaMemcpyAsync(&h_err, d_err.p, sizeof h_err, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        ctx->st.ms_h2d = th.ms();
+        ctx->st.ms_pack = tp.ms();
+        ctx->st.h2d_bytes += ctx->n1;
+        if (h_err) return fail(ctx, ASGART_B200_EINVAL, "strand is not normalised: expected bytes in {A,C,G,N,T} followed by one '$'");
+        ctx->have_strand = true;
+        return ASGART_B200_OK;
+    });
+}
+
+int32_t asgart_b200_ctx_build_index(asgart_b200_ctx* ctx) {
+    return guarded(ctx, [&]() -> int32_t {
+        if (!ctx->have_strand) return fail(ctx, ASGART_B200_ESTATE, "build_index before load_strand");
+        ctx->have_index = false;
+        ctx->idx_bits = pick_bits(ctx);
+        if (ctx->idx_bits == 32 && ctx->n1 >= 0xFFFFFFFEull) return fail(ctx, ASGART_B200_EINVAL, "32-bit indices need n+1 < 2^32-2");
+        if (ctx->idx_bits == 32) { ctx->ix64 = Index64(); build_index_t<u32>(ctx); }
+        else { ctx->ix32 = Index32(); build_index_t<u64>(ctx); }
+        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        ctx->have_index = true;
+        return ASGART_B200_OK;
+    });
+}
+
+int32_t asgart_b200_ctx_upload_sa(asgart_b200_ctx* ctx, const int64_t* SA) {
+    return guarded(ctx, [&]() -> int32_t {
+        if (!ctx->have_strand) return fail(ctx, ASGART_B200_ESTATE, "upload_sa before load_strand");
+        if (!SA) return fail(ctx, ASGART_B200_EINVAL, "null SA");
+        ctx->have_index = false;
+        ctx->idx_bits = pick_bits(ctx);
+        if (ctx->idx_bits == 32) {
+            ctx->ix64 = Index64();
+            ctx->ix32.sa.alloc(ctx->n1, ctx->stream);
+            upload_from_i64<u32>(SA, ctx->ix32.sa.p, ctx->n1, ctx->stream);
+            build_lut<u32>(ctx);
+        } else {
+            ctx->ix32 = Index32();
+            ctx->ix64.sa.alloc(ctx->n1, ctx->stream);
+            upload_from_i64<u64>(SA, ctx->ix64.sa.p, ctx->n1, ctx->stream);
+            build_lut<u64>(ctx);
+        }
+        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        ctx->have_index = true;
+        return ASGART_B200_OK;
+    });
+}
+
+int32_t asgart_b200_ctx_download_sa(asgart_b200_ctx* ctx, int64_t* SA) {
+    return guarded(ctx, [&]() -> int32_t {
+        if (!ctx->have_index) return fail(ctx, ASGART_B200_ESTATE, "download_sa before build_index");
+        if (!SA) return fail(ctx, ASGART_B200_EINVAL, "null SA");
+        if (ctx->idx_bits == 32) download_as_i64<u32>(ctx->ix32.sa.p, SA, ctx->n1, ctx->stream);
+        else download_as_i64<u64>(ctx->ix64.sa.p, SA, ctx->n1, ctx->stream);
+        return ASGART_B200_OK;
+    });
+}
+
+int32_t asgart_b200_ctx_download_lut(asgart_b200_ctx* ctx, int64_t* lo, int64_t* hi) {
+    return guarded(ctx, [&]() -> int32_t {
+        if (!ctx->have_index) return fail(ctx, ASGART_B200_ESTATE, "download_lut before build_index");
+        if (!lo || !hi) return fail(ctx, ASGART_B200_EINVAL, "null output");
+        if (ctx->idx_bits == 32) {
+            download_as_i64<u32>(ctx->ix32.lut_lo.p, lo, kLutSize, ctx->stream);
+            download_as_i64<u32>(ctx->ix32.lut_hi.p, hi, kLutSize, ctx->stream);
+        } else {
+            download_as_i64<u64>(ctx->ix64.lut_lo.p, lo, kLutSize, ctx->stream);
+            download_as_i64<u64>(ctx->ix64.lut_hi.p, hi, kLutSize, ctx->stream);
+        }
+        return ASGART_B200_OK;
+    });
+}
+
+int32_t asgart_b200_ctx_probe_ranges(asgart_b200_ctx* ctx, const asgart_b200_chunk* chunk, const asgart_b200_settings* st,
+                                     int64_t* lo, int64_t* hi, int64_t n_probes) {
+    return guarded(ctx, [&]() -> int32_t {
+        if (!ctx->have_index) return fail(ctx, ASGART_B200_ESTATE, "probe_ranges before build_index");
+        if (!lo || !hi || n_probes < 0) return fail(ctx, ASGART_B200_EINVAL, "bad output arrays");
+        ChunkPlan plan;
+        asgart_b200_settings s2 = *st;
+        s2.min_duplication_length = 0;
+        int rc = make_plan(ctx, chunk, 1, &s2, plan);
+        if (rc) return rc;
+        if (u64(n_probes) > plan.host[0].n_probes) return fail(ctx, ASGART_B200_EINVAL, "n_probes exceeds the chunk's probe count");
+        if (n_probes == 0) return ASGART_B200_OK;
+        ensure_needle(ctx, plan.mode);
+        DevBuf<i64> d_lo(n_probes, ctx->stream), d_hi(n_probes, ctx->stream);
+        auto launch = [&](auto tag) {
+            using IdxT = decltype(tag);
+            auto& ix = IxOf<IdxT>::get(ctx);
+            ProbeParams<IdxT> P{};
+            P.PT = ctx->d_pt.p; P.PN = plan.mode == PACK_DIRECT ? ctx->d_pt.p : ctx->d_pn.p;
+            P.SA = ix.sa.p; P.lut_lo = ix.lut_lo.p; P.lut_hi = ix.lut_hi.p;
+            P.chunks = plan.dev.p; P.n_chunks = 1; P.n1 = ctx->n1; P.k = plan.k; P.s = plan.s;
+            P.p_begin = 0; P.p_end = u64(n_probes);
+            probe_ranges_kernel<IdxT><<<unsigned(ceil_div(u64(n_probes), 256)), 256, 0, ctx->stream>>>(P, d_lo.p, d_hi.p);
+            KERNEL_CHECK();
+            count_launch();
+        };
+        if (ctx->idx_bits == 32) launch(u32(0)); else launch(u64(0));
+        CUDA_CHECK(cudaMemcpyAsync(lo, d_lo.p, n_probes * sizeof(i64), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_CHECK(cudaMemcpyAsync(hi, d_hi.p, n_probes * sizeof(i64), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        return ASGART_B200_OK;
+    });
+}
+
+int32_t asgart_b200_ctx_search(asgart_b200_ctx* ctx, const asgart_b200_chunk* chunks, int64_t n_chunks,
+                               const asgart_b200_settings* st, uint32_t post_mask, asgart_b200_result** out) {
+    return guarded(ctx, [&]() -> int32_t {
+        if (!out) return fail(ctx, ASGART_B200_EINVAL, "null out");
+        *out = nullptr;
+        if (!ctx->have_index) return fail(ctx, ASGART_B200_ESTATE, "search before build_index");
+        ChunkPlan plan;
+        int rc = make_plan(ctx, chunks, n_chunks, st, plan);
+        if (rc) return rc;
+        ensure_needle(ctx, plan.mode);
+        EventTimer ts(ctx->stream);
+        ts.start();
+        StageA A;
+        if (ctx->idx_bits == 32) run_stage_a<u32>(ctx, plan, st, 0, plan.total_probes, A);
+        else run_stage_a<u64>(ctx, plan, st, 0, plan.total_probes, A);
+        ts.stop();
+        ctx->st.ms_search += ts.ms();
+        asgart_b200_result* r = new asgart_b200_result();
+        try {
+            run_stage_b(ctx, plan, st, A.bits.p, A.n_events, A.ev_probe.p, A.ev_cnt.p, A.ev_moff.p, A.matches.p, A.n_matches, post_mask, r);
+        } catch (...) { delete r; throw; }
+        *out = r;
+        return ASGART_B200_OK;
+    });
+}
+
+int32_t asgart_b200_ctx_search_shard(asgart_b200_ctx* ctx, const asgart_b200_chunk* chunks, int64_t n_chunks,
+                                     const asgart_b200_settings* st, int32_t shard, int32_t n_shards, asgart_b200_partial** out) {
+    return guarded(ctx, [&]() -> int32_t {
+        if (!out || n_shards < 1 || shard < 0 || shard >= n_shards) return fail(ctx, ASGART_B200_EINVAL, "bad shard arguments");
+        *out = nullptr;
+        if (!ctx->have_index) return fail(ctx, ASGART_B200_ESTATE, "search before build_index");
+        ChunkPlan plan;
+        int rc = make_plan(ctx, chunks, n_chunks, st, plan);
+        if (rc) return rc;
+        ensure_needle(ctx, plan.mode);
+        u64 b, e;
+        shard_range(plan.total_probes, shard, n_shards, b, e);
+        EventTimer ts(ctx->stream);
+        ts.start();
+        StageA A;
+        if (ctx->idx_bits == 32) run_stage_a<u32>(ctx, plan, st, b, e, A);
+        else run_stage_a<u64>(ctx, plan, st, b, e, A);
+        ts.stop();
+        ctx->st.ms_search += ts.ms();
+        asgart_b200_partial* p = new asgart_b200_partial();
+        p->p_begin = b; p->p_end = e;
+        p->bits.resize(ceil_div(e - b, 32));
+        p->ev_probe.resize(A.n_events); p->ev_cnt.resize(A.n_events); p->matches.resize(A.n_matches);
+        cudaStream_t s = ctx->stream;
+        if (!p->bits.empty()) CUDA_CHECK(cudaMemcpyAsync(p->bits.data(), A.bits.p, p->bits.size() * 4, cudaMemcpyDeviceToHost, s));
+        if (A.n_events) {
+            CUDA_CHECK(cudaMemcpyAsync(p->ev_probe.data(), A.ev_probe.p, A.n_events * 8, cudaMemcpyDeviceToHost, s));
+            CUDA_CHECK(cudaMemcpyAsync(p->ev_cnt.data(), A.ev_cnt.p, A.n_events * 4, cudaMemcpyDeviceToHost, s));
+        }
+        if (A.n_matches) CUDA_CHECK(cudaMemcpyAsync(p->matches.data(), A.matches.p, A.n_matches * 8, cudaMemcpyDeviceToHost, s));
+        CUDA_CHECK(cudaStreamSynchronize(s));
+        ctx->st.d2h_bytes += p->bits.size() * 4 + A.n_events * 12 + A.n_matches * 8;
+        *out = p;
+        return ASGART_B200_OK;
+    });
+}
+
+int64_t asgart_b200_partial_size(const asgart_b200_partial* p) {
+    if (!p) return 0;
+    return int64_t(6 * 8 + p->bits.size() * 4 + p->ev_probe.size() * 8 + p->ev_cnt.size() * 4 + p->matches.size() * 8);
+}
+
+int32_t asgart_b200_partial_serialize(const asgart_b200_partial* p, uint8_t* buf, int64_t cap) {
+    if (!p || !buf || cap < asgart_b200_partial_size(p)) return ASGART_B200_EINVAL;
+    u64 hdr[6] = {kPartialMagic, p->p_begin, p->p_end, u64(p->bits.size()), u64(p->ev_probe.size()), u64(p->matches.size())};
+    uint8_t* w = buf;
+    memcpy(w, hdr, sizeof hdr); w += sizeof hdr;
+    memcpy(w, p->bits.data(), p->bits.size() * 4); w += p->bits.size() * 4;
+    memcpy(w, p->ev_probe.data(), p->ev_probe.size() * 8); w += p->ev_probe.size() * 8;
+    memcpy(w, p->ev_cnt.data(), p->ev_cnt.size() * 4); w += p->ev_cnt.size() * 4;
+    memcpy(w, p->matches.data(), p->matches.size() * 8);
+    return ASGART_B200_OK;
+}
+
+void asgart_b200_partial_free(asgart_b200_partial* p) { delete p; }
+
+int32_t asgart_b200_ctx_finish(asgart_b200_ctx* ctx, const asgart_b200_chunk* chunks, int64_t n_chunks, const asgart_b200_settings* st,
+                               const uint8_t* const* partials, const int64_t* sizes, int32_t n_shards, uint32_t post_mask,
+                               asgart_b200_result** out) {
+    return guarded(ctx, [&]() -> int32_t {
+        if (!out || !partials || !sizes || n_shards < 1) return fail(ctx, ASGART_B200_EINVAL, "bad finish arguments");
+        *out = nullptr;
+        if (!ctx->have_strand) return fail(ctx, ASGART_B200_ESTATE, "finish before load_strand");
+        ChunkPlan plan;
+        int rc = make_plan(ctx, chunks, n_chunks, st, plan);
+        if (rc) return rc;
+        const u64 words = ceil_div(plan.total_probes, 32);
+        std::vector<u32> bits(words, 0);
+        std::vector<u64> ev_probe, matches;
+        std::vector<u32> ev_cnt;
+        u64 expect = 0;
+        for (int r = 0; r < n_shards; ++r) {
+            const uint8_t* b = partials[r];
+            if (!b || sizes[r] < 48) return fail(ctx, ASGART_B200_EINVAL, "partial too small");
+            u64 hdr[6];
+            memcpy(hdr, b, sizeof hdr);
+            if (hdr[0] != kPartialMagic) return fail(ctx, ASGART_B200_EINVAL, "bad partial magic");
+            const u64 pb = hdr[1], pe = hdr[2], nb = hdr[3], ne = hdr[4], nm = hdr[5];
+            if (pb != expect || pe < pb || pe > plan.total_probes || ((pb & 31) && pb != plan.total_probes) || nb != ceil_div(pe - pb, 32) ||
+                u64(sizes[r]) != 48 + nb * 4 + ne * 12 + nm * 8)
+                return fail(ctx, ASGART_B200_EINVAL, "partials are not the consecutive shards of this plan");
+            expect = pe;
+            const uint8_t* p = b + 48;
+            memcpy(bits.data() + (pb >> 5), p, nb * 4); p += nb * 4;
+            size_t e0 = ev_probe.size(), m0 = matches.size();
+            ev_probe.resize(e0 + ne); ev_cnt.resize(e0 + ne); matches.resize(m0 + nm);
+            memcpy(ev_probe.data() + e0, p, ne * 8); p += ne * 8;
+            memcpy(ev_cnt.data() + e0, p, ne * 4); p += ne * 4;
+            memcpy(matches.data() + m0, p, nm * 8);
+        }
+        if (expect != plan.total_probes) return fail(ctx, ASGART_B200_EINVAL, "partials do not cover all probes");
+        cudaStream_t s = ctx->stream;
+        const u64 ne = ev_probe.size(), nm = matches.size();
+        DevBuf<u32> d_bits(words, s), d_cnt(ne, s);
+        DevBuf<u64> d_probe(ne, s), d_moff(ne, s), d_matches(nm, s);
+        if (words) CUDA_CHECK(cudaMemcpyAsync(d_bits.p, bits.data(), words * 4, cudaMemcpyHostToDevice, s));
+        if (ne) {
+            CUDA_CHECK(cudaMemcpyAsync(d_probe.p, ev_probe.data(), ne * 8, cudaMemcpyHostToDevice, s));
+            CUDA_CHECK(cudaMemcpyAsync(d_cnt.p, ev_cnt.data(), ne * 4, cudaMemcpyHostToDevice, s));
+            const u32* cp = d_cnt.p; u64* mp = d_moff.p;
+            device_scan<u64, SumOp>([cp] __device__(u64 e) { return u64(cp[e]); }, [mp] __device__(u64 e, u64 exc, u64) { mp[e] = exc; },
+                                    ne, (u64*)nullptr, s);
+        }
+        if (nm) CUDA_CHECK(cudaMemcpyAsync(d_matches.p, matches.data(), nm * 8, cudaMemcpyHostToDevice, s));
+        ctx->st.h2d_bytes += words * 4 + ne * 12 + nm * 8;
+        asgart_b200_result* r = new asgart_b200_result();
+        try {
+            run_stage_b(ctx, plan, st, d_bits.p, ne, d_probe.p, d_cnt.p, d_moff.p, d_matches.p, nm, post_mask, r);
+        } catch (...) { delete r; throw; }
+        *out = r;
+        return ASGART_B200_OK;
+    });
+}
+
+int32_t asgart_b200_ctx_post_steps(asgart_b200_ctx* ctx, const uint64_t* family_offsets, int64_t n_families,
+                                   const asgart_b200_protosd* sds, uint32_t post_mask, asgart_b200_result** out) {
+    return guarded(ctx, [&]() -> int32_t {
+        if (!out || !family_offsets || n_families < 0) return fail(ctx, ASGART_B200_EINVAL, "bad post_steps arguments");
+        *out = nullptr;
+        if ((post_mask & ASGART_B200_POST_FILTER_NS) && !ctx->have_strand) return fail(ctx, ASGART_B200_ESTATE, "FilterNs needs a loaded strand");
+        u64 n_fam = u64(n_families), n_sds = family_offsets[n_families];
+        if (n_sds && !sds) return fail(ctx, ASGART_B200_EINVAL, "null sds");
+        cudaStream_t s = ctx->stream;
+        DevBuf<asgart_b200_protosd> d_sds(n_sds, s);
+        DevBuf<u64> d_off(n_fam + 1, s);
+        CUDA_CHECK(cudaMemcpyAsync(d_off.p, family_offsets, (n_fam + 1) * 8, cudaMemcpyHostToDevice, s));
+        if (n_sds) CUDA_CHECK(cudaMemcpyAsync(d_sds.p, sds, n_sds * sizeof(asgart_b200_protosd), cudaMemcpyHostToDevice, s));
+        CUDA_CHECK(cudaStreamSynchronize(s));
+        run_post(ctx, d_sds, d_off, n_fam, n_sds, post_mask);
+        asgart_b200_result* r = new asgart_b200_result();
+        try { download_result(ctx, d_sds, d_off, n_fam, n_sds, r); } catch (...) { delete r; throw; }
+        CUDA_CHECK(cudaStreamSynchronize(s));
+        *out = r;
+        return ASGART_B200_OK;
+    });
+}
+
+int64_t asgart_b200_result_n_families(const asgart_b200_result* r) { return r ? int64_t(r->fam_off.size()) - 1 : 0; }
+int64_t asgart_b200_result_n_sds(const asgart_b200_result* r) { return r ? int64_t(r->sds.size()) : 0; }
+const uint64_t* asgart_b200_result_family_offsets(const asgart_b200_result* r) { return r ? r->fam_off.data() : nullptr; }
+const asgart_b200_protosd* asgart_b200_result_sds(const asgart_b200_result* r) { return r ? r->sds.data() : nullptr; }
+void asgart_b200_result_free(asgart_b200_result* r) { delete r; }
+
+int32_t asgart_b200_ctx_stats(const asgart_b200_ctx* ctx, asgart_b200_stats* out) {
+    if (!ctx || !out) return ASGART_B200_EINVAL;
+    asgart_b200_ctx* c = const_cast<asgart_b200_ctx*>(ctx);
+    try {
+        CUDA_CHECK(cudaSetDevice(c->device));
+        fold_family_timers(c);
+    } catch (const CudaError& e) {
+        c->err = e.what();
+        return e.code;
+    }
+    *out = c->st;
+    return ASGART_B200_OK;
+}
+
+void asgart_b200_ctx_reset_stats(asgart_b200_ctx* ctx) {
+    if (!ctx) return;
+    try {
+        cudaSetDevice(ctx->device);
+        ctx->t_sort.reset(); ctx->t_gather.reset(); ctx->t_rank.reset(); ctx->t_probe.reset(); ctx->t_emit.reset();
+    } catch (...) {}
+    ctx->launches.total = 0;
+    ctx->st = asgart_b200_stats{};
+}
+
+// ---- divsufsort64 drop-in -----------------------------------------------------------------------------
+int32_t asgart_b200_divsufsort64_ex(const uint8_t* T, int64_t* SA, int64_t n, int32_t device, int32_t index_bits) {
+    if (!T || !SA || n < 0) return ASGART_B200_EINVAL;  // divsufsort.c:337
+    if (n == 0) return ASGART_B200_OK;
+    if (n == 1) { SA[0] = 0; return ASGART_B200_OK; }
+    if (asgart_b200_device_count() <= 0) return ASGART_B200_ENODEVICE;
+    cudaStream_t s = nullptr;
+    try {
+        CUDA_CHECK(cudaSetDevice(device));
+        CUDA_CHECK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+        int bits = index_bits ? index_bits : (u64(n) < 0xFFFFFFFEull ? 32 : 64);
+        {
+            DevBuf<u8> d_text(u64(n), s);
+            CUDA_CHECK(cudaMemcpyAsync(d_text.p, T, size_t(n), cudaMemcpyHostToDevice, s));
+            if (bits == 32) {
+                if (u64(n) >= 0xFFFFFFFEull) { cudaStreamDestroy(s); return ASGART_B200_EINVAL; }
+                DevBuf<u32> sa(u64(n), s), rank(u64(n), s);
+                build_suffix_array<u32>(d_text.p, u64(n), sa.p, rank.p, s, nullptr);
+                rank.release();
+                download_as_i64<u32>(sa.p, SA, u64(n), s);
+            } else {
+                DevBuf<u64> sa(u64(n), s), rank(u64(n), s);
+                build_suffix_array<u64>(d_text.p, u64(n), sa.p, rank.p, s, nullptr);
+                rank.release();
+                download_as_i64<u64>(sa.p, SA, u64(n), s);
+            }
+        }
+        CUDA_CHECK(cudaStreamSynchronize(s));
+        cudaStreamDestroy(s);
+        return ASGART_B200_OK;
+    } catch (const CudaError& e) {
+        fprintf(stderr, "asgart_b200_divsufsort64: %s\n", e.what());
+        cudaGetLastError();
+        if (s) cudaStreamDestroy(s);
+        return e.code;
+    } catch (const std::bad_alloc&) {
+        if (s) cudaStreamDestroy(s);
+        return ASGART_B200_ENOMEM;
+    }
+}
+
+int32_t asgart_b200_divsufsort64(const uint8_t* T, int64_t* SA, int64_t n) {
+    int dev = 0;
+    if (asgart_b200_device_count() > 0 && cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); dev = 0; }
+    return asgart_b200_divsufsort64_ex(T, SA, n, dev, 0);
+}
+
+}  // extern "C"

@@ -1,0 +1,153 @@
+// common.cuh — error handling, stream-ordered device buffers, small device helpers (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <stdexcept>
+#include <string>
+
+#include "../../include/asgart_b200.h"
+
+namespace ab200 {
+
+using u8 = uint8_t;
+using u32 = uint32_t;
+using u64 = uint64_t;
+using i64 = int64_t;
+
+constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs; grids are sized in multiples of this
+
+struct CudaError : std::runtime_error {
+    int code;
+    CudaError(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+inline void cuda_check(cudaError_t e, const char* what, const char* file, int line) {
+    if (e != cudaSuccess) {
+        char buf[512];
+        snprintf(buf, sizeof buf, "%s: %s (%s:%d)", what, cudaGetErrorString(e), file, line);
+        int code = (e == cudaErrorMemoryAllocation) ? ASGART_B200_ENOMEM
+                   : (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) ? ASGART_B200_ENODEVICE
+                                                                                   : ASGART_B200_ECUDA;
+        throw CudaError(code, buf);
+    }
+}
+#define CUDA_CHECK(x) ::ab200::cuda_check((x), #x, __FILE__, __LINE__)
+#define KERNEL_CHECK() ::ab200::cuda_check(cudaGetLastError(), "kernel launch", __FILE__, __LINE__)
+
+// Launch counter (bench.py's gpu_launches claim is read from here)
+struct LaunchCounter {
+    u64 total = 0;
+};
+extern thread_local LaunchCounter* g_launch_counter;
+inline void count_launch(u64 n = 1) {
+    if (g_launch_counter) g_launch_counter->total += n;
+}
+
+// Stream-ordered device buffer (cudaMallocAsync: the pool keeps freed blocks, so repeated steps do not pay cudaMalloc)
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    cudaStream_t s = nullptr;
+    DevBuf() = default;
+    DevBuf(size_t count, cudaStream_t stream) { alloc(count, stream); }
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n), s(o.s) { o.p = nullptr; o.n = 0; }
+    DevBuf& operator=(DevBuf&& o) noexcept {
+        if (this != &o) { release(); p = o.p; n = o.n; s = o.s; o.p = nullptr; o.n = 0; }
+        return *this;
+    }
+    ~DevBuf() { release(); }
+    void alloc(size_t count, cudaStream_t stream) {
+        release();
+        s = stream;
+        n = count;
+        if (count == 0) { p = nullptr; return; }
+        CUDA_CHECK(cudaMallocAsync(reinterpret_cast<void**>(&p), count * sizeof(T), stream));
+    }
+    void release() {
+        if (p) { cudaFreeAsync(p, s); p = nullptr; n = 0; }
+    }
+    void zero() { if (p) CUDA_CHECK(cudaMemsetAsync(p, 0, n * sizeof(T), s)); }
+    size_t bytes() const { return n * sizeof(T); }
+};
+
+inline int ceil_div_i(i64 a, i64 b) { return int((a + b - 1) / b); }
+inline u64 ceil_div(u64 a, u64 b) { return (a + b - 1) / b; }
+inline int bit_width_u64(u64 v) { int b = 0; while (v) { ++b; v >>= 1; } return b; }
+
+// CUDA-event stopwatch on one stream
+struct EventTimer {
+    cudaEvent_t a = nullptr, b = nullptr;
+    cudaStream_t s = nullptr;
+    explicit EventTimer(cudaStream_t stream) : s(stream) {
+        CUDA_CHECK(cudaEventCreate(&a));
+        CUDA_CHECK(cudaEventCreate(&b));
+    }
+    ~EventTimer() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); }
+    void start() { CUDA_CHECK(cudaEventRecord(a, s)); }
+    // records the stop event; ms() synchronises on it
+    void stop() { CUDA_CHECK(cudaEventRecord(b, s)); }
+    double ms() {
+        CUDA_CHECK(cudaEventSynchronize(b));
+        float t = 0;
+        CUDA_CHECK(cudaEventElapsedTime(&t, a, b));
+        return double(t);
+    }
+};
+
+// Accumulating timer for a kernel family launched many times (radix passes, gathers): a ring of event pairs
+// that is drained lazily so the stream is never synchronised inside the hot loop.
+struct FamilyTimer {
+    static constexpr int kRing = 64;
+    cudaEvent_t a[kRing], b[kRing];
+    int used = 0;
+    cudaStream_t s = nullptr;
+    double total_ms = 0;
+    u64 launches = 0, bytes = 0;
+    bool inited = false;
+    void init(cudaStream_t stream) {
+        s = stream;
+        for (int i = 0; i < kRing; ++i) { CUDA_CHECK(cudaEventCreate(&a[i])); CUDA_CHECK(cudaEventCreate(&b[i])); }
+        inited = true;
+    }
+    void destroy() {
+        if (!inited) return;
+        for (int i = 0; i < kRing; ++i) { cudaEventDestroy(a[i]); cudaEventDestroy(b[i]); }
+        inited = false;
+    }
+    void drain() {
+        for (int i = 0; i < used; ++i) {
+            CUDA_CHECK(cudaEventSynchronize(b[i]));
+            float t = 0;
+            CUDA_CHECK(cudaEventElapsedTime(&t, a[i], b[i]));
+            total_ms += t;
+        }
+        used = 0;
+    }
+    void begin() {
+        if (used == kRing) drain();
+        CUDA_CHECK(cudaEventRecord(a[used], s));
+    }
+    void end(u64 n_launches, u64 alg_bytes) {
+        CUDA_CHECK(cudaEventRecord(b[used], s));
+        ++used;
+        launches += n_launches;
+        bytes += alg_bytes;
+    }
+    void reset() { drain(); total_ms = 0; launches = 0; bytes = 0; }
+};
+
+#ifdef __CUDACC__
+__device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }
+__device__ __forceinline__ unsigned lanemask_lt() {
+    unsigned m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+#endif
+
+}  // namespace ab200

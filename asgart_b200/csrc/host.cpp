@@ -1,0 +1,641 @@
+// host.cpp — host side of the path above the C ABI, in C++ because the reference's host is compiled code (Rust) and no
+// Rust toolchain exists in this image. It mirrors, for the duplication-search path only:
+//   prepare_data            src/bin/asgart.rs:273-471   (FASTA -> normalised strand + fragment map + chunks + '$')
+//   ProtoSD -> SD + JSON    src/bin/asgart.rs:770-821, src/structs.rs:36-98,471-493, src/exporters.rs:12-25
+//   output file naming      src/bin/asgart.rs:642-654,695-719, src/utils.rs:30-49
+//   the step pipeline       src/bin/asgart.rs:731-757 (driven through the device operator of api.cu)
+// plus the deterministic synthetic-genome generator used by bench.py and the tests (DESIGN.md "Synthetic inputs").
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <sstream>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/asgart_b200.h"
+
+namespace {
+
+struct Fragment {
+    std::string name;
+    uint64_t position, length;
+};
+
+}  // namespace
+
+struct asgart_b200_prepared {
+    std::string file_names;
+    std::vector<uint8_t> data;  // incl. '$'
+    std::vector<Fragment> map;
+    std::vector<asgart_b200_chunk> chunks;
+};
+
+namespace {
+
+thread_local std::string g_err;
+
+bool is_base(uint8_t c) { return c == 'A' || c == 'T' || c == 'G' || c == 'C' || c == 'N'; }
+bool is_masked_base(uint8_t c) { return c == 'a' || c == 't' || c == 'g' || c == 'c' || c == 'n'; }
+
+// bin/asgart.rs:291-301
+void normalise(uint8_t* seq, size_t n, bool skip_masked) {
+    for (size_t i = 0; i < n; ++i) {
+        uint8_t c = seq[i];
+        if (!skip_masked && c >= 'a' && c <= 'z') c = uint8_t(c - 32);
+        if (skip_masked && is_masked_base(c)) c = 'N';
+        else if (!is_base(c)) c = 'N';
+        seq[i] = c;
+    }
+}
+
+// bin/asgart.rs:317-366 — maximal regions split at N-runs longer than 5000; coordinates relative to the fragment
+void find_chunks(const uint8_t* s, uint64_t len, uint64_t global_off, std::vector<asgart_b200_chunk>& out) {
+    const uint64_t threshold = 5000;
+    const size_t first = out.size();
+    uint64_t start = 0, count = 0, i = 0;
+    while (i < len) {
+        if (s[i] == 'N' || s[i] == 'n') {
+            uint64_t run = 0;
+            while (i + run < len && (s[i + run] == 'N' || s[i + run] == 'n')) ++run;
+            if (run > threshold) {
+                if (count > 0) { out.push_back({global_off + start, count}); count = 0; }
+                start = i + run;
+            } else {
+                count += run;
+            }
+            i += run;
+        } else {
+            if (count == 0) { count = 1; start = i; } else { ++count; }
+            ++i;
+        }
+    }
+    if (count != 0) out.push_back({global_off + start, count});
+    if (out.size() == first) out.push_back({global_off, len});
+}
+
+size_t rtrim_len(const std::string& s) {
+    size_t e = s.size();
+    while (e > 0 && isspace((unsigned char)s[e - 1])) --e;
+    return e;
+}
+
+// bin/asgart.rs:278-313 with the bio FASTA reader's semantics (id = header up to first whitespace; lines trimmed)
+bool read_fasta(const std::string& path, bool skip_masked, uint64_t offset, asgart_b200_prepared* p) {
+    std::ifstream in(path, std::ios::binary);
+    if (!in) { g_err = "Unable to read FASTA file `" + path + "`"; return false; }
+    std::string line, name;
+    bool have = false, any = false;
+    size_t rec_start = p->data.size();
+    auto close_record = [&]() {
+        const size_t len = p->data.size() - rec_start;
+        normalise(p->data.data() + rec_start, len, skip_masked);
+        p->map.push_back(Fragment{name, uint64_t(rec_start), uint64_t(len)});
+        find_chunks(p->data.data() + rec_start, len, rec_start, p->chunks);
+    };
+    (void)offset;
+    while (std::getline(in, line)) {
+        if (!any && line.empty()) continue;
+        if (!line.empty() && line[0] == '>') {
+            if (have) close_record();
+            const size_t e = rtrim_len(line);
+            size_t sp = 1;
+            while (sp < e && !isspace((unsigned char)line[sp])) ++sp;
+            name = line.substr(1, sp - 1);
+            rec_start = p->data.size();
+            have = any = true;
+        } else {
+            if (!have) { g_err = "Unable to parse `" + path + "`"; return false; }
+            const size_t e = rtrim_len(line);
+            p->data.insert(p->data.end(), line.begin(), line.begin() + e);
+        }
+    }
+    if (have) close_record();
+    return true;
+}
+
+std::vector<std::string> split_lines(const char* s) {
+    std::vector<std::string> out;
+    if (!s) return out;
+    std::stringstream ss(s);
+    std::string f;
+    while (std::getline(ss, f, '\n')) if (!f.empty()) out.push_back(f);
+    return out;
+}
+
+// ------------------------------------------------------------------------------------------------ JSON
+void jstr(std::string& o, const std::string& s) {
+    o += '"';
+    for (unsigned char c : s) {
+        switch (c) {
+            case '"': o += "\\\""; break;
+            case '\\': o += "\\\\"; break;
+            case '\n': o += "\\n"; break;
+            case '\r': o += "\\r"; break;
+            case '\t': o += "\\t"; break;
+            case '\b': o += "\\b"; break;
+            case '\f': o += "\\f"; break;
+            default:
+                if (c < 0x20) { char b[8]; snprintf(b, sizeof b, "\\u%04x", c); o += b; }
+                else o += char(c);
+        }
+    }
+    o += '"';
+}
+
+// f32 the way serde_json (ryu) prints it: shortest digits that round-trip, ".0" appended to integral values
+std::string jf32(float v) {
+    if (v == 0.f) return std::signbit(v) ? "-0.0" : "0.0";
+    char b[64];
+    for (int prec = 1; prec <= 9; ++prec) {
+        snprintf(b, sizeof b, "%.*g", prec, double(v));
+        if (strtof(b, nullptr) == v) break;
+    }
+    std::string s(b);
+    if (s.find_first_of(".eni") == std::string::npos) s += ".0";
+    return s;
+}
+
+const Fragment* chr_by_pos(const std::vector<Fragment>& map, uint64_t pos) {  // structs.rs:86-90
+    for (const Fragment& c : map)
+        if (pos >= c.position && pos < c.position + c.length) return &c;
+    return nullptr;
+}
+
+struct Ind {  // serde_json PrettyFormatter: two spaces per level
+    std::string& o;
+    void nl(int level) { o += '\n'; o.append(size_t(level) * 2, ' '); }
+};
+
+// ------------------------------------------------------------------------------------------------ synthetic genomes
+inline uint64_t splitmix64(uint64_t x) {
+    uint64_t z = x + 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+struct Rng {  // splitmix64 stream keyed by (seed, stream id)
+    uint64_t s;
+    Rng(uint64_t seed, uint64_t stream) : s(splitmix64(seed ^ splitmix64(stream * 0xD1B54A32D192ED03ull + 0x8CB92BA72F3D8DD7ull))) {}
+    uint64_t next() { s += 0x9E3779B97F4A7C15ull; uint64_t z = s; z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; return z ^ (z >> 31); }
+    double uniform() { return double(next() >> 11) * (1.0 / 9007199254740992.0); }  // [0,1)
+    uint64_t below(uint64_t n) { return n ? uint64_t(uniform() * double(n)) % n : 0; }
+};
+
+const uint64_t kHg38[24] = {248956422, 242193529, 198295559, 190214555, 181538259, 170805979, 159345973, 145138636,
+                            138394717, 133797422, 135086622, 133275309, 114364328, 107043718, 101991189, 90338345,
+                            83257441,  80373285,  58617616,  64444167,  46709983,  50818468,  156040895, 57227415};
+const char* kHg38Names[24] = {"chr1", "chr2", "chr3", "chr4", "chr5", "chr6", "chr7", "chr8", "chr9", "chr10", "chr11", "chr12",
+                              "chr13", "chr14", "chr15", "chr16", "chr17", "chr18", "chr19", "chr20", "chr21", "chr22", "chrX", "chrY"};
+
+struct Interval { uint64_t b, e; };
+
+struct SynthSpec {
+    uint64_t seed = 1;
+    uint64_t n = 0;
+    std::vector<Fragment> frags;
+    std::vector<Interval> nruns;      // stamped last; planted pairs avoid them
+    uint64_t n_pairs = 0;
+    int rc_percent = 0;               // share of planted pairs that are reverse-complemented
+    int inter_percent = 0;            // share of pairs whose copy lands in another fragment
+    bool softmask = false;            // ~15 % lower-case, applied before planting
+    uint64_t element_copies = 0;      // C3: 300 bp element, <=10 % divergence
+    double scale = 1.0;
+};
+
+uint64_t scaled(uint64_t v, double sc, uint64_t lo) { return std::max<uint64_t>(lo, uint64_t(double(v) * sc)); }
+
+bool make_spec(int config, int part, int64_t scale_n, uint64_t seed, int64_t n_pairs, int rc_percent, SynthSpec& sp) {
+    auto single = [&](const char* name, uint64_t full_n) {
+        sp.n = scale_n > 0 ? uint64_t(scale_n) : full_n;
+        sp.scale = double(sp.n) / double(full_n);
+        sp.frags = {Fragment{name, 0, sp.n}};
+    };
+    switch (config) {
+        case 0:
+            if (scale_n <= 0) return false;
+            sp.seed = seed; sp.n = uint64_t(scale_n); sp.frags = {Fragment{"synth", 0, sp.n}};
+            sp.n_pairs = uint64_t(std::max<int64_t>(0, n_pairs)); sp.rc_percent = rc_percent;
+            return true;
+        case 1:
+            sp.seed = 101; single("synth10m", 10000000ull);
+            sp.n_pairs = scaled(40, sp.scale, 2); sp.rc_percent = 0;
+            return true;
+        case 2: {
+            sp.seed = 202; single("synthY", 57227415ull);
+            sp.n_pairs = scaled(240, sp.scale, 4); sp.rc_percent = 50; sp.softmask = true;
+            const uint64_t tel = scaled(10000, sp.scale, 5001);
+            sp.nruns.push_back({0, tel});
+            sp.nruns.push_back({sp.n - tel, sp.n});
+            const uint64_t big = scaled(3000000, sp.scale, 6000), at = scaled(10000000, sp.scale, tel + 1000);
+            sp.nruns.push_back({at, std::min(sp.n - tel, at + big)});
+            Rng r(sp.seed, 7001);
+            for (int i = 0; i < 20; ++i) {
+                const uint64_t len = 10 + r.below(1991), pos = r.below(sp.n - len);
+                sp.nruns.push_back({pos, pos + len});
+            }
+            return true;
+        }
+        case 3: {
+            sp.seed = 303; single("synth1", 248956422ull);
+            sp.n_pairs = scaled(1000, sp.scale, 4); sp.rc_percent = 50;
+            sp.element_copies = scaled(1500, sp.scale, 600);
+            const uint64_t big = scaled(18000000, sp.scale, 6000), at = scaled(121700000, sp.scale, 1000);
+            sp.nruns.push_back({at, std::min(sp.n, at + big)});
+            Rng r(sp.seed, 7001);
+            for (int i = 0; i < 30; ++i) {
+                const uint64_t len = 10 + r.below(1991), pos = r.below(sp.n - len);
+                sp.nruns.push_back({pos, pos + len});
+            }
+            return true;
+        }
+        case 4: {
+            sp.seed = 404;
+            sp.scale = scale_n > 0 ? double(scale_n) / 3088269832.0 : 1.0;
+            uint64_t pos = 0;
+            for (int f = 0; f < 24; ++f) {
+                const uint64_t len = scaled(kHg38[f], sp.scale, 20000);
+                sp.frags.push_back(Fragment{kHg38Names[f], pos, len});
+                const uint64_t tel = std::min<uint64_t>(len / 8, scaled(10000, sp.scale, 5001));
+                sp.nruns.push_back({pos, pos + tel});
+                sp.nruns.push_back({pos + len - tel, pos + len});
+                const uint64_t cen = std::max<uint64_t>(5001, len / 50), cat = pos + len * 2 / 5;
+                sp.nruns.push_back({cat, cat + cen});
+                pos += len;
+            }
+            sp.n = pos;
+            sp.n_pairs = scaled(8000, sp.scale, 8); sp.rc_percent = 50; sp.inter_percent = 30;
+            return true;
+        }
+        case 5: {
+            sp.seed = part == 0 ? 505 : 506;
+            sp.scale = scale_n > 0 ? double(scale_n) / 1000000000.0 : 1.0;
+            uint64_t pos = 0;
+            for (int f = 0; f < 10; ++f) {
+                const uint64_t len = scaled(100000000ull, sp.scale, 20000);
+                char nm[32];
+                snprintf(nm, sizeof nm, "%c%d", part == 0 ? 'A' : 'B', f + 1);
+                sp.frags.push_back(Fragment{nm, pos, len});
+                pos += len;
+            }
+            sp.n = pos;
+            sp.n_pairs = scaled(500, sp.scale, 2); sp.rc_percent = 50;
+            return true;
+        }
+        default: return false;
+    }
+}
+
+bool hits_nrun(const std::vector<Interval>& nr, uint64_t b, uint64_t e) {
+    for (const Interval& r : nr) if (b < r.e && r.b < e) return true;
+    return false;
+}
+int frag_of(const std::vector<Fragment>& fr, uint64_t pos) {
+    for (size_t f = 0; f < fr.size(); ++f) if (pos >= fr[f].position && pos < fr[f].position + fr[f].length) return int(f);
+    return -1;
+}
+inline uint8_t comp_keep_case(uint8_t c) {
+    switch (c) {
+        case 'A': return 'T'; case 'T': return 'A'; case 'C': return 'G'; case 'G': return 'C';
+        case 'a': return 't'; case 't': return 'a'; case 'c': return 'g'; case 'g': return 'c';
+        default: return c;
+    }
+}
+inline uint8_t other_base(uint8_t c, Rng& r) {
+    const bool lower = c >= 'a';
+    const char* up = "ACGT";
+    uint8_t u = lower ? uint8_t(c - 32) : c;
+    int k = int(r.below(3));
+    for (int i = 0; i < 4; ++i) if (uint8_t(up[i]) != u) { if (k-- == 0) { u = uint8_t(up[i]); break; } }
+    return lower ? uint8_t(u + 32) : u;
+}
+
+// mutated copy of src[0..L): divergence d, events 80 % substitutions / 20 % indels of 1-3 bp, output length fixed at L
+void mutate_copy(const uint8_t* src, uint64_t avail, uint64_t L, double d, Rng& r, std::vector<uint8_t>& out) {
+    out.clear();
+    out.reserve(L);
+    uint64_t cur = 0;
+    while (out.size() < L) {
+        if (cur >= avail) { out.push_back(uint8_t("ACGT"[r.below(4)])); continue; }
+        if (r.uniform() < d) {
+            const double ev = r.uniform();
+            if (ev < 0.8) { out.push_back(other_base(src[cur], r)); ++cur; }
+            else {
+                const uint64_t len = 1 + r.below(3);
+                if (ev < 0.9) { for (uint64_t j = 0; j < len && out.size() < L; ++j) out.push_back(uint8_t("ACGT"[r.below(4)])); }
+                else cur += len;
+            }
+        } else { out.push_back(src[cur]); ++cur; }
+    }
+}
+
+void plant_pairs(std::vector<uint8_t>& g, uint64_t off, const SynthSpec& sp, const uint8_t* donor, uint64_t donor_n, uint64_t n_pairs,
+                 uint64_t stream_base) {
+    // g = this genome (absolute coordinates start at `off` inside it == 0 here), donor = genome the source is cut from
+    (void)off;
+    std::vector<uint8_t> buf;
+    for (uint64_t j = 0; j < n_pairs; ++j) {
+        Rng r(sp.seed, stream_base + j);
+        const double lmin = std::log(2000.0), lmax = std::log(50000.0);
+        uint64_t L = uint64_t(std::exp(lmin + r.uniform() * (lmax - lmin)));
+        L = std::min<uint64_t>(L, std::max<uint64_t>(200, sp.n / 40));
+        const double d = r.uniform() * 0.02;
+        const bool rc = int(r.below(100)) < sp.rc_percent;
+        const bool inter = int(r.below(100)) < sp.inter_percent;
+        for (int attempt = 0; attempt < 200; ++attempt) {
+            const uint64_t src = r.below(donor_n - L), dst = r.below(sp.n - L);
+            const int fd = frag_of(sp.frags, dst);
+            if (fd < 0 || dst + L > sp.frags[fd].position + sp.frags[fd].length) continue;
+            if (hits_nrun(sp.nruns, dst, dst + L)) continue;
+            if (donor == g.data()) {
+                const int fs = frag_of(sp.frags, src);
+                if (fs < 0 || src + L > sp.frags[fs].position + sp.frags[fs].length) continue;
+                if (hits_nrun(sp.nruns, src, src + L)) continue;
+                if (src < dst + L && dst < src + L) continue;
+                if (sp.frags.size() > 1 && (inter ? fs == fd : fs != fd)) continue;
+            }
+            mutate_copy(donor + src, donor_n - src, L, d, r, buf);
+            if (rc) {
+                std::reverse(buf.begin(), buf.end());
+                for (auto& c : buf) c = comp_keep_case(c);
+            }
+            memcpy(g.data() + dst, buf.data(), L);
+            break;
+        }
+    }
+}
+
+void generate(const SynthSpec& sp, std::vector<uint8_t>& g, int threads, const std::vector<uint8_t>* donor_a, uint64_t shared_segments) {
+    g.resize(sp.n);
+    const uint64_t key = sp.seed * 0x9E3779B97F4A7C15ull;
+    const int nt = std::max(1, threads);
+    std::vector<std::thread> pool;
+    auto fill = [&](uint64_t b, uint64_t e) {
+        for (uint64_t i = b; i < e; ++i) g[i] = uint8_t("ACGT"[splitmix64(key + i) >> 62]);
+    };
+    const uint64_t per = (sp.n + nt - 1) / nt;
+    for (int t = 0; t < nt; ++t) {
+        const uint64_t b = std::min(sp.n, t * per), e = std::min(sp.n, b + per);
+        if (b < e) pool.emplace_back(fill, b, e);
+    }
+    for (auto& th : pool) th.join();
+    if (sp.softmask) {  // ~15 % lower-case in intervals of mean 300 bp (mean gap 1700 bp)
+        Rng r(sp.seed, 9001);
+        uint64_t pos = 0;
+        for (;;) {
+            pos += uint64_t(-std::log(1.0 - r.uniform()) * 1700.0) + 1;
+            const uint64_t len = uint64_t(-std::log(1.0 - r.uniform()) * 300.0) + 1;
+            if (pos >= sp.n) break;
+            const uint64_t e = std::min(sp.n, pos + len);
+            for (uint64_t i = pos; i < e; ++i) g[i] = uint8_t(g[i] + 32);
+            pos = e;
+        }
+    }
+    plant_pairs(g, 0, sp, g.data(), sp.n, sp.n_pairs, 100000);
+    if (donor_a) plant_pairs(g, 0, sp, donor_a->data(), donor_a->size(), shared_segments, 500000);
+    if (sp.element_copies) {
+        Rng re(sp.seed, 8001);
+        uint8_t elem[300];
+        for (auto& c : elem) c = uint8_t("ACGT"[re.below(4)]);
+        for (uint64_t c = 0; c < sp.element_copies; ++c) {
+            Rng r(sp.seed, 800000 + c);
+            const double d = r.uniform() * 0.10;
+            for (int attempt = 0; attempt < 100; ++attempt) {
+                const uint64_t pos = r.below(sp.n - 300);
+                if (hits_nrun(sp.nruns, pos, pos + 300)) continue;
+                for (int i = 0; i < 300; ++i) g[pos + i] = (r.uniform() < d) ? other_base(elem[i], r) : elem[i];
+                break;
+            }
+        }
+    }
+    for (const Interval& r : sp.nruns)
+        for (uint64_t i = r.b; i < r.e && i < sp.n; ++i) g[i] = 'N';
+}
+
+}  // namespace
+
+// ================================================================================================ C ABI
+extern "C" {
+
+asgart_b200_prepared* asgart_b200_prepare_files(const char* files, int32_t skip_masked, const char** err) {
+    if (err) *err = nullptr;
+    auto* p = new asgart_b200_prepared();
+    const std::vector<std::string> fl = split_lines(files);
+    for (size_t i = 0; i < fl.size(); ++i) {
+        if (!read_fasta(fl[i], skip_masked != 0, 0, p)) {
+            delete p;
+            if (err) *err = g_err.c_str();
+            return nullptr;
+        }
+        p->file_names += (i ? ", " : "") + fl[i];  // bin/asgart.rs:466
+    }
+    p->data.push_back('$');  // bin/asgart.rs:430
+    return p;
+}
+
+asgart_b200_prepared* asgart_b200_prepare_memory(const char* file_names, const uint8_t* strand, int64_t n, const char* fragment_names,
+                                                 const uint64_t* frag_pos, const uint64_t* frag_len, int64_t n_fragments) {
+    if (!strand || n < 0 || !frag_pos || !frag_len) return nullptr;
+    auto* p = new asgart_b200_prepared();
+    p->file_names = file_names ? file_names : "";
+    p->data.assign(strand, strand + n);
+    const std::vector<std::string> names = split_lines(fragment_names);
+    for (int64_t i = 0; i < n_fragments; ++i) {
+        if (frag_pos[i] + frag_len[i] > uint64_t(n)) { delete p; return nullptr; }
+        p->map.push_back(Fragment{size_t(i) < names.size() ? names[i] : std::string("fragment") + std::to_string(i), frag_pos[i], frag_len[i]});
+        find_chunks(p->data.data() + frag_pos[i], frag_len[i], frag_pos[i], p->chunks);
+    }
+    p->data.push_back('$');
+    return p;
+}
+
+const uint8_t* asgart_b200_prepared_strand(const asgart_b200_prepared* p, int64_t* n_plus_1) {
+    if (n_plus_1) *n_plus_1 = int64_t(p->data.size());
+    return p->data.data();
+}
+const asgart_b200_chunk* asgart_b200_prepared_chunks(const asgart_b200_prepared* p, int64_t* n_chunks) {
+    if (n_chunks) *n_chunks = int64_t(p->chunks.size());
+    return p->chunks.data();
+}
+int64_t asgart_b200_prepared_n_fragments(const asgart_b200_prepared* p) { return int64_t(p->map.size()); }
+const char* asgart_b200_prepared_fragment(const asgart_b200_prepared* p, int64_t i, uint64_t* position, uint64_t* length) {
+    if (position) *position = p->map[i].position;
+    if (length) *length = p->map[i].length;
+    return p->map[i].name.c_str();
+}
+void asgart_b200_prepared_free(asgart_b200_prepared* p) { delete p; }
+
+char* asgart_b200_to_json(const asgart_b200_prepared* p, const asgart_b200_settings* st, const uint64_t* fam_off, int64_t n_fam,
+                          const asgart_b200_protosd* sds) {
+    std::string o;
+    o.reserve(4096 + size_t(n_fam ? fam_off[n_fam] : 0) * 420);
+    Ind in{o};
+    auto key = [&](int level, const char* k) { in.nl(level); o += '"'; o += k; o += "\": "; };
+    auto num = [&](uint64_t v) { o += std::to_string(v); };
+    uint64_t total = 0;
+    for (const Fragment& f : p->map) total += f.length;  // bin/asgart.rs:772
+    o += '{';
+    key(1, "strand"); o += '{';
+    key(2, "name"); jstr(o, p->file_names); o += ',';
+    key(2, "length"); num(total); o += ',';
+    key(2, "map"); o += '[';
+    for (size_t i = 0; i < p->map.size(); ++i) {
+        if (i) o += ',';
+        in.nl(3); o += '{';
+        key(4, "name"); jstr(o, p->map[i].name); o += ',';
+        key(4, "position"); num(p->map[i].position); o += ',';
+        key(4, "length"); num(p->map[i].length);
+        in.nl(3); o += '}';
+    }
+    if (!p->map.empty()) in.nl(2);
+    o += ']';
+    in.nl(1); o += "},";
+    key(1, "settings"); o += '{';
+    key(2, "probe_size"); num(st->probe_size); o += ',';
+    key(2, "max_gap_size"); num(st->max_gap_size); o += ',';
+    key(2, "min_duplication_length"); num(st->min_duplication_length); o += ',';
+    key(2, "max_cardinality"); num(st->max_cardinality); o += ',';
+    key(2, "trim");
+    if (st->has_trim) { o += '['; in.nl(3); num(st->trim_a); o += ','; in.nl(3); num(st->trim_b); in.nl(2); o += ']'; }
+    else o += "null";
+    o += ',';
+    key(2, "skip_masked"); o += st->skip_masked ? "true" : "false";
+    in.nl(1); o += "},";
+    key(1, "families"); o += '[';
+    for (int64_t f = 0; f < n_fam; ++f) {
+        if (f) o += ',';
+        in.nl(2); o += '[';
+        for (uint64_t j = fam_off[f]; j < fam_off[f + 1]; ++j) {
+            const asgart_b200_protosd& sd = sds[j];
+            const Fragment* cl = chr_by_pos(p->map, sd.left);    // bin/asgart.rs:785-806
+            const Fragment* cr = chr_by_pos(p->map, sd.right);
+            if (j > fam_off[f]) o += ',';
+            in.nl(3); o += '{';
+            key(4, "chr_left"); jstr(o, cl ? cl->name : "unknown"); o += ',';
+            key(4, "chr_right"); jstr(o, cr ? cr->name : "unknown"); o += ',';
+            key(4, "global_left_position"); num(sd.left); o += ',';
+            key(4, "global_right_position"); num(sd.right); o += ',';
+            key(4, "chr_left_position"); num(sd.left - (cl ? cl->position : 0)); o += ',';
+            key(4, "chr_right_position"); num(sd.right - (cr ? cr->position : 0)); o += ',';
+            key(4, "left_length"); num(sd.left_length); o += ',';
+            key(4, "right_length"); num(sd.right_length); o += ',';
+            key(4, "left_seq"); o += "null,";
+            key(4, "right_seq"); o += "null,";
+            key(4, "identity"); o += jf32(sd.identity); o += ',';
+            key(4, "reversed"); o += sd.reversed ? "true" : "false"; o += ',';
+            key(4, "complemented"); o += sd.complemented ? "true" : "false";
+            in.nl(3); o += '}';
+        }
+        if (fam_off[f + 1] > fam_off[f]) in.nl(2);
+        o += ']';
+    }
+    if (n_fam > 0) in.nl(1);
+    o += ']';
+    in.nl(0); o += "}\n";  // exporters.rs:15-17: writeln!
+    char* out = static_cast<char*>(malloc(o.size() + 1));
+    if (out) memcpy(out, o.c_str(), o.size() + 1);
+    return out;
+}
+
+void asgart_b200_free_string(char* s) { free(s); }
+
+// bin/asgart.rs:642-654 (radix = file stems joined by '-'), :695-719, utils.rs:30-49 (extension forced to json)
+char* asgart_b200_out_filename(const char* files, const char* prefix, const char* out, const asgart_b200_settings* st) {
+    std::string name;
+    if (out && *out) {
+        name = out;
+    } else {
+        std::string radix;
+        const std::vector<std::string> fl = split_lines(files);
+        for (size_t i = 0; i < fl.size(); ++i) {
+            std::string base = fl[i];
+            const size_t slash = base.find_last_of('/');
+            if (slash != std::string::npos) base = base.substr(slash + 1);
+            const size_t dot = base.find_last_of('.');
+            if (dot != std::string::npos && dot != 0) base = base.substr(0, dot);  // Path::file_stem
+            radix += (i ? "-" : "") + base;
+        }
+        name = std::string(prefix ? prefix : "") + radix + ((st->reverse || st->complement) ? "_" : "") + (st->reverse ? "R" : "") +
+               (st->complement ? "C" : "");
+        if (st->has_trim) name += "_" + std::to_string(st->trim_a) + "-" + std::to_string(st->trim_b);
+        name += ".json";
+    }
+    // PathBuf::set_extension("json") on the file name component
+    const size_t slash = name.find_last_of('/');
+    const size_t start = slash == std::string::npos ? 0 : slash + 1;
+    const size_t dot = name.find_last_of('.');
+    if (dot != std::string::npos && dot > start) name = name.substr(0, dot);
+    name += ".json";
+    char* r = static_cast<char*>(malloc(name.size() + 1));
+    if (r) memcpy(r, name.c_str(), name.size() + 1);
+    return r;
+}
+
+// bin/asgart.rs:731-822: prepare_data -> SearchDuplications -> FilterNs -> ReOrder -> ReduceOverlap -> Sort -> JSON
+char* asgart_b200_run_files(const char* files, const asgart_b200_settings* st, int32_t device, const char** err) {
+    static thread_local std::string msg;
+    if (err) *err = nullptr;
+    auto failf = [&](const std::string& m) -> char* { msg = m; if (err) *err = msg.c_str(); return nullptr; };
+    const char* perr = nullptr;
+    asgart_b200_prepared* p = asgart_b200_prepare_files(files, int32_t(st->skip_masked), &perr);
+    if (!p) return failf(perr ? perr : "prepare_data failed");
+    asgart_b200_ctx* ctx = nullptr;
+    int rc = asgart_b200_ctx_create(device, &ctx);
+    if (rc) { asgart_b200_prepared_free(p); return failf("no usable CUDA device (code " + std::to_string(rc) + "); this build has no CPU path"); }
+    asgart_b200_result* res = nullptr;
+    char* js = nullptr;
+    rc = asgart_b200_ctx_load_strand(ctx, p->data.data(), int64_t(p->data.size()));
+    if (!rc) rc = asgart_b200_ctx_build_index(ctx);
+    if (!rc) rc = asgart_b200_ctx_search(ctx, p->chunks.data(), int64_t(p->chunks.size()), st, ASGART_B200_POST_ALL, &res);
+    if (rc) failf(std::string("device pipeline failed: ") + asgart_b200_ctx_last_error(ctx));
+    else js = asgart_b200_to_json(p, st, asgart_b200_result_family_offsets(res), asgart_b200_result_n_families(res), asgart_b200_result_sds(res));
+    asgart_b200_result_free(res);
+    asgart_b200_ctx_destroy(ctx);
+    asgart_b200_prepared_free(p);
+    return js;
+}
+
+// ---- synthetic genomes ---------------------------------------------------------------------------------
+int64_t asgart_b200_synth_length(int32_t config, int32_t part, int64_t scale_n) {
+    SynthSpec sp;
+    if (!make_spec(config, part, scale_n, 1, 0, 0, sp)) return -1;
+    return int64_t(sp.n);
+}
+
+int64_t asgart_b200_synth_fragments(int32_t config, int32_t part, int64_t scale_n, char* names_buf, int64_t names_cap, uint64_t* pos,
+                                    uint64_t* len, int64_t cap) {
+    SynthSpec sp;
+    if (!make_spec(config, part, scale_n, 1, 0, 0, sp)) return -1;
+    std::string names;
+    for (size_t i = 0; i < sp.frags.size(); ++i) {
+        names += (i ? "\n" : "") + sp.frags[i].name;
+        if (int64_t(i) < cap) { if (pos) pos[i] = sp.frags[i].position; if (len) len[i] = sp.frags[i].length; }
+    }
+    if (names_buf && names_cap > 0) { strncpy(names_buf, names.c_str(), size_t(names_cap - 1)); names_buf[names_cap - 1] = 0; }
+    return int64_t(sp.frags.size());
+}
+
+int64_t asgart_b200_synth_fill(int32_t config, int32_t part, int64_t scale_n, uint64_t seed, int64_t n_pairs, int32_t rc_percent,
+                               uint8_t* out, int64_t cap, int32_t threads) {
+    SynthSpec sp;
+    if (!make_spec(config, part, scale_n, seed, n_pairs, rc_percent, sp)) return -1;
+    if (!out || cap < int64_t(sp.n)) return -1;
+    std::vector<uint8_t> g;
+    if (config == 5 && part == 1) {
+        SynthSpec sa;
+        make_spec(5, 0, scale_n, seed, n_pairs, rc_percent, sa);
+        std::vector<uint8_t> a;
+        generate(sa, a, threads, nullptr, 0);
+        generate(sp, g, threads, &a, scaled(3000, sp.scale, 4));
+    } else {
+        generate(sp, g, threads, nullptr, 0);
+    }
+    memcpy(out, g.data(), sp.n);
+    return int64_t(sp.n);
+}
+
+}  // extern "C"

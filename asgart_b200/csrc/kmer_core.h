@@ -1,0 +1,147 @@
+// kmer_core.h — packed-text arithmetic shared by the CUDA kernels (and compiled for the host by tests/emul/ only,
+// to unit-test the logic where no GPU exists; the product never runs it on the CPU).
+//
+// Packed text: 4-bit order-preserving codes, 16 per u64 word, first symbol in the most significant nibble, so that
+// the lexicographic order of k-mers under the reference's byte order  $ < A < C < G < N < T  (ASCII; what
+// `dna[x..x+k].cmp(pattern)` sees, src/searcher.rs:147-151,168) is the unsigned order of the packed words.
+// A pure 2-bit packing cannot express this 6-symbol alphabet (N sorts between G and T and is a real symbol: with -S
+// every soft-masked base is N, src/bin/asgart.rs:294-300).
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define AB_HD __host__ __device__ __forceinline__
+#else
+#define AB_HD inline
+#endif
+
+namespace ab200 {
+
+enum : uint32_t { CODE_PAD = 0, CODE_END = 1, CODE_A = 2, CODE_C = 3, CODE_G = 4, CODE_N = 5, CODE_T = 6, CODE_BAD = 15 };
+
+AB_HD uint32_t code_of_byte(uint8_t c) {
+    switch (c) {
+        case '$': return CODE_END;
+        case 'A': return CODE_A;
+        case 'C': return CODE_C;
+        case 'G': return CODE_G;
+        case 'N': return CODE_N;
+        case 'T': return CODE_T;
+        default: return CODE_BAD;
+    }
+}
+// complement on codes (src/utils.rs:1-18): A<->T, C<->G, N->N
+AB_HD uint32_t complement_code(uint32_t c) {
+    switch (c) {
+        case CODE_A: return CODE_T;
+        case CODE_T: return CODE_A;
+        case CODE_C: return CODE_G;
+        case CODE_G: return CODE_C;
+        default: return c;
+    }
+}
+
+struct Win {
+    uint64_t hi, lo;  // 32 symbols, first symbol in the top nibble of hi
+};
+
+// 32 symbols starting at `pos` (the packed array is padded with >= 3 zero words)
+AB_HD Win load_window(const uint64_t* __restrict__ P, uint64_t pos) {
+    const uint64_t w = pos >> 4;
+    const unsigned o = unsigned(pos & 15u) * 4u;
+    const uint64_t a = P[w], b = P[w + 1];
+    Win r;
+    if (o == 0) { r.hi = a; r.lo = b; }
+    else {
+        const uint64_t c = P[w + 2];
+        r.hi = (a << o) | (b >> (64u - o));
+        r.lo = (b << o) | (c >> (64u - o));
+    }
+    return r;
+}
+// keep the first k symbols (1 <= k <= 32)
+AB_HD Win mask_window(Win w, int k) {
+    if (k <= 16) { w.hi &= (k == 16) ? ~uint64_t(0) : ~(~uint64_t(0) >> (4 * k)); w.lo = 0; }
+    else if (k < 32) { w.lo &= ~(~uint64_t(0) >> (4 * (k - 16))); }
+    return w;
+}
+AB_HD int cmp_window(const Win& a, const Win& b) {
+    if (a.hi != b.hi) return a.hi < b.hi ? -1 : 1;
+    if (a.lo != b.lo) return a.lo < b.lo ? -1 : 1;
+    return 0;
+}
+
+// text k-mer at x (packed PT) against needle k-mer at q (packed PN); pw0 = the needle's first window, already masked
+AB_HD int cmp_kmer(const uint64_t* __restrict__ PT, uint64_t x, const uint64_t* __restrict__ PN, uint64_t q, int k, const Win& pw0) {
+    const int k0 = k < 32 ? k : 32;
+    int c = cmp_window(mask_window(load_window(PT, x), k0), pw0);
+    if (c != 0 || k <= 32) return c;
+    for (int off = 32; off < k; off += 32) {
+        const int kk = (k - off) < 32 ? (k - off) : 32;
+        c = cmp_window(mask_window(load_window(PT, x + off), kk), mask_window(load_window(PN, q + off), kk));
+        if (c != 0) return c;
+    }
+    return 0;
+}
+
+// 8-mer LUT slot: the first 8 symbols read as a base-5 number, digits A=0,C=1,G=2,N=3,T=4 (lexicographic, so slots are
+// in SA order). Returns false when any of the 8 symbols is '$' or padding (such suffixes are in no bucket, like the
+// reference's 5^8 enumeration, src/searcher.rs:99-117).
+constexpr uint32_t kLutSize = 390625;  // 5^8
+AB_HD bool lut_slot(uint64_t win_hi, uint32_t& slot) {
+    uint32_t s = 0;
+    bool ok = true;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const uint32_t nib = uint32_t(win_hi >> (60 - 4 * j)) & 15u;
+        ok = ok && (nib >= CODE_A && nib <= CODE_T);
+        s = s * 5u + (nib - CODE_A);
+    }
+    slot = s;
+    return ok;
+}
+
+// superslice::Ext::equal_range_by restated (third-party crate "1.0", call site src/searcher.rs:164): lower and upper
+// bound in lock step over `len` slots, `size -= half`, one final probe each. f(ix) -> -1/0/+1.
+// Kept literal because the reference's comparator is non-monotone near the end of the strand (quirk Q6,
+// src/searcher.rs:165-166), where the result depends on the exact probe sequence.
+template <typename F>
+AB_HD void equal_range_lockstep(uint64_t len, F f, uint64_t& r0, uint64_t& r1) {
+    if (len == 0) { r0 = r1 = 0; return; }
+    uint64_t size = len, b0 = 0, b1 = 0;
+    while (size > 1) {
+        const uint64_t half = size >> 1;
+        const uint64_t m0 = b0 + half, m1 = b1 + half;
+        const int c0 = f(m0);
+        const int c1 = (m1 == m0) ? c0 : f(m1);
+        if (c0 < 0) b0 = m0;
+        if (c1 <= 0) b1 = m1;
+        size -= half;
+    }
+    const int c0 = f(b0);
+    const int c1 = (b1 == b0) ? c0 : f(b1);
+    r0 = b0 + (c0 < 0 ? 1u : 0u);
+    r1 = b1 + (c1 <= 0 ? 1u : 0u);
+}
+
+// the two match filters of src/automaton.rs:106-113 (i is needle-local: quirk Q1)
+AB_HD bool match_survives(uint64_t m_start, uint64_t i, uint64_t c0, uint64_t len, bool reverse) {
+    if (m_start == i) return false;
+    return reverse ? (m_start >= c0 + len - i) : (m_start > i + c0);
+}
+
+// number of loop iterations of src/automaton.rs:96-98 for a chunk of length len (0 when the reference returns early,
+// :92-94, or when len < k + s, where the reference's usize subtraction would underflow)
+AB_HD uint64_t probes_in_chunk(uint64_t len, uint64_t k, uint64_t s, uint64_t min_len) {
+    if (len < min_len || len < k + s || s == 0) return 0;
+    const uint64_t limit = len - k - s;
+    return (limit + s - 1) / s;
+}
+
+AB_HD uint32_t ceil_log2_u64(uint64_t v) {  // ceil(log2(v)), v >= 1
+    uint32_t l = 0;
+    while ((uint64_t(1) << l) < v && l < 63) ++l;
+    return l;
+}
+
+}  // namespace ab200

@@ -1,0 +1,214 @@
+/* asgart_b200.h — C ABI of the B200-native duplication-search hot path.
+ *
+ * This is the drop-in boundary for delehef/asgart (reference @ 523b07c; citations relative to its root).
+ * The reference has exactly one native boundary today, `src/divsufsort.rs:8-33` (extern "C" over the
+ * libdivsufsort static library that build.rs:4-16 builds); this header is what a `build.rs` + `extern "C"`
+ * block would bind instead. Plain pointers and sizes only; all buffers passed in are caller-owned and are
+ * not retained after the call returns; results are library-owned and freed with asgart_b200_result_free.
+ *
+ * Two levels:
+ *   (1) asgart_b200_divsufsort64 — literal replacement for `divsufsort64` (src/divsufsort.rs:10, called from
+ *       r_divsufsort, src/bin/asgart.rs:473-479).
+ *   (2) a handle-based operator that replaces the *body* of SearchDuplications::run
+ *       (src/bin/asgart.rs:137-258: SA build :149, Searcher::new :151, chunk fan-out :201-240, flatten :241-253)
+ *       and, optionally, the FilterNs / ReOrder / ReduceOverlap / Sort steps (:33-96, :481-562). Per-probe FFI
+ *       (Searcher::search, src/searcher.rs:145) is deliberately NOT exposed: the probe loop lives on the GPU.
+ *
+ * There is no CPU fallback: every compute entry point returns ASGART_B200_ENODEVICE when no CUDA device is usable.
+ * A context is not thread-safe (one caller thread at a time); kernels run on a library-owned stream.
+ */
+#ifndef ASGART_B200_H
+#define ASGART_B200_H 1
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ASGART_B200_API __attribute__((visibility("default")))
+
+/* ---- status codes: 0 / -1 / -2 keep divsufsort64's meaning (libdivsufsort/lib/divsufsort.c:337-357) ---- */
+#define ASGART_B200_OK          0
+#define ASGART_B200_EINVAL     (-1)  /* bad arguments (NULL, negative size, strand not normalised, k out of range) */
+#define ASGART_B200_ENOMEM     (-2)  /* host or device allocation failed */
+#define ASGART_B200_ECUDA      (-3)  /* CUDA runtime error; see asgart_b200_ctx_last_error */
+#define ASGART_B200_ESTATE     (-4)  /* call order violated (e.g. search before build_index) */
+#define ASGART_B200_ENODEVICE  (-5)  /* no usable CUDA device: the product has no CPU path */
+
+/* ---- (1) drop-in for divsufsort64 (src/divsufsort.rs:10) ------------------------------------------------
+ * T[0..n) any bytes, SA[0..n) output, both host memory. Suffix array built on the current CUDA device by
+ * prefix doubling (hand-written radix sort + rank update); bit-identical to divsufsort64's output because the
+ * suffix array of a text is unique. */
+ASGART_B200_API int32_t asgart_b200_divsufsort64(const uint8_t *T, int64_t *SA, int64_t n);
+/* same, on an explicit device and with the index width forced (0 = auto, 32 or 64) — for tests */
+ASGART_B200_API int32_t asgart_b200_divsufsort64_ex(const uint8_t *T, int64_t *SA, int64_t n, int32_t device,
+                                                    int32_t index_bits);
+/* replaces divsufsort64_version (src/divsufsort.rs:11) */
+ASGART_B200_API const char *asgart_b200_version(void);
+
+/* ---- (2) the search operator ---------------------------------------------------------------------------- */
+typedef struct asgart_b200_ctx asgart_b200_ctx;
+typedef struct asgart_b200_result asgart_b200_result;
+typedef struct asgart_b200_partial asgart_b200_partial;
+
+/* mirror of RunSettings (src/structs.rs:36-58). max_gap_size is ALREADY gap_size + probe_size
+ * (src/bin/asgart.rs:681). threads_count / compute_score have no meaning here. trim is carried for the JSON
+ * settings block only (--trim is out of scope). */
+typedef struct asgart_b200_settings {
+    uint64_t probe_size;
+    uint32_t max_gap_size;
+    uint32_t reverse;
+    uint32_t complement;
+    uint32_t skip_masked;
+    uint64_t min_duplication_length;
+    uint64_t max_cardinality;
+    uint32_t has_trim;
+    uint64_t trim_a, trim_b;
+} asgart_b200_settings;
+
+/* one entry of chunks_to_process (src/bin/asgart.rs:115, :317-366): global start, length */
+typedef struct asgart_b200_chunk {
+    uint64_t start;
+    uint64_t length;
+} asgart_b200_chunk;
+
+/* mirror of ProtoSD (src/structs.rs:418-429) */
+typedef struct asgart_b200_protosd {
+    uint64_t left;
+    uint64_t right;
+    uint64_t left_length;
+    uint64_t right_length;
+    float identity;
+    uint8_t reversed;
+    uint8_t complemented;
+    uint8_t _pad[2];
+} asgart_b200_protosd;
+
+/* post-step selection for asgart_b200_ctx_search (applied in the reference's order, src/bin/asgart.rs:738-747) */
+#define ASGART_B200_POST_FILTER_NS       1u  /* FilterNs      src/bin/asgart.rs:81-96, src/structs.rs:454-467 */
+#define ASGART_B200_POST_REORDER         2u  /* ReOrder       src/bin/asgart.rs:33-51 */
+#define ASGART_B200_POST_REDUCE_OVERLAP  4u  /* ReduceOverlap src/bin/asgart.rs:67-79, :481-562 */
+#define ASGART_B200_POST_SORT            8u  /* Sort          src/bin/asgart.rs:53-65 */
+#define ASGART_B200_POST_ALL            15u
+
+/* lifetime */
+ASGART_B200_API int32_t asgart_b200_device_count(void);
+ASGART_B200_API int32_t asgart_b200_ctx_create(int32_t device, asgart_b200_ctx **out);
+ASGART_B200_API void asgart_b200_ctx_destroy(asgart_b200_ctx *ctx);
+ASGART_B200_API const char *asgart_b200_ctx_last_error(const asgart_b200_ctx *ctx);
+
+/* Strand = what prepare_data produces (src/bin/asgart.rs:273-471): bytes in {A,C,G,N,T} followed by one '$'
+ * (n_plus_1 bytes, host memory; pinned memory makes the copy asynchronous). Copies to the device and packs it. */
+ASGART_B200_API int32_t asgart_b200_ctx_load_strand(asgart_b200_ctx *ctx, const uint8_t *T, int64_t n_plus_1);
+/* Suffix array (replaces r_divsufsort, :149) + 8-mer LUT (replaces Searcher::new, :151; src/searcher.rs:99-143) */
+ASGART_B200_API int32_t asgart_b200_ctx_build_index(asgart_b200_ctx *ctx);
+/* force the suffix-index width of the next build_index / upload_sa: 0 = auto (32 bits when n+1 < 2^32-1), 32, 64 */
+ASGART_B200_API int32_t asgart_b200_ctx_set_index_bits(asgart_b200_ctx *ctx, int32_t bits);
+/* test hooks: use a suffix array built elsewhere (still builds the LUT on the device) / read the index back */
+ASGART_B200_API int32_t asgart_b200_ctx_upload_sa(asgart_b200_ctx *ctx, const int64_t *SA);
+ASGART_B200_API int32_t asgart_b200_ctx_download_sa(asgart_b200_ctx *ctx, int64_t *SA);
+/* LUT as 5^8 (lo, hi) pairs indexed by the 8-mer read as a base-5 number with digits A=0,C=1,G=2,N=3,T=4 (first
+ * letter most significant). Empty buckets have lo == hi (value unspecified). */
+#define ASGART_B200_LUT_SIZE 390625
+ASGART_B200_API int32_t asgart_b200_ctx_download_lut(asgart_b200_ctx *ctx, int64_t *lo, int64_t *hi);
+
+/* SearchDuplications::run body + selected post-steps. Families come back in the reference's order:
+ * chunk order, then flush order, then arm-creation order (src/bin/asgart.rs:241-253, src/automaton.rs:182-200). */
+ASGART_B200_API int32_t asgart_b200_ctx_search(asgart_b200_ctx *ctx, const asgart_b200_chunk *chunks, int64_t n_chunks,
+                                               const asgart_b200_settings *settings, uint32_t post_mask,
+                                               asgart_b200_result **out);
+/* Searcher::search for a batch of probes taken from the strand itself — test hook for the probe kernel:
+ * probe p is the probe_size-mer the reference would cut at needle index i = (p+1)*(probe_size/2) of chunk 0 under
+ * `settings` (src/automaton.rs:96-104). Writes the equal range [lo, hi) in the SA for each (unfiltered). */
+ASGART_B200_API int32_t asgart_b200_ctx_probe_ranges(asgart_b200_ctx *ctx, const asgart_b200_chunk *chunk,
+                                                     const asgart_b200_settings *settings, int64_t *lo, int64_t *hi,
+                                                     int64_t n_probes);
+
+/* Multi-GPU (one process per GPU; strand + index replicated; probes partitioned by position):
+ *   every rank: ctx_search_shard(rank, world) -> partial; exchange the serialised partials (NCCL all-gather);
+ *   any rank:   ctx_finish(partials[world]) -> families (identical on every rank and for every world size). */
+ASGART_B200_API int32_t asgart_b200_ctx_search_shard(asgart_b200_ctx *ctx, const asgart_b200_chunk *chunks,
+                                                     int64_t n_chunks, const asgart_b200_settings *settings,
+                                                     int32_t shard, int32_t n_shards, asgart_b200_partial **out);
+ASGART_B200_API int64_t asgart_b200_partial_size(const asgart_b200_partial *p);           /* bytes when serialised */
+ASGART_B200_API int32_t asgart_b200_partial_serialize(const asgart_b200_partial *p, uint8_t *buf, int64_t cap);
+ASGART_B200_API void asgart_b200_partial_free(asgart_b200_partial *p);
+ASGART_B200_API int32_t asgart_b200_ctx_finish(asgart_b200_ctx *ctx, const asgart_b200_chunk *chunks, int64_t n_chunks,
+                                               const asgart_b200_settings *settings, const uint8_t *const *partials,
+                                               const int64_t *partial_sizes, int32_t n_shards, uint32_t post_mask,
+                                               asgart_b200_result **out);
+
+/* results */
+ASGART_B200_API int64_t asgart_b200_result_n_families(const asgart_b200_result *r);
+ASGART_B200_API int64_t asgart_b200_result_n_sds(const asgart_b200_result *r);
+ASGART_B200_API const uint64_t *asgart_b200_result_family_offsets(const asgart_b200_result *r); /* n_families+1 */
+ASGART_B200_API const asgart_b200_protosd *asgart_b200_result_sds(const asgart_b200_result *r);
+ASGART_B200_API void asgart_b200_result_free(asgart_b200_result *r);
+
+/* post-steps on caller-provided families (host arrays in, library-owned result out) — FilterNs needs the strand
+ * loaded in ctx */
+ASGART_B200_API int32_t asgart_b200_ctx_post_steps(asgart_b200_ctx *ctx, const uint64_t *family_offsets,
+                                                   int64_t n_families, const asgart_b200_protosd *sds,
+                                                   uint32_t post_mask, asgart_b200_result **out);
+
+/* ---- instrumentation (device time from CUDA events on the library's stream) ------------------------------ */
+typedef struct asgart_b200_stats {
+    /* phases of the last load/build/search, milliseconds */
+    double ms_h2d, ms_pack, ms_sa_build, ms_lut, ms_search, ms_automaton, ms_post, ms_d2h;
+    /* kernel families inside them: accumulated device ms, launches and algorithmic bytes */
+    double ms_sa_sort, ms_sa_gather, ms_sa_rank, ms_probe, ms_emit;
+    uint64_t launches_total;
+    uint64_t launches_sa_sort, launches_sa_gather, launches_probe;
+    uint64_t bytes_sa_sort, bytes_sa_gather, bytes_probe;
+    /* counters of the last search */
+    uint64_t n_probes, n_searched, n_skipped_n, n_skipped_card, n_matches, n_events, n_segments;
+    uint64_t sa_rounds, sa_index_bits;
+    uint64_t h2d_bytes, d2h_bytes;
+} asgart_b200_stats;
+ASGART_B200_API int32_t asgart_b200_ctx_stats(const asgart_b200_ctx *ctx, asgart_b200_stats *out);
+ASGART_B200_API void asgart_b200_ctx_reset_stats(asgart_b200_ctx *ctx);
+
+/* ---- host side of the path (C++ mirror of prepare_data / SD conversion / JSON export) -------------------- */
+typedef struct asgart_b200_prepared asgart_b200_prepared;
+/* prepare_data (src/bin/asgart.rs:273-471) for '\n'-separated FASTA paths; NULL + *err (static storage) on error */
+ASGART_B200_API asgart_b200_prepared *asgart_b200_prepare_files(const char *files, int32_t skip_masked, const char **err);
+/* the same from an in-memory, already normalised strand WITHOUT '$' and its fragment map */
+ASGART_B200_API asgart_b200_prepared *asgart_b200_prepare_memory(const char *file_names, const uint8_t *strand, int64_t n,
+                                                                 const char *fragment_names, const uint64_t *frag_pos,
+                                                                 const uint64_t *frag_len, int64_t n_fragments);
+ASGART_B200_API const uint8_t *asgart_b200_prepared_strand(const asgart_b200_prepared *p, int64_t *n_plus_1);
+ASGART_B200_API const asgart_b200_chunk *asgart_b200_prepared_chunks(const asgart_b200_prepared *p, int64_t *n_chunks);
+ASGART_B200_API int64_t asgart_b200_prepared_n_fragments(const asgart_b200_prepared *p);
+ASGART_B200_API const char *asgart_b200_prepared_fragment(const asgart_b200_prepared *p, int64_t i, uint64_t *position,
+                                                          uint64_t *length);
+ASGART_B200_API void asgart_b200_prepared_free(asgart_b200_prepared *p);
+/* RunResult -> JSON exactly as JSONExporter::save writes it (src/exporters.rs:12-25; ProtoSD->SD src/bin/asgart.rs:776-821).
+ * Returns a malloc'd NUL-terminated string; free with asgart_b200_free_string. */
+ASGART_B200_API char *asgart_b200_to_json(const asgart_b200_prepared *p, const asgart_b200_settings *settings,
+                                          const uint64_t *family_offsets, int64_t n_families,
+                                          const asgart_b200_protosd *sds);
+ASGART_B200_API void asgart_b200_free_string(char *s);
+/* default output file name (src/bin/asgart.rs:642-654, :695-719; src/utils.rs:30-49). malloc'd. */
+ASGART_B200_API char *asgart_b200_out_filename(const char *files, const char *prefix, const char *out,
+                                               const asgart_b200_settings *settings);
+/* whole `asgart FILES...` run on one device: prepare_data -> index -> search -> post-steps -> JSON text (malloc'd) */
+ASGART_B200_API char *asgart_b200_run_files(const char *files, const asgart_b200_settings *settings, int32_t device,
+                                            const char **err);
+
+/* ---- deterministic synthetic genomes (bench/test input; DESIGN.md "Synthetic inputs") ---------------------- */
+/* Fills out[0..n) (no '$') with the config's sequence (upper/lower case ACGT and N). config: 1..5 = BASELINE.json
+ * configs C1..C5 (C5: part 0/1 via `part`), 0 = custom (seed, n_pairs, rc_fraction_percent, no N, no mask).
+ * `scale_n` > 0 overrides the config's length (planted-pair count scales with it). Returns the length written. */
+ASGART_B200_API int64_t asgart_b200_synth_length(int32_t config, int32_t part, int64_t scale_n);
+ASGART_B200_API int64_t asgart_b200_synth_fill(int32_t config, int32_t part, int64_t scale_n, uint64_t seed,
+                                               int64_t n_pairs, int32_t rc_percent, uint8_t *out, int64_t cap,
+                                               int32_t threads);
+/* fragment table of the config (names '\n'-separated into names_buf); returns the fragment count */
+ASGART_B200_API int64_t asgart_b200_synth_fragments(int32_t config, int32_t part, int64_t scale_n, char *names_buf,
+                                                    int64_t names_cap, uint64_t *pos, uint64_t *len, int64_t cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ASGART_B200_H */

@@ -1,0 +1,90 @@
+"""Device-logic headers (kmer_core.h / automaton_core.h) compiled for the host, against the oracle.
+Covers the packed-window comparator, the LUT slots, the literal lock-step equal range, the match filters and the
+event / segment / death-time reformulation of the automaton — everything that does not need CUDA to be checked."""
+import numpy as np
+import pytest
+
+import oracle
+from asgart_b200 import _lib as ablib
+from tests import cases, emul_harness, kat
+
+
+def _settings_pair(kw):
+    so = oracle.make_settings(**kw)
+    sc = ablib.Settings(so.probe_size, so.max_gap_size, so.reverse, so.complement, so.skip_masked,
+                        so.min_duplication_length, so.max_cardinality, 0, 0, 0)
+    return so, sc
+
+
+def _strip(fams):
+    return [[sd[:4] for sd in f] for f in fams]
+
+
+@pytest.mark.parametrize("case", kat.cases(), ids=lambda c: c[0])
+def test_emul_kat(case):
+    name, text, chunks, kw, expected = case
+    strand = np.concatenate([text, np.frombuffer(b"$", dtype=np.uint8)])
+    sa = oracle.best_suffix_array(strand)
+    so, sc = _settings_pair(kw)
+    want = oracle.search(strand, sa, chunks, so, 0, threads=1)
+    got, ctr = emul_harness.search(strand, sa, chunks, sc)
+    assert got == _strip(want.families.as_lists())
+    assert ctr == want.counters
+
+
+@pytest.mark.parametrize("seed", [11, 12, 13])
+@pytest.mark.parametrize("label,kw", cases.settings_grid(), ids=[s[0] for s in cases.settings_grid()])
+def test_emul_stress(seed, label, kw):
+    text = cases.stress_text(seed)
+    prep = oracle.Prepared.from_memory(text, [("a", 0, 25000), ("b", 25000, len(text) - 25000)])
+    strand = prep.strand
+    sa = oracle.best_suffix_array(strand)
+    so, sc = _settings_pair(kw)
+    want = oracle.search(strand, sa, prep.chunks, so, 0, threads=2)
+    got, ctr = emul_harness.search(strand, sa, prep.chunks, sc)
+    assert got == _strip(want.families.as_lists())
+    assert ctr == want.counters
+    assert ctr["matches"] > 0
+
+
+def test_emul_lut_matches_oracle():
+    text = cases.stress_text(5, n=30000)
+    strand = np.concatenate([text, np.frombuffer(b"$", dtype=np.uint8)])
+    sa = oracle.best_suffix_array(strand)
+    keys, lo, hi = oracle.lut(strand, sa)
+    L = emul_harness.lib()
+    glo = np.zeros(ablib.LUT_SIZE, dtype=np.int64)
+    ghi = np.zeros(ablib.LUT_SIZE, dtype=np.int64)
+    L.emul_lut(strand.ctypes.data, len(strand), sa.ctypes.data, glo.ctypes.data, ghi.ctypes.data)
+    # oracle entries are in the reference's enumeration order with LE-u64 keys; ours are base-5 slots (A,C,G,N,T)
+    digit = {ord("A"): 0, ord("C"): 1, ord("G"): 2, ord("N"): 3, ord("T"): 4}
+    n_nonempty = 0
+    for k, a, b in zip(keys, lo, hi):
+        bs = int(k).to_bytes(8, "little")
+        slot = 0
+        for ch in bs:
+            slot = slot * 5 + digit[ch]
+        if b > a:
+            n_nonempty += 1
+            assert (glo[slot], ghi[slot]) == (a, b)
+        else:
+            assert glo[slot] == ghi[slot]
+    assert n_nonempty > 1000
+
+
+def test_q6_forced_less_near_strand_end():
+    """Quirk Q6: suffixes within k-1 of the end compare Less regardless of content (searcher.rs:165-166). Build a text
+    whose tail shares 8-mers with many probes so the literal bisection matters, and require equality with the oracle."""
+    rng = np.random.default_rng(3)
+    unit = kat.rand_dna(rng, 11)
+    body = np.tile(unit, 400)                      # 4400 bp of an 11-periodic repeat: every probe shares 8-mers with the tail
+    text = np.concatenate([kat.rand_dna(rng, 3000), body])
+    strand = np.concatenate([text, np.frombuffer(b"$", dtype=np.uint8)])
+    sa = oracle.best_suffix_array(strand)
+    for kw in (dict(probe_size=20, gap_size=100, min_length=200, max_cardinality=100000),
+               dict(probe_size=20, gap_size=100, min_length=200, max_cardinality=100000, reverse=True, complement=True)):
+        so, sc = _settings_pair(kw)
+        want = oracle.search(strand, sa, [(0, len(text))], so, 0)
+        got, ctr = emul_harness.search(strand, sa, [(0, len(text))], sc)
+        assert got == _strip(want.families.as_lists())
+        assert ctr == want.counters

@@ -1,0 +1,239 @@
+"""Parity tests proper: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+Bit-exact bar: suffix array, LUT, probe ranges, proto-duplicons, families after post-steps, JSON text."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import asgart_b200 as ab
+import oracle
+from asgart_b200 import _lib
+from tests import cases, kat
+from tests.test_oracle_ref import _texts
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _osettings(st: ab.RunSettings):
+    return oracle.make_settings(probe_size=st.probe_size, gap_size=st.gap_size, min_length=st.min_duplication_length,
+                                max_cardinality=st.max_cardinality, reverse=st.reverse, complement=st.complement,
+                                skip_masked=st.skip_masked)
+
+
+def _rs(kw):
+    kw = dict(kw)
+    if "min_length" in kw:
+        kw["min_duplication_length"] = kw.pop("min_length")
+    return ab.RunSettings(**kw)
+
+
+# ------------------------------------------------------------------------------------------------ suffix array
+@pytest.mark.parametrize("bits", [32, 64])
+@pytest.mark.parametrize("name", list(_texts().keys()))
+def test_sa_small_texts(name, bits):
+    t = _texts()[name]
+    want = oracle.best_suffix_array(t)
+    got = ab.r_divsufsort(t, device=0, index_bits=bits)
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("bits", [32, 64])
+def test_sa_golden_fixtures(bits):
+    """Fixtures made by the reference's own divsufsort64 (tests/golden/make_golden.py)."""
+    gold = json.load(open(os.path.join(GOLD, "sa_golden.json")))
+    for name, entry in gold["cases"].items():
+        t = np.frombuffer(bytes.fromhex(entry["text_hex"]), dtype=np.uint8)
+        assert ab.r_divsufsort(t, device=0, index_bits=bits).tolist() == entry["sa"], name
+
+
+def test_sa_edge_cases():
+    assert ab.r_divsufsort(b"").tolist() == []
+    assert ab.r_divsufsort(b"A").tolist() == [0]
+    assert ab.r_divsufsort(b"AA").tolist() == [1, 0]
+    assert ab.r_divsufsort(b"$").tolist() == [0]
+    a = np.zeros(70000, dtype=np.uint8)              # one symbol, every suffix ties until the end: worst case for doubling
+    assert np.array_equal(ab.r_divsufsort(a), np.arange(70000)[::-1])
+    b = np.tile(np.frombuffer(b"ACGTTGCA", dtype=np.uint8), 9000)   # period-8 text
+    assert np.array_equal(ab.r_divsufsort(b), oracle.best_suffix_array(b))
+
+
+@pytest.mark.parametrize("bits", [32, 64])
+def test_sa_medium_with_repeats(bits):
+    n = 1_500_000 if bits == 32 else 400_000
+    text = cases.stress_text(77, n=n, n_dups=60)
+    text[n // 3: n // 3 + 200_000 // (1 if bits == 32 else 4)] = ord("N")       # a long N-run: deep LCPs
+    strand = np.concatenate([text, np.frombuffer(b"$", dtype=np.uint8)])
+    got = ab.r_divsufsort(strand, device=0, index_bits=bits)
+    if oracle.ref() is not None:
+        assert oracle.ref_sufcheck64(strand, got) == 0
+        assert np.array_equal(got, oracle.ref_divsufsort64(strand))
+    else:
+        assert np.array_equal(got, oracle.suffix_array(strand))
+    assert got[0] == len(strand) - 1
+
+
+# ------------------------------------------------------------------------------------------------ LUT + probes
+def _slot_of_key(k):
+    digit = {ord("A"): 0, ord("C"): 1, ord("G"): 2, ord("N"): 3, ord("T"): 4}
+    s = 0
+    for ch in int(k).to_bytes(8, "little"):
+        s = s * 5 + digit[ch]
+    return s
+
+
+@pytest.mark.parametrize("bits", [32, 64])
+def test_lut_and_probe_ranges(bits):
+    text = cases.stress_text(5, n=50000)
+    strand = np.concatenate([text, np.frombuffer(b"$", dtype=np.uint8)])
+    sa = oracle.best_suffix_array(strand)
+    with ab.Context(0) as ctx:
+        ctx.set_index_bits(bits)
+        ctx.load_strand(strand)
+        ctx.upload_sa(sa)
+        lo, hi = ctx.download_lut()
+        keys, olo, ohi = oracle.lut(strand, sa)
+        slots = np.array([_slot_of_key(k) for k in keys])
+        ne = ohi > olo
+        assert np.array_equal(lo[slots[ne]], olo[ne]) and np.array_equal(hi[slots[ne]], ohi[ne])
+        assert np.array_equal(lo[slots[~ne]], hi[slots[~ne]])
+        # probe equal ranges == Searcher::search (unfiltered), for all four needle transforms and k = 20 / 32 / 40
+        osr = oracle.OracleSearcher(strand, sa)
+        comp = kat.complement
+        for kw in (dict(), dict(reverse=True, complement=True), dict(reverse=True), dict(complement=True),
+                   dict(probe_size=32, reverse=True, complement=True), dict(probe_size=40)):
+            st = ab.RunSettings(**kw)
+            chunk = (1000, 30000)
+            k, s = st.probe_size, st.probe_size // 2
+            nprobes = -(-(chunk[1] - k - s) // s)
+            glo, ghi = ctx.probe_ranges(chunk, st, nprobes)
+            needle = text[chunk[0]:chunk[0] + chunk[1]]
+            if st.complement:
+                needle = comp(needle)
+            if st.reverse:
+                needle = needle[::-1]
+            for p in list(range(0, nprobes, 37)) + [nprobes - 1]:
+                i = (p + 1) * s
+                want = osr.search(needle[i:i + k].tobytes())
+                assert ghi[p] - glo[p] == len(want), (kw, p)
+                assert np.array_equal(sa[glo[p]:ghi[p]], want), (kw, p)
+
+
+# ------------------------------------------------------------------------------------------------ search + automaton
+@pytest.mark.parametrize("case", kat.cases(), ids=lambda c: c[0])
+def test_search_kat(case):
+    name, text, chunks, kw, expected = case
+    strand = np.concatenate([text, np.frombuffer(b"$", dtype=np.uint8)])
+    with ab.Context(0) as ctx:
+        ctx.load_strand(strand)
+        ctx.build_index()
+        got = ctx.search(chunks, _rs(kw), ab.POST_ALL).as_lists()
+    if name == "KAT-3COPIES":
+        assert [sorted(f) for f in got] == [sorted(f) for f in expected]
+    else:
+        assert got == expected
+
+
+@pytest.mark.parametrize("bits", [32, 64])
+@pytest.mark.parametrize("seed", [11, 12, 13])
+def test_search_stress_all_settings(seed, bits):
+    text = cases.stress_text(seed)
+    prep = ab.Prepared.from_memory(text, [("a", 0, 25000), ("b", 25000, len(text) - 25000)])
+    strand = np.array(prep.strand)
+    sa = oracle.best_suffix_array(strand)
+    with ab.Context(0) as ctx:
+        ctx.set_index_bits(bits)
+        ctx.load_strand(strand)
+        ctx.build_index()
+        assert np.array_equal(ctx.download_sa(), sa)
+        for label, kw in cases.settings_grid():
+            st = _rs(kw)
+            ctx.reset_stats()
+            raw = ctx.search(prep.chunks, st, 0)
+            want_raw = oracle.search(strand, sa, prep.chunks, _osettings(st), 0, threads=2)
+            assert raw.as_lists() == want_raw.families.as_lists(), label
+            s = ctx.stats()
+            c = want_raw.counters
+            assert (s["n_probes"], s["n_searched"], s["n_skipped_n"], s["n_skipped_card"], s["n_matches"], s["bytes_probe"]) == \
+                   (c["probes"], c["searched"], c["skipped_n"], c["skipped_card"], c["matches"], c["alg_bytes"]), label
+            full = ctx.search(prep.chunks, st, ab.POST_ALL)
+            want = oracle.search(strand, sa, prep.chunks, _osettings(st), oracle.POST_ALL, threads=2)
+            assert full.as_lists() == want.families.as_lists(), label
+            # each post-step on its own, fed with the oracle's raw families
+            for mask in (ab.POST_FILTER_NS, ab.POST_REORDER, ab.POST_REDUCE_OVERLAP, ab.POST_SORT, ab.POST_FILTER_NS | ab.POST_SORT):
+                assert ctx.post_steps(raw, mask).as_lists() == oracle.post_steps(want_raw.families, strand, mask).as_lists(), (label, mask)
+
+
+def test_post_steps_unit_cases():
+    t = np.full(3001, ord("A"), dtype=np.uint8); t[-1] = ord("$")
+    t[0:200] = ord("N"); t[1200:1401] = ord("N")
+    with ab.Context(0) as ctx:
+        ctx.load_strand(t)
+        keep = ctx.post_steps(ab.families_from_lists([[(0, 2000, 1000, 1000)]]), ab.POST_FILTER_NS)
+        drop = ctx.post_steps(ab.families_from_lists([[(0, 1100, 1000, 1000)]]), ab.POST_FILTER_NS)
+        assert keep.n_families == 1 and drop.n_families == 0            # 200/1000 <= 0.2 kept, 201/1000 dropped (f32)
+        merged = ctx.post_steps(ab.families_from_lists([[(100, 2000, 500, 600), (400, 2300, 500, 450), (150, 2050, 100, 100)]]),
+                                ab.POST_REDUCE_OVERLAP)
+        assert [x[:4] for x in merged.as_lists()[0]] == [(100, 2000, 950, 800)]   # merge() with its mixed-up lengths (Q5)
+        ro = ctx.post_steps(ab.families_from_lists([[(900, 100, 10, 20)]]), ab.POST_REORDER)
+        assert [x[:4] for x in ro.as_lists()[0]] == [(100, 900, 10, 20)]          # positions only (Q4)
+        fams = [[(50, 9, 1, 1), (10, 8, 1, 1), (50, 7, 1, 1), (10, 6, 1, 1)], [], [(3, 3, 3, 3)]]
+        srt = ctx.post_steps(ab.families_from_lists(fams), ab.POST_SORT)
+        assert [[x[:2] for x in f] for f in srt.as_lists()] == [[(10, 8), (10, 6), (50, 9), (50, 7)], [(3, 3)]]   # stable
+
+
+def test_ragged_and_empty_inputs():
+    text = cases.stress_text(3, n=20000)
+    strand = np.concatenate([text, np.frombuffer(b"$", dtype=np.uint8)])
+    sa = oracle.best_suffix_array(strand)
+    with ab.Context(0) as ctx:
+        ctx.load_strand(strand)
+        ctx.build_index()
+        st = ab.RunSettings(min_duplication_length=300)
+        so = _osettings(st)
+        for chunks in ([], [(0, 10)], [(0, 299)], [(0, 300)], [(5, 31), (100, 5000), (5100, 0), (6000, 14000)], [(19990, 10)], [(0, 20000)]):
+            got = ctx.search(chunks, st, ab.POST_ALL).as_lists()
+            want = oracle.search(strand, sa, chunks, so, oracle.POST_ALL).families.as_lists()
+            assert got == want, chunks
+        with pytest.raises(ab.AsgartB200Error):
+            ctx.search([(19000, 2000)], st)                                   # chunk outside the strand
+        with pytest.raises(ab.AsgartB200Error):
+            ctx.search([(0, 20000)], ab.RunSettings(probe_size=7))            # reference needs k >= 8
+        with pytest.raises(ab.AsgartB200Error):
+            ctx.load_strand(np.frombuffer(b"ACGTXACGT$", dtype=np.uint8))     # not normalised
+        with pytest.raises(ab.AsgartB200Error):
+            ctx.load_strand(np.frombuffer(b"ACGTACGT", dtype=np.uint8))       # no '$'
+
+
+@pytest.mark.parametrize("n_shards", [1, 2, 3, 8])
+def test_sharded_search_equals_single(n_shards):
+    """Probe-range sharding (what N GPUs do) gives the same families for every shard count."""
+    text = cases.stress_text(12)
+    prep = ab.Prepared.from_memory(text, [("a", 0, 25000), ("b", 25000, len(text) - 25000)])
+    strand = np.array(prep.strand)
+    with ab.Context(0) as ctx:
+        ctx.load_strand(strand)
+        ctx.build_index()
+        for label, kw in cases.settings_grid()[:6]:
+            st = _rs(kw)
+            single = ctx.search(prep.chunks, st, ab.POST_ALL).as_lists()
+            parts = [ctx.search_shard(prep.chunks, st, r, n_shards) for r in range(n_shards)]
+            assert ctx.finish(prep.chunks, st, parts, ab.POST_ALL).as_lists() == single, label
+
+
+def test_run_files_json_identical_to_oracle(tmp_path):
+    g, fr = ab.synth_genome(2, scale_n=800_000)
+    fa = tmp_path / "synthY.fa"
+    with open(fa, "w") as f:
+        f.write(">synthY synthetic chrY-shaped\n")
+        s = g.tobytes().decode()
+        for i in range(0, len(s), 60):
+            f.write(s[i:i + 60] + "\n")
+    for kw in (dict(), dict(reverse=True, complement=True, skip_masked=True), dict(skip_masked=True)):
+        st = ab.RunSettings(**kw)
+        js = ab.search_duplications([str(fa)], st)
+        want = oracle.run_files([str(fa)], _osettings(st), threads=2)
+        assert js == want
+        assert json.loads(js)["settings"]["max_gap_size"] == 120
+    assert len(json.loads(ab.search_duplications([str(fa)], ab.RunSettings()))["families"]) > 0
