@@ -52,9 +52,10 @@ class ProtoSD(C.Structure):
 class Stats(C.Structure):
     _fields_ = (
         [(n, C.c_double) for n in ("ms_h2d", "ms_pack", "ms_sa_build", "ms_lut", "ms_search", "ms_automaton", "ms_post",
-                                   "ms_d2h", "ms_sa_sort", "ms_sa_gather", "ms_sa_rank", "ms_probe", "ms_emit")]
+                                   "ms_d2h", "ms_sa_sort", "ms_sa_gather", "ms_sa_rank", "ms_probe", "ms_emit", "ms_sa_scatter")]
         + [(n, C.c_uint64) for n in ("launches_total", "launches_sa_sort", "launches_sa_gather", "launches_probe",
-                                     "bytes_sa_sort", "bytes_sa_gather", "bytes_probe", "n_probes", "n_searched",
+                                     "launches_sa_scatter", "bytes_sa_sort", "bytes_sa_gather", "bytes_probe",
+                                     "bytes_sa_scatter", "n_probes", "n_searched",
                                      "n_skipped_n", "n_skipped_card", "n_matches", "n_events", "n_segments", "sa_rounds",
                                      "sa_index_bits", "h2d_bytes", "d2h_bytes")]
     )
@@ -73,7 +74,7 @@ SYMBOLS = [
     "asgart_b200_partial_serialize", "asgart_b200_partial_free", "asgart_b200_ctx_finish",
     "asgart_b200_result_n_families", "asgart_b200_result_n_sds", "asgart_b200_result_family_offsets",
     "asgart_b200_result_sds", "asgart_b200_result_free", "asgart_b200_ctx_post_steps", "asgart_b200_ctx_stats",
-    "asgart_b200_ctx_reset_stats", "asgart_b200_prepare_files", "asgart_b200_prepare_memory",
+    "asgart_b200_ctx_reset_stats", "asgart_b200_ctx_timer_start", "asgart_b200_ctx_timer_stop", "asgart_b200_prepare_files", "asgart_b200_prepare_memory",
     "asgart_b200_prepared_strand", "asgart_b200_prepared_chunks", "asgart_b200_prepared_n_fragments",
     "asgart_b200_prepared_fragment", "asgart_b200_prepared_free", "asgart_b200_to_json", "asgart_b200_free_string",
     "asgart_b200_out_filename", "asgart_b200_run_files", "asgart_b200_synth_length", "asgart_b200_synth_fill",
@@ -123,6 +124,8 @@ def load() -> C.CDLL:
         "asgart_b200_ctx_post_steps": (i32, [vp, vp, i64, vp, u32, C.POINTER(vp)]),
         "asgart_b200_ctx_stats": (i32, [vp, C.POINTER(Stats)]),
         "asgart_b200_ctx_reset_stats": (None, [vp]),
+        "asgart_b200_ctx_timer_start": (i32, [vp]),
+        "asgart_b200_ctx_timer_stop": (i32, [vp, C.POINTER(C.c_double)]),
         "asgart_b200_prepare_files": (vp, [C.c_char_p, i32, C.POINTER(C.c_char_p)]),
         "asgart_b200_prepare_memory": (vp, [C.c_char_p, vp, i64, C.c_char_p, vp, vp, i64]),
         "asgart_b200_prepared_strand": (vp, [vp, C.POINTER(i64)]),

@@ -235,6 +235,14 @@ class Context:
     def reset_stats(self):
         self.L.asgart_b200_ctx_reset_stats(self.h)
 
+    def timer_start(self):
+        self._check(self.L.asgart_b200_ctx_timer_start(self.h))
+
+    def timer_stop(self) -> float:
+        ms = C.c_double()
+        self._check(self.L.asgart_b200_ctx_timer_stop(self.h, C.byref(ms)))
+        return ms.value
+
 
 def families_from_lists(fams: Sequence[Sequence[Tuple[int, int, int, int]]], reverse=False, complement=False) -> Families:
     off = [0]

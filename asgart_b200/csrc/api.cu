@@ -62,7 +62,8 @@ struct asgart_b200_ctx {
     Index32 ix32;
     Index64 ix64;
     asgart_b200_stats st{};
-    FamilyTimer t_sort, t_gather, t_rank, t_probe, t_emit;
+    FamilyTimer t_sort, t_gather, t_rank, t_probe, t_emit, t_scatter;
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr;
     LaunchCounter launches;
 };
 
@@ -144,7 +145,7 @@ void build_index_t(asgart_b200_ctx* ctx) {
     {
         DevBuf<IdxT> rank(ctx->n1, ctx->stream);
         SaStats ss;
-        ss.sort = &ctx->t_sort; ss.gather = &ctx->t_gather; ss.rank = &ctx->t_rank;
+        ss.sort = &ctx->t_sort; ss.gather = &ctx->t_gather; ss.rank = &ctx->t_rank; ss.scatter = &ctx->t_scatter;
         build_suffix_array<IdxT>(ctx->d_text.p, ctx->n1, ix.sa.p, rank.p, ctx->stream, &ss);
         ctx->st.sa_rounds = ss.rounds;
     }
@@ -425,6 +426,9 @@ void run_stage_b(asgart_b200_ctx* ctx, const ChunkPlan& plan, const asgart_b200_
         // automaton
         DevBuf<i64> op_target(n_matches, s);
         DevBuf<u64> a_ls(n_matches, s), a_le(n_matches, s), a_rs(n_matches, s), a_re(n_matches, s), a_death(n_matches, s);
+        DevBuf<u32> act_arm(n_matches, s);
+        DevBuf<u64> act_rs(n_matches, s), act_re(n_matches, s), act_death(n_matches, s);
+        DevBuf<i64> act_thr(n_matches, s);
         DevBuf<asgart_b200_protosd> out_sd(n_matches, s);
         DevBuf<u8> out_flag(n_matches, s);
         out_flag.zero();
@@ -432,8 +436,13 @@ void run_stage_b(asgart_b200_ctx* ctx, const ChunkPlan& plan, const asgart_b200_
         B.ev_i = ev_i.p; B.ev_t = ev_t.p; B.ev_moff = ev_moff; B.ev_cnt = ev_cnt; B.ev_chunk = ev_chunk.p;
         B.seg_first = seg_first.p; B.matches = matches; B.op_target = op_target.p;
         B.a_ls = a_ls.p; B.a_le = a_le.p; B.a_rs = a_rs.p; B.a_re = a_re.p; B.a_death = a_death.p;
+        B.act_arm = act_arm.p; B.act_rs = act_rs.p; B.act_re = act_re.p; B.act_thr = act_thr.p; B.act_death = act_death.p;
         B.out_sd = out_sd.p; B.out_flag = out_flag.p; B.chunk_tc = tc.p; B.chunks = plan.dev.p;
-        automaton_kernel<<<unsigned(ceil_div(n_seg, 64)), 64, 0, s>>>(B, plan.ap, n_seg, st->reverse ? 1 : 0, st->complement ? 1 : 0);
+        if (getenv("ASGART_B200_AUTOMATON_V1"))  // thread-per-segment reference kernel, kept for A/B checks
+            automaton_kernel<<<unsigned(ceil_div(n_seg, 64)), 64, 0, s>>>(B, plan.ap, n_seg, st->reverse ? 1 : 0, st->complement ? 1 : 0);
+        else
+            automaton_warp_kernel<<<unsigned(ceil_div(n_seg * 32, 128)), 128, 0, s>>>(B, plan.ap, n_seg, st->reverse ? 1 : 0,
+                                                                                     st->complement ? 1 : 0);
         KERNEL_CHECK();
         count_launch();
         // compaction into CSR families
@@ -477,13 +486,14 @@ void shard_range(u64 total, int shard, int n_shards, u64& b, u64& e) {
 }
 
 void fold_family_timers(asgart_b200_ctx* ctx) {
-    ctx->t_sort.drain(); ctx->t_gather.drain(); ctx->t_rank.drain(); ctx->t_probe.drain(); ctx->t_emit.drain();
+    ctx->t_sort.drain(); ctx->t_gather.drain(); ctx->t_rank.drain(); ctx->t_probe.drain(); ctx->t_emit.drain(); ctx->t_scatter.drain();
     asgart_b200_stats& S = ctx->st;
     S.ms_sa_sort = ctx->t_sort.total_ms; S.launches_sa_sort = ctx->t_sort.launches; S.bytes_sa_sort = ctx->t_sort.bytes;
     S.ms_sa_gather = ctx->t_gather.total_ms; S.launches_sa_gather = ctx->t_gather.launches; S.bytes_sa_gather = ctx->t_gather.bytes;
     S.ms_sa_rank = ctx->t_rank.total_ms;
     S.ms_probe = ctx->t_probe.total_ms; S.launches_probe = ctx->t_probe.launches; S.bytes_probe = ctx->t_probe.bytes;
     S.ms_emit = ctx->t_emit.total_ms;
+    S.ms_sa_scatter = ctx->t_scatter.total_ms; S.launches_sa_scatter = ctx->t_scatter.launches; S.bytes_sa_scatter = ctx->t_scatter.bytes;
     S.launches_total = ctx->launches.total;
     S.sa_index_bits = u64(ctx->idx_bits);
 }
@@ -519,7 +529,8 @@ int32_t asgart_b200_ctx_create(int32_t device, asgart_b200_ctx** out) {
         u64 thr = ~u64(0);
         CUDA_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
         ctx->t_sort.init(ctx->stream); ctx->t_gather.init(ctx->stream); ctx->t_rank.init(ctx->stream);
-        ctx->t_probe.init(ctx->stream); ctx->t_emit.init(ctx->stream);
+        ctx->t_probe.init(ctx->stream); ctx->t_emit.init(ctx->stream); ctx->t_scatter.init(ctx->stream);
+        CUDA_CHECK(cudaEventCreate(&ctx->ev_a)); CUDA_CHECK(cudaEventCreate(&ctx->ev_b));
     } catch (const CudaError& e) {
         int code = e.code;
         delete ctx;
@@ -534,7 +545,9 @@ void asgart_b200_ctx_destroy(asgart_b200_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    ctx->t_sort.destroy(); ctx->t_gather.destroy(); ctx->t_rank.destroy(); ctx->t_probe.destroy(); ctx->t_emit.destroy();
+    ctx->t_sort.destroy(); ctx->t_gather.destroy(); ctx->t_rank.destroy(); ctx->t_probe.destroy(); ctx->t_emit.destroy(); ctx->t_scatter.destroy();
+    if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
+    if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
     ctx->d_text.release(); ctx->d_pt.release(); ctx->d_pn.release();
     ctx->ix32.sa.release(); ctx->ix32.lut_lo.release(); ctx->ix32.lut_hi.release();
     ctx->ix64.sa.release(); ctx->ix64.lut_lo.release(); ctx->ix64.lut_hi.release();
@@ -862,10 +875,25 @@ void asgart_b200_ctx_reset_stats(asgart_b200_ctx* ctx) {
     if (!ctx) return;
     try {
         cudaSetDevice(ctx->device);
-        ctx->t_sort.reset(); ctx->t_gather.reset(); ctx->t_rank.reset(); ctx->t_probe.reset(); ctx->t_emit.reset();
+        ctx->t_sort.reset(); ctx->t_gather.reset(); ctx->t_rank.reset(); ctx->t_probe.reset(); ctx->t_emit.reset(); ctx->t_scatter.reset();
     } catch (...) {}
     ctx->launches.total = 0;
     ctx->st = asgart_b200_stats{};
+}
+
+int32_t asgart_b200_ctx_timer_start(asgart_b200_ctx* ctx) {
+    return guarded(ctx, [&]() -> int32_t { CUDA_CHECK(cudaEventRecord(ctx->ev_a, ctx->stream)); return ASGART_B200_OK; });
+}
+int32_t asgart_b200_ctx_timer_stop(asgart_b200_ctx* ctx, double* elapsed_ms) {
+    return guarded(ctx, [&]() -> int32_t {
+        if (!elapsed_ms) return fail(ctx, ASGART_B200_EINVAL, "null elapsed_ms");
+        CUDA_CHECK(cudaEventRecord(ctx->ev_b, ctx->stream));
+        CUDA_CHECK(cudaEventSynchronize(ctx->ev_b));
+        float t = 0;
+        CUDA_CHECK(cudaEventElapsedTime(&t, ctx->ev_a, ctx->ev_b));
+        *elapsed_ms = double(t);
+        return ASGART_B200_OK;
+    });
 }
 
 // ---- divsufsort64 drop-in -----------------------------------------------------------------------------

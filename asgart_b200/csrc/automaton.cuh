@@ -53,6 +53,12 @@ struct AutoBuffers {
     const u64* matches;
     i64* op_target;
     u64 *a_ls, *a_le, *a_rs, *a_re, *a_death;  // arm store, indexed like matches
+    // active list of the warp kernel (arms that can still be extended), same capacity, creation order preserved
+    u32* act_arm;   // index into the segment's arm store
+    u64* act_rs;
+    u64* act_re;
+    i64* act_thr;   // max(G, trunc(0.1 * left length)), refreshed when the arm is extended
+    u64* act_death;
     asgart_b200_protosd* out_sd;               // slot array, indexed like matches
     u8* out_flag;                              // 0 empty, 1 duplicon, 3 duplicon that opens a family
     const u64* chunk_tc;                       // processed iterations per chunk
@@ -81,6 +87,175 @@ __global__ void automaton_kernel(AutoBuffers B, AutoParams P, u64 n_segments, u3
                          B.out_flag[cursor] = head ? 3 : 1;
                          ++cursor;
                      });
+}
+
+// One warp per segment. Same event-driven semantics as simulate_segment (automaton_core.h), with the work of one
+// event spread over the lanes:
+//   phase 1  lane = match: scan the active arms in creation order for the first one the match extends (snapshot
+//            semantics: nothing is modified until every match has been classified)          src/automaton.rs:122-134
+//   phase 2  ExtendArm ops: per arm the last match in SA order wins (__match_any_sync picks it)              :136-143
+//   phase 3  NewArm ops appended in match order (ballot + prefix popcount)                                   :145-163
+// Arms that can no longer be extended (death < t) are dropped from the active list by an order-preserving warp
+// compaction; the arm store keeps every arm of the open family for the flush (:182-200).
+__global__ void __launch_bounds__(128) automaton_warp_kernel(AutoBuffers B, AutoParams P, u64 n_segments, u32 reversed_flag,
+                                                             u32 complemented_flag) {
+    const u64 sidx = (u64(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    if (sidx >= n_segments) return;  // whole warps leave together
+    const unsigned lane = lane_id();
+    const unsigned lt = lanemask_lt();
+    const unsigned FULL = 0xffffffffu;
+    const u64 e0 = B.seg_first[sidx], e1 = B.seg_first[sidx + 1];
+    const u32 c = B.ev_chunk[e0];
+    const ChunkDev ch = B.chunks[c];
+    const u64 Tc = B.chunk_tc[c];
+    const u64 slot0 = B.ev_moff[e0];
+    u64* a_ls = B.a_ls + slot0; u64* a_le = B.a_le + slot0; u64* a_rs = B.a_rs + slot0; u64* a_re = B.a_re + slot0;
+    u32* act_arm = B.act_arm + slot0; u64* act_rs = B.act_rs + slot0; u64* act_re = B.act_re + slot0;
+    i64* act_thr = B.act_thr + slot0; u64* act_death = B.act_death + slot0;
+    i64* op_target = B.op_target;
+    const u64* matches = B.matches;
+    u64 n_arms = 0, fam_start = 0, n_act = 0, max_death = 0, act_min_death = ~u64(0), cursor = slot0;
+    const i64 Gi = i64(P.G);
+
+    auto flush = [&]() {
+        bool first = true;
+        for (u64 base = fam_start; base < n_arms; base += 32) {
+            const u64 a = base + lane;
+            bool ok = false;
+            u64 rl = 0, ll = 0;
+            if (a < n_arms) { rl = a_re[a] - a_rs[a]; ll = a_le[a] - a_ls[a]; ok = rl >= P.min_len; }
+            const unsigned m = __ballot_sync(FULL, ok);
+            if (ok) {
+                const u64 slot = cursor + __popc(m & lt);
+                asgart_b200_protosd o;
+                o.left = P.reverse ? (ch.c0 + ch.len - a_ls[a] - ll) : (a_ls[a] + ch.c0);
+                o.right = a_rs[a];
+                o.left_length = ll; o.right_length = rl;
+                o.identity = 0.f;
+                o.reversed = u8(reversed_flag); o.complemented = u8(complemented_flag);
+                o._pad[0] = o._pad[1] = 0;
+                B.out_sd[slot] = o;
+                B.out_flag[slot] = (first && (m & lt) == 0) ? 3 : 1;
+            }
+            if (m) { first = false; cursor += __popc(m); }
+        }
+        fam_start = n_arms;
+        n_act = 0;
+        max_death = 0;
+        act_min_death = ~u64(0);
+        __syncwarp();
+    };
+
+    auto compact = [&](u64 t) {  // drop arms with death < t, keep order; recompute the exact minimum death
+        u64 w = 0, mn = ~u64(0);
+        for (u64 base = 0; base < n_act; base += 32) {
+            const u64 a = base + lane;
+            u32 arm = 0; u64 rs = 0, re = 0, death = 0; i64 thr = 0;
+            bool keep = false;
+            if (a < n_act) {
+                arm = act_arm[a]; rs = act_rs[a]; re = act_re[a]; thr = act_thr[a]; death = act_death[a];
+                keep = death >= t;
+            }
+            const unsigned m = __ballot_sync(FULL, keep);
+            __syncwarp();  // all reads of this block of 32 done before anyone overwrites (w <= base)
+            if (keep) {
+                const u64 d = w + __popc(m & lt);
+                act_arm[d] = arm; act_rs[d] = rs; act_re[d] = re; act_thr[d] = thr; act_death[d] = death;
+                mn = death < mn ? death : mn;
+            }
+            w += __popc(m);
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) { const u64 o = __shfl_xor_sync(FULL, mn, d); mn = o < mn ? o : mn; }
+        n_act = w;
+        act_min_death = mn;
+        __syncwarp();
+    };
+
+    for (u64 eb = e0; eb < e1; eb += 32) {
+        u64 my_t = 0, my_i = 0, my_moff = 0; u32 my_cnt = 0;
+        if (eb + lane < e1) { my_t = B.ev_t[eb + lane]; my_i = B.ev_i[eb + lane]; my_moff = B.ev_moff[eb + lane]; my_cnt = B.ev_cnt[eb + lane]; }
+        const int nev = int(min(u64(32), e1 - eb));
+        for (int j = 0; j < nev; ++j) {
+            const u64 t = __shfl_sync(FULL, my_t, j), i = __shfl_sync(FULL, my_i, j), m0 = __shfl_sync(FULL, my_moff, j);
+            const u32 cnt = __shfl_sync(FULL, my_cnt, j);
+            if (n_arms > fam_start && max_death < t) flush();
+            if (n_act > 0 && act_min_death < t) compact(t);
+            const u64 snap = n_act;
+            const bool single = cnt <= 32;
+            i64 my_target = -1;
+            u64 my_ms = 0;
+            // phase 1
+            for (u32 r0 = 0; r0 < cnt; r0 += 32) {
+                const u32 r = r0 + lane;
+                const bool valid = r < cnt;
+                const u64 ms = valid ? matches[m0 + r] : 0, me = ms + P.k;
+                i64 target = -1;
+                bool searching = valid;
+                for (u64 a = 0; a < snap; ++a) {
+                    if (__ballot_sync(FULL, searching) == 0) break;
+                    const u64 re = act_re[a];
+                    if (searching && act_death[a] >= t && me > re && d_ss_core(act_rs[a], re, ms, me) < act_thr[a]) {
+                        target = i64(a);
+                        searching = false;
+                    }
+                }
+                if (single) { my_target = target; my_ms = ms; }
+                else if (valid) op_target[m0 + r] = target;
+            }
+            __syncwarp();
+            // phase 2: extends, last match per arm wins
+            bool any_ext = false, any_new = false;
+            for (u32 r0 = 0; r0 < cnt; r0 += 32) {
+                const u32 r = r0 + lane;
+                const bool valid = r < cnt;
+                i64 target = -1; u64 ms = 0;
+                if (single) { target = my_target; ms = my_ms; }
+                else if (valid) { target = op_target[m0 + r]; ms = matches[m0 + r]; }
+                const bool ext = valid && target >= 0;
+                const unsigned peers = __match_any_sync(FULL, ext ? target : i64(-1) - i64(lane));
+                if (ext && (31 - __clz(peers)) == int(lane)) {
+                    const u64 a = u64(target);
+                    const u32 arm = act_arm[a];
+                    const u64 le = i + P.k, re = ms + P.k;
+                    a_le[arm] = le; a_re[arm] = re;
+                    act_re[a] = re;
+                    const i64 tenth = i64(0.1 * double(le - a_ls[arm]));  // src/automaton.rs:69
+                    act_thr[a] = Gi > tenth ? Gi : tenth;
+                    act_death[a] = t + P.q_ext;
+                }
+                any_ext = any_ext || (__ballot_sync(FULL, ext) != 0);
+                __syncwarp();  // a later round may extend the same arm again: keep rounds ordered
+            }
+            // phase 3: new arms in match order
+            for (u32 r0 = 0; r0 < cnt; r0 += 32) {
+                const u32 r = r0 + lane;
+                const bool valid = r < cnt;
+                i64 target = 0; u64 ms = 0;
+                if (single) { target = my_target; ms = my_ms; }
+                else if (valid) { target = op_target[m0 + r]; ms = matches[m0 + r]; }
+                const bool isnew = valid && target < 0;
+                const unsigned m = __ballot_sync(FULL, isnew);
+                if (isnew) {
+                    const u64 off = __popc(m & lt);
+                    const u64 arm = n_arms + off, a = n_act + off;
+                    a_ls[arm] = i; a_le[arm] = i + P.k; a_rs[arm] = ms; a_re[arm] = ms + P.k;
+                    act_arm[a] = u32(arm); act_rs[a] = ms; act_re[a] = ms + P.k;
+                    const i64 tenth = i64(0.1 * double(P.k));
+                    act_thr[a] = Gi > tenth ? Gi : tenth;
+                    act_death[a] = t + P.q_new;
+                }
+                if (m) { any_new = true; n_arms += __popc(m); n_act += __popc(m); }
+            }
+            if (any_ext && t + P.q_ext > max_death) max_death = t + P.q_ext;
+            if (any_new) {
+                if (t + P.q_new > max_death) max_death = t + P.q_new;
+                if (t + P.q_new < act_min_death) act_min_death = t + P.q_new;
+            }
+            __syncwarp();
+        }
+    }
+    if (n_arms > fam_start && max_death + 1 <= Tc) flush();
 }
 
 // ------------------------------------------------------------------------------------------------ post-steps

@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(kRsThreads) rs_scatter_kernel(const KeyT* __re
 // Ping-pongs between (keys, vals) and (keys_alt, vals_alt); on return `keys`/`vals` point at the sorted data.
 template <typename KeyT, typename ValT>
 void radix_sort_pairs(KeyT*& keys, KeyT*& keys_alt, ValT*& vals, ValT*& vals_alt, u64 n, const int* shifts, int n_passes,
-                      cudaStream_t stream, FamilyTimer* timer = nullptr) {
+                      cudaStream_t stream, FamilyTimer* timer = nullptr, FamilyTimer* scatter_timer = nullptr) {
     if (n == 0 || n_passes == 0) return;
     constexpr int ITEMS = RsItems<KeyT>::value;
     constexpr int TILE = kRsThreads * ITEMS;
@@ -171,15 +171,18 @@ void radix_sort_pairs(KeyT*& keys, KeyT*& keys_alt, ValT*& vals, ValT*& vals_alt
             u32* op = offs32.p;
             device_scan<u32, SumOp>([hp] __device__(u64 i) { return hp[i]; },
                                     [op] __device__(u64 i, u32 exc, u32) { op[i] = exc; }, table, (u32*)nullptr, stream);
+            if (scatter_timer) scatter_timer->begin();
             rs_scatter_kernel<KeyT, ValT, u32, ITEMS>
                 <<<unsigned(tiles), kRsThreads, 0, stream>>>(keys, vals, keys_alt, vals_alt, n, shift, offs32.p, tiles);
         } else {
             u64* op = offs64.p;
             device_scan<u64, SumOp>([hp] __device__(u64 i) { return u64(hp[i]); },
                                     [op] __device__(u64 i, u64 exc, u64) { op[i] = exc; }, table, (u64*)nullptr, stream);
+            if (scatter_timer) scatter_timer->begin();
             rs_scatter_kernel<KeyT, ValT, u64, ITEMS>
                 <<<unsigned(tiles), kRsThreads, 0, stream>>>(keys, vals, keys_alt, vals_alt, n, shift, offs64.p, tiles);
         }
+        if (scatter_timer) scatter_timer->end(1, n * (2 * sizeof(KeyT) + 2 * sizeof(ValT)));
         KERNEL_CHECK();
         count_launch(2);
         if (timer) timer->end(5, n * (2 * sizeof(KeyT) + 2 * sizeof(ValT)));

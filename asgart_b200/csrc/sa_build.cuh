@@ -26,6 +26,7 @@ namespace ab200 {
 
 struct SaStats {
     FamilyTimer* sort = nullptr;    // radix passes
+    FamilyTimer* scatter = nullptr; // rs_scatter_kernel alone
     FamilyTimer* gather = nullptr;  // rank[I + h] gathers
     FamilyTimer* rank = nullptr;    // re-rank / compaction scans
     u64 rounds = 0;
@@ -60,16 +61,16 @@ constexpr int kInitTile = kInitThreads * kInitItems;
 
 // key[i] = codes of T[i .. i+p0) packed most-significant-first, b bits each; vals[i] = i
 template <typename IdxT>
-__global__ void __launch_bounds__(kInitThreads) init_keys_kernel(const u8* __restrict__ text, u64 n, const u8* __restrict__ code,
+__global__ void __launch_bounds__(kInitThreads) init_keys_kernel(const u8* __restrict__ text, u64 n, const uint16_t* __restrict__ code,
                                                                   int b, int p0, u64* __restrict__ keys, IdxT* __restrict__ vals) {
-    __shared__ u8 sc[kInitTile + 64];
-    __shared__ u8 scode[256];
+    __shared__ uint16_t sc[kInitTile + 64];   // codes reach 256 when every byte value occurs
+    __shared__ uint16_t scode[256];
     scode[threadIdx.x] = code[threadIdx.x];
     __syncthreads();
     const u64 base = u64(blockIdx.x) * kInitTile;
     for (u32 i = threadIdx.x; i < kInitTile + 64; i += kInitThreads) {
         u64 p = base + i;
-        sc[i] = p < n ? scode[text[p]] : u8(0);
+        sc[i] = p < n ? scode[text[p]] : uint16_t(0);
     }
     __syncthreads();
     const u32 t0 = threadIdx.x * kInitItems;
@@ -151,13 +152,13 @@ void build_suffix_array(const u8* d_text, u64 n, IdxT* d_sa, IdxT* d_rank, cudaS
     unsigned long long h_hist[256];
     CUDA_CHECK(cudaMemcpyAsync(h_hist, d_hist.p, sizeof h_hist, cudaMemcpyDeviceToHost, stream));
     CUDA_CHECK(cudaStreamSynchronize(stream));
-    u8 h_code[256];
+    uint16_t h_code[256];
     int sigma = 0;
-    for (int c = 0; c < 256; ++c) h_code[c] = h_hist[c] ? u8(++sigma) : u8(0);
+    for (int c = 0; c < 256; ++c) h_code[c] = h_hist[c] ? uint16_t(++sigma) : uint16_t(0);
     const int b = std::max(1, bit_width_u64(u64(sigma)));  // codes 0..sigma
     const int p0 = 64 / b;
-    DevBuf<u8> d_code(256, stream);
-    CUDA_CHECK(cudaMemcpyAsync(d_code.p, h_code, 256, cudaMemcpyHostToDevice, stream));
+    DevBuf<uint16_t> d_code(256, stream);
+    CUDA_CHECK(cudaMemcpyAsync(d_code.p, h_code, sizeof h_code, cudaMemcpyHostToDevice, stream));
 
     // ---- 1. initial keys + sort
     DevBuf<IdxT> Gbuf, Ibuf;
@@ -174,7 +175,8 @@ void build_suffix_array(const u8* d_text, u64 n, IdxT* d_sa, IdxT* d_rank, cudaS
         for (int s = 0; s < b * p0; s += 8) shifts.push_back(s);
         u64 *k = keysA.p, *ka = keysB.p;
         IdxT *v = valsA.p, *va = valsB.p;
-        radix_sort_pairs<u64, IdxT>(k, ka, v, va, n, shifts.data(), int(shifts.size()), stream, st ? st->sort : nullptr);
+        radix_sort_pairs<u64, IdxT>(k, ka, v, va, n, shifts.data(), int(shifts.size()), stream, st ? st->sort : nullptr,
+                                    st ? st->scatter : nullptr);
 
         // ---- 2. heads -> rank, SA, work list
         using MC = MaxCnt<IdxT>;
@@ -234,7 +236,8 @@ void build_suffix_array(const u8* d_text, u64 n, IdxT* d_sa, IdxT* d_rank, cudaS
         }
         KeyT *k = KA.p, *ka = KB.p;
         IdxT *v = Ibuf.p, *va = IB.p;
-        radix_sort_pairs<KeyT, IdxT>(k, ka, v, va, U, shifts.data(), int(shifts.size()), stream, st ? st->sort : nullptr);
+        radix_sort_pairs<KeyT, IdxT>(k, ka, v, va, U, shifts.data(), int(shifts.size()), stream, st ? st->sort : nullptr,
+                                     st ? st->scatter : nullptr);
 
         using M2 = Max2Cnt<IdxT>;
         DevBuf<M2> d_total(1, stream);

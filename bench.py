@@ -1,0 +1,320 @@
+#!/usr/bin/env python
+"""bench.py — the hot path (SA build + LUT + probe search + arm automaton + post-steps) on synthetic genomes.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config 1..4] [--scale-n BP] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 ... bench.py --gpus N ...
+
+One JSON line on rank 0. A "step" = one whole pass of the path over the workload genome:
+  value  (bp/s)  device-resident input: strand already in HBM, K x [build_index + search + post-steps], CUDA events on
+                 the library's stream, max over ranks.
+  e2e    (bp/s)  same through the C ABI with HOST buffers: K x [load_strand (H2D from pinned memory) + build_index +
+                 search + post-steps + families D2H].
+Workload (N=1 default) = BASELINE.json configs[1]: synthetic 57 Mbp chrY-sized sequence, planted direct + RC
+duplications, -RC -S. N>1: the same genome, strand + index replicated per GPU, probes partitioned by position, one
+NCCL all-gather of the stage-A partials (strong scaling).
+`--impl reference` times the reference algorithm on the host cores: the reference's own libdivsufsort64 (oracle/_ref) +
+the oracle port of its Rust probe loop/automaton/post-steps (no Rust toolchain exists here), all host threads.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+CONFIG_FLAGS = {
+    1: dict(),
+    2: dict(reverse=True, complement=True, skip_masked=True),
+    3: dict(reverse=True, complement=True, max_cardinality=500),
+    4: dict(reverse=True, complement=True),
+}
+CONFIG_NAMES = {
+    1: "C1 synthetic 10 Mbp single-FASTA, 40 planted direct pairs, direct only",
+    2: "C2 synthetic 57 Mbp chrY-sized, planted direct+RC duplications, -RC -S",
+    3: "C3 synthetic 250 Mbp chr1-sized, -RC, max_cardinality=500",
+    4: "C4 synthetic 3.1 Gbp 24-fragment multiFASTA, -RC",
+}
+FULL_N = {1: 10_000_000, 2: 57_227_415, 3: 248_956_422, 4: 3_088_269_832}
+METRIC = "bp/s searched end-to-end (SA build + search + clustering; -RC, k=20, g=100)"
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled during the timed region."""
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def make_workload(config: int, scale_n: int):
+    import asgart_b200 as ab
+    flags = CONFIG_FLAGS[config]
+    st = ab.RunSettings(**flags)
+    g, fr = ab.synth_genome(config, scale_n=scale_n, threads=os.cpu_count() or 8)
+    prep = ab.Prepared.from_memory(ab.normalise(g, st.skip_masked), fr, f"synthC{config}.fa")
+    return st, prep
+
+
+def searched_bp(prep) -> int:
+    return int(sum(c[1] for c in prep.chunks))
+
+
+# ---------------------------------------------------------------------------------------------------- reference arm
+def cpu_reference_pass(strand: np.ndarray, chunks, st, threads: int):
+    """One pass of the reference algorithm on the CPU. The only place (with cpu_baseline) bench.py executes oracle/."""
+    import oracle
+    so = oracle.make_settings(probe_size=st.probe_size, gap_size=st.gap_size, min_length=st.min_duplication_length,
+                              max_cardinality=st.max_cardinality, reverse=st.reverse, complement=st.complement,
+                              skip_masked=st.skip_masked)
+    kind = "reference" if oracle.ref() is not None else "port"
+    t0 = time.perf_counter()
+    sa = oracle.ref_divsufsort64(strand) if oracle.ref() is not None else oracle.suffix_array(strand)   # single thread, like build.rs builds it
+    t1 = time.perf_counter()
+    out = oracle.search(strand, sa, chunks, so, oracle.POST_ALL, threads=threads)
+    t2 = time.perf_counter()
+    return {"seconds": t2 - t0, "sa_s": t1 - t0, "lut_s": out.seconds["lut"], "search_s": out.seconds["search"],
+            "post_s": out.seconds["post"], "families": len(out.families.fam_offsets) - 1, "sa_kind": kind}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    full_n = args.scale_n or FULL_N[args.config]
+    # bounded sample: ~0.4 us/bp of CPU work measured on this class of host; keep the whole run near two minutes
+    budget_bp = int(120.0 / 0.4e-6 / max(1, args.steps + args.warmup))
+    sample_n = min(full_n, max(2_000_000, budget_bp))
+    st, prep = make_workload(args.config, 0 if sample_n == FULL_N[args.config] else sample_n)
+    strand = np.array(prep.strand)
+    bp = searched_bp(prep)
+    for _ in range(args.warmup):
+        cpu_reference_pass(strand, prep.chunks, st, cores)
+    t0 = time.perf_counter()
+    last = None
+    for _ in range(args.steps):
+        last = cpu_reference_pass(strand, prep.chunks, st, cores)
+    dt = time.perf_counter() - t0
+    value = bp * args.steps / dt
+    sample = (f"{'whole' if sample_n == full_n else 'scaled'} workload: {len(strand) - 1} bp generated by the same generator "
+              f"(config C{args.config}), {bp} bp in chunks; SA by the reference's libdivsufsort64 (1 thread) + oracle port of the "
+              f"Rust probe loop/automaton/post-steps ({cores} threads over {len(prep.chunks)} chunks)")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "bp/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "u8/int64", "data": "synthetic",
+        "config": {"workload": CONFIG_NAMES[args.config], "sample_bp": len(strand) - 1, "flags": CONFIG_FLAGS[args.config]},
+        "cpu_baseline": {"value": value, "unit": "bp/s", "cores": cores, "kind": last["sa_kind"] if last else "port", "sample": sample,
+                         "phases_s": {k: round(v, 3) for k, v in (last or {}).items() if k.endswith("_s")}},
+        "e2e": {"value": value, "unit": "bp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import torch
+
+    import asgart_b200 as ab
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+
+    st, prep = make_workload(args.config, args.scale_n)
+    n1 = len(prep.strand)
+    bp = searched_bp(prep)
+    pinned = torch.empty(n1, dtype=torch.uint8).pin_memory()
+    pinned.numpy()[:] = prep.strand
+    ctx = ab.Context(local)
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if dist is not None:
+            dist.barrier()
+
+    def search(post=ab.POST_ALL):
+        if dist is None:
+            return ctx.search(prep.chunks, st, post)
+        from asgart_b200.dist import sharded_search
+        return sharded_search(ctx, prep.chunks, st, post, dev)
+
+    def step_resident():
+        ctx.build_index()
+        return search()
+
+    def step_e2e():
+        ctx.load_strand_ptr(pinned.data_ptr(), n1)
+        ctx.build_index()
+        return search()
+
+    def timed(fn, steps):
+        barrier()
+        ctx.timer_start()
+        t0 = time.perf_counter()
+        fam = None
+        for _ in range(steps):
+            fam = fn()
+        ms = ctx.timer_stop()
+        barrier()
+        wall = (time.perf_counter() - t0) * 1e3
+        if dist is not None:
+            t = torch.tensor([ms, wall], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms, wall = float(t[0]), float(t[1])
+        return ms, wall, fam
+
+    # ---- device-resident value
+    ctx.load_strand_ptr(pinned.data_ptr(), n1)
+    for _ in range(args.warmup):
+        step_resident()
+    ctx.reset_stats()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms, wall, fam = timed(step_resident, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    stats = ctx.stats()
+    # ---- end to end through the C ABI with host buffers
+    for _ in range(min(args.warmup, 3)):
+        step_e2e()
+    ctx.reset_stats()
+    ms_e2e, wall_e2e, fam2 = timed(step_e2e, args.steps)
+    stats_e2e = ctx.stats()
+    assert fam2.as_lists() == fam.as_lists()
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        K = args.steps
+        scat_ms = stats["ms_sa_scatter"] / max(1, stats["launches_sa_scatter"])
+        scat_bytes = stats["bytes_sa_scatter"] / max(1, stats["launches_sa_scatter"])
+        achieved = scat_bytes / (scat_ms * 1e-3) / 1e9 if scat_ms > 0 else 0.0
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            try:
+                traffic = json.load(open(tpath)).get("rs_scatter_kernel_dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        line = {
+            "metric": METRIC, "value": bp * K / (ms * 1e-3), "unit": "bp/s", "n_gpus": world, "steps": K, "warmup": args.warmup,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32",
+            "data": "synthetic",
+            "config": {"workload": CONFIG_NAMES[args.config], "strand_bp": n1 - 1, "searched_bp": bp, "chunks": len(prep.chunks),
+                       "flags": CONFIG_FLAGS[args.config], "probe_size": st.probe_size, "gap_size": st.gap_size,
+                       "parallelism": f"probe-range x{world}, strand+SA replicated",
+                       "l2": "inputs larger than L2 (text+SA+sort buffers > 1 GB per step vs 126 MB L2)",
+                       "timing": "CUDA events on the library stream around the K-step loop; wall clock agrees within ms_per_step_wall"},
+            "ms_per_step_wall": wall / K,
+            "clocks": clocks,
+            "e2e": {"value": bp * K / (ms_e2e * 1e-3), "unit": "bp/s", "ms_per_step": ms_e2e / K,
+                    "h2d_bytes_per_step": stats_e2e["h2d_bytes"] // K, "d2h_bytes_per_step": stats_e2e["d2h_bytes"] // K},
+            "gpu_launches": int(stats["launches_total"]),
+            "roofline": {"kernel": "rs_scatter_kernel (radix-sort scatter pass of the SA build)", "bound": "hbm",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
+                         "traffic": traffic, "peak_source": peak_src,
+                         "bytes_per_launch": scat_bytes, "ms_per_launch": scat_ms,
+                         "launches_per_step": stats["launches_sa_scatter"] / K,
+                         "share_of_step": stats["ms_sa_scatter"] / ms if ms else None},
+            "kernel_families": {
+                "sa_sort_pass": {"ms_per_step": stats["ms_sa_sort"] / K, "alg_GBps": stats["bytes_sa_sort"] / max(stats["ms_sa_sort"], 1e-9) / 1e6},
+                "sa_gather": {"ms_per_step": stats["ms_sa_gather"] / K, "alg_GBps": stats["bytes_sa_gather"] / max(stats["ms_sa_gather"], 1e-9) / 1e6},
+                "probe_search": {"ms_per_step": stats["ms_probe"] / K, "alg_GBps": stats["bytes_probe"] / max(stats["ms_probe"], 1e-9) / 1e6,
+                                 "probes_per_s": stats["n_probes"] / max(stats["ms_probe"], 1e-9) * 1e3},
+            },
+            "phases_ms_per_step": {k: stats[k] / K for k in ("ms_sa_build", "ms_lut", "ms_search", "ms_automaton", "ms_post", "ms_d2h")},
+            "counters_per_step": {k: stats[k] // K for k in ("n_probes", "n_searched", "n_skipped_n", "n_skipped_card", "n_matches")}
+                                 | {"sa_rounds": stats["sa_rounds"], "families": fam.n_families, "duplicons": len(fam.sds)},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            full = n1 - 1
+            sample_n = min(full, 60_000_000)
+            if sample_n == full:
+                s_strand, s_chunks, s_bp = np.array(prep.strand), prep.chunks, bp
+            else:
+                st2, prep2 = make_workload(args.config, sample_n)
+                s_strand, s_chunks, s_bp = np.array(prep2.strand), prep2.chunks, searched_bp(prep2)
+            r = cpu_reference_pass(s_strand, s_chunks, st, cores)
+            line["cpu_baseline"] = {
+                "value": s_bp / r["seconds"], "unit": "bp/s", "cores": cores, "kind": r["sa_kind"],
+                "sample": (f"{'whole workload' if sample_n == full else 'scaled workload'}: {len(s_strand) - 1} bp, one pass; SA by the "
+                           f"reference's libdivsufsort64 (1 thread, as build.rs builds it) + oracle port of the Rust probe "
+                           f"loop/automaton/post-steps on {cores} threads over {len(s_chunks)} chunks (no rustc in this image)"),
+                "phases_s": {k: round(v, 3) for k, v in r.items() if k.endswith("_s")}, "families": r["families"]}
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--config", type=int, default=2, choices=[1, 2, 3, 4])
+    ap.add_argument("--scale-n", type=int, default=0, help="override the config's genome length (bp)")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        if args.warmup < 3:
+            args.warmup = 3
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -158,9 +158,10 @@ typedef struct asgart_b200_stats {
     double ms_h2d, ms_pack, ms_sa_build, ms_lut, ms_search, ms_automaton, ms_post, ms_d2h;
     /* kernel families inside them: accumulated device ms, launches and algorithmic bytes */
     double ms_sa_sort, ms_sa_gather, ms_sa_rank, ms_probe, ms_emit;
+    double ms_sa_scatter;          /* rs_scatter_kernel alone (the dominant kernel), inside ms_sa_sort */
     uint64_t launches_total;
-    uint64_t launches_sa_sort, launches_sa_gather, launches_probe;
-    uint64_t bytes_sa_sort, bytes_sa_gather, bytes_probe;
+    uint64_t launches_sa_sort, launches_sa_gather, launches_probe, launches_sa_scatter;
+    uint64_t bytes_sa_sort, bytes_sa_gather, bytes_probe, bytes_sa_scatter;
     /* counters of the last search */
     uint64_t n_probes, n_searched, n_skipped_n, n_skipped_card, n_matches, n_events, n_segments;
     uint64_t sa_rounds, sa_index_bits;
@@ -168,6 +169,9 @@ typedef struct asgart_b200_stats {
 } asgart_b200_stats;
 ASGART_B200_API int32_t asgart_b200_ctx_stats(const asgart_b200_ctx *ctx, asgart_b200_stats *out);
 ASGART_B200_API void asgart_b200_ctx_reset_stats(asgart_b200_ctx *ctx);
+/* a CUDA-event stopwatch on the library's stream, for timing a region of calls on the device */
+ASGART_B200_API int32_t asgart_b200_ctx_timer_start(asgart_b200_ctx *ctx);
+ASGART_B200_API int32_t asgart_b200_ctx_timer_stop(asgart_b200_ctx *ctx, double *elapsed_ms);
 
 /* ---- host side of the path (C++ mirror of prepare_data / SD conversion / JSON export) -------------------- */
 typedef struct asgart_b200_prepared asgart_b200_prepared;

@@ -175,7 +175,8 @@ def test_post_steps_unit_cases():
         assert keep.n_families == 1 and drop.n_families == 0            # 200/1000 <= 0.2 kept, 201/1000 dropped (f32)
         merged = ctx.post_steps(ab.families_from_lists([[(100, 2000, 500, 600), (400, 2300, 500, 450), (150, 2050, 100, 100)]]),
                                 ab.POST_REDUCE_OVERLAP)
-        assert [x[:4] for x in merged.as_lists()[0]] == [(100, 2000, 950, 800)]   # merge() with its mixed-up lengths (Q5)
+        # merge() with its mixed-up lengths (Q5): lsize = max(400+500, 100+600) - 100, rsize = max(2300+500, 2000+600) - 2000
+        assert [x[:4] for x in merged.as_lists()[0]] == [(100, 2000, 800, 800)]
         ro = ctx.post_steps(ab.families_from_lists([[(900, 100, 10, 20)]]), ab.POST_REORDER)
         assert [x[:4] for x in ro.as_lists()[0]] == [(100, 900, 10, 20)]          # positions only (Q4)
         fams = [[(50, 9, 1, 1), (10, 8, 1, 1), (50, 7, 1, 1), (10, 6, 1, 1)], [], [(3, 3, 3, 3)]]
