@@ -153,8 +153,8 @@ void build_index_t(asgart_b200_ctx* ctx) {
     tlut.start();
     build_lut<IdxT>(ctx);
     tlut.stop();
-    ctx->st.ms_sa_build = tsa.ms();
-    ctx->st.ms_lut = tlut.ms();
+    ctx->st.ms_sa_build += tsa.ms();
+    ctx->st.ms_lut += tlut.ms();
 }
 
 template <typename T>
@@ -583,8 +583,8 @@ int32_t asgart_b200_ctx_load_strand(asgart_b200_ctx* ctx, const uint8_t* T, int6
         u32 h_err = 0;
         CUDA_CHECK(cudaMemcpyAsync(&h_err, d_err.p, sizeof h_err, cudaMemcpyDeviceToHost, ctx->stream));
         CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-        ctx->st.ms_h2d = th.ms();
-        ctx->st.ms_pack = tp.ms();
+        ctx->st.ms_h2d += th.ms();
+        ctx->st.ms_pack += tp.ms();
         ctx->st.h2d_bytes += ctx->n1;
         if (h_err) return fail(ctx, ASGART_B200_EINVAL, "strand is not normalised: expected bytes in {A,C,G,N,T} followed by one '$'");
         ctx->have_strand = true;
