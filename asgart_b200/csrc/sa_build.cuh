@@ -86,59 +86,129 @@ __global__ void __launch_bounds__(kInitThreads) init_keys_kernel(const u8* __res
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// scan accumulator of the re-ranking passes: two running maxima (positions of the latest old / new group head) and
+// three running sums (compaction counters)
 template <typename IdxT>
-struct MaxCnt {
-    IdxT mx, cnt;
-    MaxCnt() = default;
-    __host__ __device__ explicit MaxCnt(int) : mx(0), cnt(0) {}
-    __host__ __device__ MaxCnt(IdxT m, IdxT c) : mx(m), cnt(c) {}
+struct RankAcc {
+    IdxT a, b, c, d, e;
+    RankAcc() = default;
+    __host__ __device__ explicit RankAcc(int) : a(0), b(0), c(0), d(0), e(0) {}
+    __host__ __device__ RankAcc(IdxT a_, IdxT b_, IdxT c_, IdxT d_, IdxT e_) : a(a_), b(b_), c(c_), d(d_), e(e_) {}
 };
-struct MaxCntOp {
-    template <typename T> __device__ __forceinline__ T operator()(const T& a, const T& b) const {
-        return T(a.mx > b.mx ? a.mx : b.mx, a.cnt + b.cnt);
-    }
-};
-template <typename IdxT>
-struct Max2Cnt {
-    IdxT cg, cs, cnt;
-    Max2Cnt() = default;
-    __host__ __device__ explicit Max2Cnt(int) : cg(0), cs(0), cnt(0) {}
-    __host__ __device__ Max2Cnt(IdxT a, IdxT b, IdxT c) : cg(a), cs(b), cnt(c) {}
-};
-struct Max2CntOp {
-    template <typename T> __device__ __forceinline__ T operator()(const T& a, const T& b) const {
-        return T(a.cg > b.cg ? a.cg : b.cg, a.cs > b.cs ? a.cs : b.cs, a.cnt + b.cnt);
+struct RankAccOp {
+    template <typename T> __device__ __forceinline__ T operator()(const T& x, const T& y) const {
+        return T(x.a > y.a ? x.a : y.a, x.b > y.b ? x.b : y.b, x.c + y.c, x.d + y.d, x.e + y.e);
     }
 };
 
-// composite (group, key2) keys
+// composite (group, key2) keys of the large-group radix path
 template <typename IdxT> struct CompKey;
 template <> struct CompKey<u32> {
     using type = u64;
     __device__ static __forceinline__ u64 make(u32 g, u32 k2, int kb) { return (u64(g) << kb) | u64(k2); }
-    __device__ static __forceinline__ u32 group(u64 k, int kb) { return u32(k >> kb); }
+    __device__ static __forceinline__ u32 key2(u64 k, int kb) { return u32(k & ((u64(1) << kb) - 1)); }
 };
 template <> struct CompKey<u64> {
     using type = U128;
     __device__ static __forceinline__ U128 make(u64 g, u64 k2, int) { return U128{g, k2}; }
-    __device__ static __forceinline__ u64 group(const U128& k, int) { return k.hi; }
+    __device__ static __forceinline__ u64 key2(const U128& k, int) { return k.lo; }
 };
 
+constexpr int kSmallGroup = 32;  // groups up to this size are sorted in place by one thread; larger ones go through radix passes
+
+// key2 = rank of the suffix D symbols further on (+1; 0 = past the end): the random gather of prefix doubling
 template <typename IdxT>
-__global__ void gather_rank_kernel(const IdxT* __restrict__ G, const IdxT* __restrict__ I, const IdxT* __restrict__ rank,
-                                   u64 U, u64 n, u64 h, int kb, typename CompKey<IdxT>::type* __restrict__ K) {
+__global__ void gather_rank_kernel(const IdxT* __restrict__ I, const IdxT* __restrict__ D, const IdxT* __restrict__ rank, u64 U, u64 n,
+                                   IdxT* __restrict__ K2) {
     const u64 stride = u64(gridDim.x) * blockDim.x;
     for (u64 c = u64(blockIdx.x) * blockDim.x + threadIdx.x; c < U; c += stride) {
-        const u64 p = u64(I[c]) + h;
-        const IdxT k2 = p < n ? IdxT(rank[p] + 1) : IdxT(0);
-        K[c] = CompKey<IdxT>::make(G[c], k2, kb);
+        const u64 p = u64(I[c]) + u64(D[c]);
+        K2[c] = p < n ? IdxT(rank[p] + 1) : IdxT(0);
     }
+}
+
+// one thread per group: groups of <= kSmallGroup suffixes are insertion-sorted by key2 in place, larger ones report
+// their size for the radix path
+template <typename IdxT>
+__global__ void small_group_sort_kernel(const IdxT* __restrict__ hs, u64 n_groups, u64 U, IdxT* __restrict__ K2, IdxT* __restrict__ I,
+                                        IdxT* __restrict__ large_sz) {
+    const u64 j = u64(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (j >= n_groups) return;
+    const u64 s = hs[j], m = (j + 1 < n_groups ? u64(hs[j + 1]) : U) - s;
+    if (m > kSmallGroup) { large_sz[j] = IdxT(m); return; }
+    large_sz[j] = 0;
+    for (u64 r = 1; r < m; ++r) {
+        const IdxT k = K2[s + r], v = I[s + r];
+        u64 w = r;
+        while (w > 0 && K2[s + w - 1] > k) { K2[s + w] = K2[s + w - 1]; I[s + w] = I[s + w - 1]; --w; }
+        if (w != r) { K2[s + w] = k; I[s + w] = v; }
+    }
+}
+
+// last j with arr[j] <= v   (arr non-decreasing, arr[0] <= v)
+template <typename IdxT>
+__device__ __forceinline__ u64 last_le(const IdxT* __restrict__ arr, u64 len, u64 v) {
+    u64 lo = 0, hi = len;
+    while (hi - lo > 1) {
+        const u64 mid = (lo + hi) >> 1;
+        if (u64(arr[mid]) <= v) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+template <typename IdxT>
+__global__ void large_copy_out_kernel(const IdxT* __restrict__ hs, const IdxT* __restrict__ large_sz, const IdxT* __restrict__ loff,
+                                      u64 n_groups, u64 U, const IdxT* __restrict__ K2,
+                                      const IdxT* __restrict__ I, int kb, typename CompKey<IdxT>::type* __restrict__ Lk, IdxT* __restrict__ Li) {
+    const u64 c = u64(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (c >= U) return;
+    const u64 j = last_le(hs, n_groups, c);
+    if (large_sz[j] == 0) return;
+    const u64 q = u64(loff[j]) + (c - u64(hs[j]));
+    // keyed on the group's ordinal in the list, not its head index: the list is grouped but not globally ordered by head
+    // (ordinary groups first, then the run groups), and the sorted elements are copied back in list order
+    Lk[q] = CompKey<IdxT>::make(IdxT(j), K2[c], kb);
+    Li[q] = I[c];
+}
+
+template <typename IdxT>
+__global__ void large_copy_back_kernel(const IdxT* __restrict__ hs, const IdxT* __restrict__ loff, u64 n_groups, u64 UL,
+                                       const typename CompKey<IdxT>::type* __restrict__ Lk, const IdxT* __restrict__ Li, int kb,
+                                       IdxT* __restrict__ K2, IdxT* __restrict__ I) {
+    const u64 q = u64(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (q >= UL) return;
+    const u64 j = last_le(loff, n_groups, q);  // the large group that owns slot q (last index of the plateau)
+    const u64 c = u64(hs[j]) + (q - u64(loff[j]));
+    K2[c] = CompKey<IdxT>::key2(Lk[q], kb);
+    I[c] = Li[q];
+}
+
+// secondary key of a suffix that starts a run of >= p0 equal symbols x: with r = run length left and c = the symbol after
+// the run, suffixes order by ascending r when c < x and by descending r, after all of those, when c > x.
+template <typename IdxT>
+__global__ void run_key_kernel(const u8* __restrict__ text, const uint16_t* __restrict__ code, const IdxT* __restrict__ E,
+                               const IdxT* __restrict__ GS, const IdxT* __restrict__ IS, u64 US, u64 n, int kb0, u64* __restrict__ K,
+                               IdxT* __restrict__ Gx) {
+    const u64 c = u64(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (c >= US) return;
+    const u64 i = IS[c], e = E[i], r = e - i;
+    const u32 x = code[text[i]];
+    const u32 cs = e < n ? code[text[e]] : 0u;
+    const u64 flag = cs > x ? 1 : 0;
+    const u64 val = flag ? (n - r) : r;
+    K[c] = (u64(x) << (kb0 + 1)) | (flag << kb0) | val;
+    Gx[x] = GS[c];  // every member of the pure-x group carries the same head index
 }
 
 template <typename IdxT>
 void build_suffix_array(const u8* d_text, u64 n, IdxT* d_sa, IdxT* d_rank, cudaStream_t stream, SaStats* st) {
     using KeyT = typename CompKey<IdxT>::type;
+    using Acc = RankAcc<IdxT>;
     if (n == 0) return;
+    auto sync_read = [&](void* dst, const void* src, size_t bytes) {
+        CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, stream));
+        CUDA_CHECK(cudaStreamSynchronize(stream));
+    };
 
     // ---- 0. alphabet
     DevBuf<unsigned long long> d_hist(256, stream);
@@ -150,8 +220,7 @@ void build_suffix_array(const u8* d_text, u64 n, IdxT* d_sa, IdxT* d_rank, cudaS
         count_launch();
     }
     unsigned long long h_hist[256];
-    CUDA_CHECK(cudaMemcpyAsync(h_hist, d_hist.p, sizeof h_hist, cudaMemcpyDeviceToHost, stream));
-    CUDA_CHECK(cudaStreamSynchronize(stream));
+    sync_read(h_hist, d_hist.p, sizeof h_hist);
     uint16_t h_code[256];
     int sigma = 0;
     for (int c = 0; c < 256; ++c) h_code[c] = h_hist[c] ? uint16_t(++sigma) : uint16_t(0);
@@ -159,11 +228,19 @@ void build_suffix_array(const u8* d_text, u64 n, IdxT* d_sa, IdxT* d_rank, cudaS
     const int p0 = 64 / b;
     DevBuf<uint16_t> d_code(256, stream);
     CUDA_CHECK(cudaMemcpyAsync(d_code.p, h_code, sizeof h_code, cudaMemcpyHostToDevice, stream));
+    u64 rep_unit = 0;  // sum of 2^(b*j): a key whose p0 symbols are all equal to c is c * rep_unit
+    for (int j = 0; j < p0; ++j) rep_unit |= u64(1) << (b * j);
+    const u64 sym_mask = (u64(1) << b) - 1;
 
-    // ---- 1. initial keys + sort
-    DevBuf<IdxT> Gbuf, Ibuf;
-    u64 U = 0;
-    DevBuf<IdxT> d_total_mc_store;  // unused placeholder to keep allocation order simple
+    // work list of the suffixes that are not yet unique: group head index, suffix, depth already compared, and the
+    // start of every group inside the list (groups are contiguous)
+    DevBuf<IdxT> Gw, Iw, Dw, HSw;
+    u64 U = 0, NG = 0;
+
+    // ---- 1. initial keys + sort, 2. heads -> rank, SA, work lists (ordinary groups A / single-symbol-run groups S)
+    DevBuf<IdxT> GS, IS;
+    u64 UA = 0, US = 0, NGA = 0;
+    DevBuf<IdxT> GA, IA, HSA;
     {
         DevBuf<u64> keysA(n, stream), keysB(n, stream);
         DevBuf<IdxT> valsA(n, stream), valsB(n, stream);
@@ -178,109 +255,215 @@ void build_suffix_array(const u8* d_text, u64 n, IdxT* d_sa, IdxT* d_rank, cudaS
         radix_sort_pairs<u64, IdxT>(k, ka, v, va, n, shifts.data(), int(shifts.size()), stream, st ? st->sort : nullptr,
                                     st ? st->scatter : nullptr);
 
-        // ---- 2. heads -> rank, SA, work list
-        using MC = MaxCnt<IdxT>;
-        DevBuf<MC> d_total(1, stream);
+        DevBuf<Acc> d_total(1, stream);
         const u64* kk = k;
         const IdxT* vv = v;
-        auto in = [kk, n] __device__(u64 i) {
+        auto in = [kk, n, rep_unit, sym_mask] __device__(u64 i) {
             const u64 cur = kk[i];
             const bool head = i == 0 || kk[i - 1] != cur;
             const bool tail = i + 1 == n || kk[i + 1] != cur;
-            return MC(head ? IdxT(i) : IdxT(0), (head && tail) ? IdxT(0) : IdxT(1));
+            const bool uns = !(head && tail);
+            const bool pure = cur == (cur & sym_mask) * rep_unit;
+            return Acc(head ? IdxT(i) : IdxT(0), IdxT(0), (uns && !pure) ? IdxT(1) : IdxT(0), (uns && pure) ? IdxT(1) : IdxT(0),
+                       (uns && !pure && head) ? IdxT(1) : IdxT(0));
         };
         if (st && st->rank) st->rank->begin();
-        ScanPlan<MC, MaxCntOp> plan;
+        ScanPlan<Acc, RankAccOp> plan;
         plan.prepare(in, n, d_total.p, stream);
-        MC h_total;
-        CUDA_CHECK(cudaMemcpyAsync(&h_total, d_total.p, sizeof(MC), cudaMemcpyDeviceToHost, stream));
-        CUDA_CHECK(cudaStreamSynchronize(stream));
-        U = u64(h_total.cnt);
-        Gbuf.alloc(U, stream);
-        Ibuf.alloc(U, stream);
-        IdxT *G = Gbuf.p, *I = Ibuf.p;
-        plan.finish(in, [kk, vv, n, d_rank, d_sa, G, I] __device__(u64 i, const MC& exc, const MC& inc) {
+        Acc tot;
+        sync_read(&tot, d_total.p, sizeof tot);
+        UA = u64(tot.c); US = u64(tot.d); NGA = u64(tot.e);
+        GA.alloc(UA, stream); IA.alloc(UA, stream); HSA.alloc(NGA, stream);
+        GS.alloc(US, stream); IS.alloc(US, stream);
+        IdxT *ga = GA.p, *ia = IA.p, *hsa = HSA.p, *gs = GS.p, *is = IS.p;
+        plan.finish(in, [=] __device__(u64 i, const Acc& exc, const Acc& inc) {
             const u64 cur = kk[i];
             const bool head = i == 0 || kk[i - 1] != cur;
             const bool tail = i + 1 == n || kk[i + 1] != cur;
             const IdxT idx = vv[i];
-            d_rank[idx] = inc.mx;
+            d_rank[idx] = inc.a;
             d_sa[i] = idx;
-            if (!(head && tail)) { G[exc.cnt] = inc.mx; I[exc.cnt] = idx; }
+            if (head && tail) return;
+            if (cur == (cur & sym_mask) * rep_unit) { gs[exc.d] = inc.a; is[exc.d] = idx; }
+            else {
+                ga[exc.c] = inc.a; ia[exc.c] = idx;
+                if (head) hsa[exc.e] = exc.c;
+            }
         });
         if (st && st->rank) st->rank->end(3, 0);
     }
 
-    // ---- 3. doubling rounds
-    const int kb = std::max(1, bit_width_u64(n));      // key2 in [0, n]
-    const int gb = std::max(1, bit_width_u64(n - 1));  // group head index in [0, n)
-    std::vector<int> shifts;
-    if (sizeof(IdxT) == 4) {
-        for (int s = 0; s < kb + gb; s += 8) shifts.push_back(s);
-    } else {
-        for (int s = 0; s < kb; s += 8) shifts.push_back(s);
-        for (int s = 0; s < gb; s += 8) shifts.push_back(64 + s);
+    // ---- 3. run round: suffixes starting a run of >= p0 equal symbols are ordered by (symbol after the run, run length)
+    // in one sort and then continue at depth = run length, instead of needing log2(run length) doubling rounds
+    DevBuf<IdxT> GS2, IS2, DS2, HSS2;
+    u64 US2 = 0, NGS2 = 0;
+    if (US > 0) {
+        if (st) st->rounds++;
+        DevBuf<IdxT> E(n, stream);
+        {
+            IdxT* ep = E.p;
+            const u8* tp = d_text;
+            device_scan<IdxT, MaxOp>(
+                [tp, n] __device__(u64 kx) { const u64 i = n - 1 - kx; return (i + 1 == n || tp[i] != tp[i + 1]) ? IdxT(kx + 1) : IdxT(0); },
+                [ep, n] __device__(u64 kx, IdxT, IdxT inc) { ep[n - 1 - kx] = IdxT(n - u64(inc) + 1); }, n, (IdxT*)nullptr, stream);
+        }
+        const int kb0 = std::max(1, bit_width_u64(n));
+        DevBuf<u64> KA(US, stream), KB(US, stream);
+        DevBuf<IdxT> IB(US, stream), Gx(sigma + 2, stream);
+        run_key_kernel<IdxT><<<unsigned(ceil_div(US, 256)), 256, 0, stream>>>(d_text, d_code.p, E.p, GS.p, IS.p, US, n, kb0, KA.p, Gx.p);
+        KERNEL_CHECK();
+        count_launch();
+        std::vector<int> shifts;
+        for (int s = 0; s < kb0 + 1 + bit_width_u64(u64(sigma)); s += 8) shifts.push_back(s);
+        u64 *k = KA.p, *ka = KB.p;
+        IdxT *v = IS.p, *va = IB.p;
+        radix_sort_pairs<u64, IdxT>(k, ka, v, va, US, shifts.data(), int(shifts.size()), stream, st ? st->sort : nullptr,
+                                    st ? st->scatter : nullptr);
+        DevBuf<Acc> d_total(1, stream);
+        const u64* kk = k;
+        const IdxT* vv = v;
+        const u64 USc = US;
+        auto in = [kk, USc, kb0] __device__(u64 c) {
+            const u64 cur = kk[c];
+            bool head_old = true, head_new = true, tail_new = true;
+            if (c > 0) { const u64 prev = kk[c - 1]; head_new = prev != cur; head_old = (prev >> (kb0 + 1)) != (cur >> (kb0 + 1)); }
+            if (c + 1 < USc) tail_new = kk[c + 1] != cur;
+            const bool surv = !(head_new && tail_new);
+            return Acc(head_old ? IdxT(c) : IdxT(0), head_new ? IdxT(c) : IdxT(0), surv ? IdxT(1) : IdxT(0),
+                       (surv && head_new) ? IdxT(1) : IdxT(0), IdxT(0));
+        };
+        if (st && st->rank) st->rank->begin();
+        ScanPlan<Acc, RankAccOp> plan;
+        plan.prepare(in, US, d_total.p, stream);
+        Acc tot;
+        sync_read(&tot, d_total.p, sizeof tot);
+        US2 = u64(tot.c); NGS2 = u64(tot.d);
+        GS2.alloc(US2, stream); IS2.alloc(US2, stream); DS2.alloc(US2, stream); HSS2.alloc(NGS2, stream);
+        IdxT *g2 = GS2.p, *i2 = IS2.p, *d2 = DS2.p, *hs2 = HSS2.p;
+        const IdxT* gx = Gx.p;
+        plan.finish(in, [=] __device__(u64 c, const Acc& exc, const Acc& inc) {
+            const u64 cur = kk[c];
+            const bool head_new = c == 0 || kk[c - 1] != cur;
+            const bool tail_new = c + 1 == USc || kk[c + 1] != cur;
+            const IdxT g = gx[cur >> (kb0 + 1)];
+            const IdxT idx = vv[c];
+            const IdxT ng = g + (inc.b - inc.a);
+            d_rank[idx] = ng;
+            if (head_new && tail_new) { d_sa[u64(g) + (c - u64(inc.a))] = idx; return; }
+            const u64 val = cur & ((u64(1) << kb0) - 1);
+            const u64 r = ((cur >> kb0) & 1) ? (n - val) : val;
+            g2[exc.c] = ng; i2[exc.c] = idx; d2[exc.c] = IdxT(r);
+            if (head_new) hs2[exc.d] = exc.c;
+        });
+        if (st && st->rank) st->rank->end(3, 0);
     }
-    u64 h = u64(p0);
+    GS.release(); IS.release();
+
+    // ---- 4. merged work list: ordinary groups at depth p0, then the run groups at depth = run length
+    U = UA + US2; NG = NGA + NGS2;
+    if (U > 0) {
+        Gw.alloc(U, stream); Iw.alloc(U, stream); Dw.alloc(U, stream); HSw.alloc(NG, stream);
+        IdxT *gw = Gw.p, *iw = Iw.p, *dw = Dw.p, *hw = HSw.p;
+        const IdxT *ga = GA.p, *ia = IA.p, *hsa = HSA.p, *g2 = GS2.p, *i2 = IS2.p, *d2 = DS2.p, *hs2 = HSS2.p;
+        const u64 UAc = UA, NGAc = NGA, NGc = NG;
+        const IdxT p0i = IdxT(p0);
+        for_each_index(U, [=] __device__(u64 c) {
+            if (c < UAc) { gw[c] = ga[c]; iw[c] = ia[c]; dw[c] = p0i; }
+            else { gw[c] = g2[c - UAc]; iw[c] = i2[c - UAc]; dw[c] = d2[c - UAc]; }
+            if (c < NGc) hw[c] = c < NGAc ? hsa[c] : IdxT(u64(hs2[c - NGAc]) + UAc);
+        }, stream);
+    }
+    GA.release(); IA.release(); HSA.release(); GS2.release(); IS2.release(); DS2.release(); HSS2.release();
+
+    // ---- 5. doubling rounds: every suffix of the list looks D symbols ahead, where D >= H symbols are already known
+    // to be equal inside its group and rank[] orders all suffixes by at least their first H symbols
+    const int kb = std::max(1, bit_width_u64(n));  // key2 in [0, n]
+    u64 H = u64(p0);
     while (U > 0) {
         if (st) st->rounds++;
-        DevBuf<KeyT> KA(U, stream), KB(U, stream);
-        DevBuf<IdxT> IB(U, stream);
+        DevBuf<IdxT> K2(U, stream), large_sz(NG, stream), loff(NG + 1, stream);
         {
             if (st && st->gather) st->gather->begin();
             int blocks = int(std::min<u64>(ceil_div(U, 256), u64(kNumSMs) * 16));
-            gather_rank_kernel<IdxT><<<blocks, 256, 0, stream>>>(Gbuf.p, Ibuf.p, d_rank, U, n, h, kb, KA.p);
+            gather_rank_kernel<IdxT><<<blocks, 256, 0, stream>>>(Iw.p, Dw.p, d_rank, U, n, K2.p);
             KERNEL_CHECK();
             count_launch();
             if (st && st->gather) st->gather->end(1, U * 3 * sizeof(IdxT));
         }
-        KeyT *k = KA.p, *ka = KB.p;
-        IdxT *v = Ibuf.p, *va = IB.p;
-        radix_sort_pairs<KeyT, IdxT>(k, ka, v, va, U, shifts.data(), int(shifts.size()), stream, st ? st->sort : nullptr,
-                                     st ? st->scatter : nullptr);
-
-        using M2 = Max2Cnt<IdxT>;
-        DevBuf<M2> d_total(1, stream);
-        const KeyT* kk = k;
-        const IdxT* vv = v;
-        const u64 Uc = U;
-        auto in = [kk, Uc, kb] __device__(u64 c) {
-            const KeyT cur = kk[c];
-            bool head_new = true, head_old = true, tail_new = true;
-            if (c > 0) {
-                const KeyT prev = kk[c - 1];
-                head_new = prev != cur;
-                head_old = CompKey<IdxT>::group(prev, kb) != CompKey<IdxT>::group(cur, kb);
+        if (st && st->rank) st->rank->begin();
+        small_group_sort_kernel<IdxT><<<unsigned(ceil_div(NG, 128)), 128, 0, stream>>>(HSw.p, NG, U, K2.p, Iw.p, large_sz.p);
+        KERNEL_CHECK();
+        count_launch();
+        u64 UL = 0;
+        {
+            const IdxT* lz = large_sz.p;
+            IdxT* lo = loff.p;
+            device_scan<IdxT, SumOp>([lz] __device__(u64 j) { return lz[j]; }, [lo] __device__(u64 j, IdxT exc, IdxT) { lo[j] = exc; }, NG,
+                                     loff.p + NG, stream);
+            IdxT h_ul = 0;
+            sync_read(&h_ul, loff.p + NG, sizeof h_ul);
+            UL = u64(h_ul);
+        }
+        if (st && st->rank) st->rank->end(4, 0);
+        if (UL > 0) {
+            DevBuf<KeyT> LA(UL, stream), LB(UL, stream);
+            DevBuf<IdxT> LIA(UL, stream), LIB(UL, stream);
+            large_copy_out_kernel<IdxT><<<unsigned(ceil_div(U, 256)), 256, 0, stream>>>(HSw.p, large_sz.p, loff.p, NG, U, K2.p, Iw.p, kb, LA.p,
+                                                                                        LIA.p);
+            KERNEL_CHECK();
+            const int jb = std::max(1, bit_width_u64(NG - 1));  // group ordinal in [0, NG)
+            std::vector<int> shifts;
+            if (sizeof(IdxT) == 4) {
+                for (int s = 0; s < kb + jb; s += 8) shifts.push_back(s);
+            } else {
+                for (int s = 0; s < kb; s += 8) shifts.push_back(s);
+                for (int s = 0; s < jb; s += 8) shifts.push_back(64 + s);
             }
-            if (c + 1 < Uc) tail_new = kk[c + 1] != cur;
-            return M2(head_old ? IdxT(c) : IdxT(0), head_new ? IdxT(c) : IdxT(0), (head_new && tail_new) ? IdxT(0) : IdxT(1));
+            KeyT *k = LA.p, *ka = LB.p;
+            IdxT *v = LIA.p, *va = LIB.p;
+            radix_sort_pairs<KeyT, IdxT>(k, ka, v, va, UL, shifts.data(), int(shifts.size()), stream, st ? st->sort : nullptr,
+                                         st ? st->scatter : nullptr);
+            large_copy_back_kernel<IdxT><<<unsigned(ceil_div(UL, 256)), 256, 0, stream>>>(HSw.p, loff.p, NG, UL, k, v, kb, K2.p, Iw.p);
+            KERNEL_CHECK();
+            count_launch(2);
+        }
+
+        DevBuf<Acc> d_total(1, stream);
+        const IdxT *gg = Gw.p, *k2 = K2.p, *ii = Iw.p, *dd = Dw.p;
+        const u64 Uc = U;
+        auto in = [gg, k2, Uc] __device__(u64 c) {
+            const IdxT g = gg[c], kv = k2[c];
+            bool head_old = true, head_new = true, tail_new = true;
+            if (c > 0) { head_old = gg[c - 1] != g; head_new = head_old || k2[c - 1] != kv; }
+            if (c + 1 < Uc) tail_new = gg[c + 1] != g || k2[c + 1] != kv;
+            const bool surv = !(head_new && tail_new);
+            return Acc(head_old ? IdxT(c) : IdxT(0), head_new ? IdxT(c) : IdxT(0), surv ? IdxT(1) : IdxT(0),
+                       (surv && head_new) ? IdxT(1) : IdxT(0), IdxT(0));
         };
         if (st && st->rank) st->rank->begin();
-        ScanPlan<M2, Max2CntOp> plan;
+        ScanPlan<Acc, RankAccOp> plan;
         plan.prepare(in, U, d_total.p, stream);
-        M2 h_total;
-        CUDA_CHECK(cudaMemcpyAsync(&h_total, d_total.p, sizeof(M2), cudaMemcpyDeviceToHost, stream));
-        CUDA_CHECK(cudaStreamSynchronize(stream));
-        const u64 U2 = u64(h_total.cnt);
-        DevBuf<IdxT> G2(U2, stream), I2(U2, stream);
-        IdxT *g2 = G2.p, *i2 = I2.p;
-        plan.finish(in, [kk, vv, Uc, kb, d_rank, d_sa, g2, i2] __device__(u64 c, const M2& exc, const M2& inc) {
-            const KeyT cur = kk[c];
-            const bool head_new = c == 0 || kk[c - 1] != cur;
-            const bool tail_new = c + 1 == Uc || kk[c + 1] != cur;
-            const IdxT g = CompKey<IdxT>::group(cur, kb);
-            const IdxT idx = vv[c];
-            const IdxT ng = g + (inc.cs - inc.cg);
+        Acc tot;
+        sync_read(&tot, d_total.p, sizeof tot);
+        const u64 U2 = u64(tot.c), NG2 = u64(tot.d);
+        DevBuf<IdxT> G2(U2, stream), I2(U2, stream), D2(U2, stream), HS2(NG2, stream);
+        IdxT *g2 = G2.p, *i2 = I2.p, *d2 = D2.p, *hs2 = HS2.p;
+        const IdxT Hi = IdxT(H);
+        plan.finish(in, [=] __device__(u64 c, const Acc& exc, const Acc& inc) {
+            const IdxT g = gg[c], kv = k2[c];
+            const bool head_new = c == 0 || gg[c - 1] != g || k2[c - 1] != kv;
+            const bool tail_new = c + 1 == Uc || gg[c + 1] != g || k2[c + 1] != kv;
+            const IdxT idx = ii[c];
+            const IdxT ng = g + (inc.b - inc.a);
             d_rank[idx] = ng;
-            if (head_new && tail_new) d_sa[u64(g) + (c - u64(inc.cg))] = idx;
-            else { g2[exc.cnt] = ng; i2[exc.cnt] = idx; }
+            if (head_new && tail_new) { d_sa[u64(g) + (c - u64(inc.a))] = idx; return; }
+            g2[exc.c] = ng; i2[exc.c] = idx; d2[exc.c] = dd[c] + Hi;
+            if (head_new) hs2[exc.d] = exc.c;
         });
         if (st && st->rank) st->rank->end(3, 0);
-        // v may point at Ibuf or IB; both are released when replaced / at scope end (stream-ordered)
-        Gbuf = std::move(G2);
-        Ibuf = std::move(I2);
-        U = U2;
-        h <<= 1;
+        Gw = std::move(G2); Iw = std::move(I2); Dw = std::move(D2); HSw = std::move(HS2);
+        U = U2; NG = NG2;
+        H <<= 1;
     }
 }
 

@@ -1,6 +1,8 @@
 // scan.cuh — device-wide scans (reduce-then-scan, three launches, no inter-block spinning).
 // Input and output go through functors so flag extraction / scatter can be fused into the scan passes.
 #pragma once
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace ab200 {
@@ -134,6 +136,21 @@ void device_scan(InFn in, OutFn out, u64 n, T* d_total, cudaStream_t stream, Op 
     scan_final_kernel<T, Op, InFn, OutFn><<<unsigned(tiles), kScanThreads, 0, stream>>>(in, n, sums.p, out, op);
     KERNEL_CHECK();
     count_launch(3);
+}
+
+// plain element-wise pass: f(i) for i in [0, n)
+template <typename F>
+__global__ void for_each_index_kernel(u64 n, F f) {
+    const u64 stride = u64(gridDim.x) * blockDim.x;
+    for (u64 i = u64(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) f(i);
+}
+template <typename F>
+void for_each_index(u64 n, F f, cudaStream_t stream) {
+    if (n == 0) return;
+    const unsigned blocks = unsigned(std::min<u64>(ceil_div(n, 256), u64(kNumSMs) * 32));
+    for_each_index_kernel<F><<<blocks, 256, 0, stream>>>(n, f);
+    KERNEL_CHECK();
+    count_launch();
 }
 
 // Two-phase form: prepare() computes the tile prefixes and the grand total (so the caller can size the outputs

@@ -74,6 +74,36 @@ def test_sa_medium_with_repeats(bits):
     assert got[0] == len(strand) - 1
 
 
+@pytest.mark.parametrize("bits,scale", [(32, 3_000_000), (64, 600_000)])
+def test_sa_soft_masked_genome(bits, scale):
+    """C2-shaped input with -S: thousands of N-runs of assorted lengths (the run round and the large-group path of the
+    doubling rounds), telomeric runs touching both ends of the strand, planted exact repeats."""
+    g, fr = ab.synth_genome(2, scale_n=scale)
+    strand = np.concatenate([ab.normalise(g, True), np.frombuffer(b"$", dtype=np.uint8)])
+    got = ab.r_divsufsort(strand, device=0, index_bits=bits)
+    want = oracle.best_suffix_array(strand) if (oracle.ref() is not None or scale <= 600_000) else None
+    assert np.array_equal(got, want)
+    # same genome without masking (upper-cased): only the long N-runs remain
+    strand2 = np.concatenate([ab.normalise(g, False), np.frombuffer(b"$", dtype=np.uint8)])
+    assert np.array_equal(ab.r_divsufsort(strand2, device=0, index_bits=bits), oracle.best_suffix_array(strand2))
+
+
+def test_sa_runs_of_every_symbol():
+    """Runs longer than the initial key of several symbols, followed by smaller and by larger symbols, and a run that
+    reaches the end of the text (no terminator)."""
+    rng = np.random.default_rng(9)
+    parts = []
+    for _ in range(300):
+        x = b"ACGNT"[int(rng.integers(0, 5))]
+        parts.append(np.full(int(rng.integers(1, 120)), x, dtype=np.uint8))
+        parts.append(kat.rand_dna(rng, int(rng.integers(1, 40))))
+    t = np.concatenate(parts + [np.full(77, ord("T"), dtype=np.uint8)])
+    for bits in (32, 64):
+        assert np.array_equal(ab.r_divsufsort(t, device=0, index_bits=bits), oracle.best_suffix_array(t))
+    t2 = np.concatenate([t, np.frombuffer(b"$", dtype=np.uint8)])
+    assert np.array_equal(ab.r_divsufsort(t2), oracle.best_suffix_array(t2))
+
+
 # ------------------------------------------------------------------------------------------------ LUT + probes
 def _slot_of_key(k):
     digit = {ord("A"): 0, ord("C"): 1, ord("G"): 2, ord("N"): 3, ord("T"): 4}
