@@ -289,24 +289,23 @@ void run_stage_a(asgart_b200_ctx* ctx, const ChunkPlan& plan, const asgart_b200_
     A.ev_probe.alloc(A.n_events, s); A.ev_cnt.alloc(A.n_events, s); A.ev_moff.alloc(A.n_events, s);
     A.matches.alloc(A.n_matches, s);
     {
-        u64* ev_probe = A.ev_probe.p; u32* ev_cnt = A.ev_cnt.p; u64* ev_moff = A.ev_moff.p; u64* matches = A.matches.p;
-        const IdxT* lo = out_lo.p; const IdxT* raw = out_raw.p; const IdxT* SA = ix.sa.p;
-        const ChunkDev* chunks = plan.dev.p; const u32 n_chunks = u32(plan.host.size());
-        const u32 sstep = plan.s; const bool rev = st->reverse != 0;
+        DevBuf<IdxT> ev_lo(A.n_events, s), ev_raw(A.n_events, s);
+        u64* ev_probe = A.ev_probe.p; u32* ev_cnt = A.ev_cnt.p; u64* ev_moff = A.ev_moff.p;
+        IdxT* elo = ev_lo.p; IdxT* eraw = ev_raw.p;
+        const IdxT* lo = out_lo.p; const IdxT* raw = out_raw.p;
         scan.finish(in, [=] __device__(u64 o, const Sum2& exc, const Sum2&) {
             const u32 v = surv[o];
             if (!v) return;
-            const u64 g = p_begin + o;
-            ev_probe[exc.b] = g; ev_cnt[exc.b] = v; ev_moff[exc.b] = exc.a;
-            const ChunkDev ch = chunks[chunk_of_probe(chunks, n_chunks, g)];
-            const u64 i = (g - ch.probe_base + 1) * sstep;
-            const u64 b = u64(lo[o]), e = b + u64(raw[o]);
-            u64 w = exc.a;
-            for (u64 j = b; j < e; ++j) {
-                const u64 x = u64(SA[j]);
-                if (match_survives(x, i, ch.c0, ch.len, rev)) matches[w++] = x;
-            }
+            ev_probe[exc.b] = p_begin + o; ev_cnt[exc.b] = v; ev_moff[exc.b] = exc.a;
+            elo[exc.b] = lo[o]; eraw[exc.b] = raw[o];
         });
+        if (A.n_events) {
+            emit_matches_kernel<IdxT><<<unsigned(ceil_div(A.n_events * 32, 256)), 256, 0, s>>>(
+                ix.sa.p, A.ev_probe.p, A.ev_moff.p, ev_lo.p, ev_raw.p, A.n_events, plan.dev.p, u32(plan.host.size()), plan.s,
+                st->reverse ? 1 : 0, A.matches.p);
+            KERNEL_CHECK();
+            count_launch();
+        }
     }
     ctx->t_emit.end(3, 0);
 }
@@ -427,7 +426,7 @@ void run_stage_b(asgart_b200_ctx* ctx, const ChunkPlan& plan, const asgart_b200_
         DevBuf<i64> op_target(n_matches, s);
         DevBuf<u64> a_ls(n_matches, s), a_le(n_matches, s), a_rs(n_matches, s), a_re(n_matches, s), a_death(n_matches, s);
         DevBuf<u32> act_arm(n_matches, s);
-        DevBuf<u64> act_rs(n_matches, s), act_re(n_matches, s), act_death(n_matches, s);
+        DevBuf<u64> act_rs(n_matches, s), act_re(n_matches, s), act_death(n_matches, s), act_ls(n_matches, s);
         DevBuf<i64> act_thr(n_matches, s);
         DevBuf<asgart_b200_protosd> out_sd(n_matches, s);
         DevBuf<u8> out_flag(n_matches, s);
@@ -436,13 +435,19 @@ void run_stage_b(asgart_b200_ctx* ctx, const ChunkPlan& plan, const asgart_b200_
         B.ev_i = ev_i.p; B.ev_t = ev_t.p; B.ev_moff = ev_moff; B.ev_cnt = ev_cnt; B.ev_chunk = ev_chunk.p;
         B.seg_first = seg_first.p; B.matches = matches; B.op_target = op_target.p;
         B.a_ls = a_ls.p; B.a_le = a_le.p; B.a_rs = a_rs.p; B.a_re = a_re.p; B.a_death = a_death.p;
-        B.act_arm = act_arm.p; B.act_rs = act_rs.p; B.act_re = act_re.p; B.act_thr = act_thr.p; B.act_death = act_death.p;
+        B.act_arm = act_arm.p; B.act_ls = act_ls.p; B.act_rs = act_rs.p; B.act_re = act_re.p; B.act_thr = act_thr.p; B.act_death = act_death.p;
         B.out_sd = out_sd.p; B.out_flag = out_flag.p; B.chunk_tc = tc.p; B.chunks = plan.dev.p;
         if (getenv("ASGART_B200_AUTOMATON_V1"))  // thread-per-segment reference kernel, kept for A/B checks
             automaton_kernel<<<unsigned(ceil_div(n_seg, 64)), 64, 0, s>>>(B, plan.ap, n_seg, st->reverse ? 1 : 0, st->complement ? 1 : 0);
-        else
-            automaton_warp_kernel<<<unsigned(ceil_div(n_seg * 32, 128)), 128, 0, s>>>(B, plan.ap, n_seg, st->reverse ? 1 : 0,
-                                                                                     st->complement ? 1 : 0);
+        else {
+            // light segments: one warp each; heavy segments: one 8-warp block each (every block checks which launch owns it)
+            automaton_segment_kernel<1, kActCapLight><<<unsigned(n_seg), 32, 0, s>>>(B, plan.ap, n_seg, n_matches, n_events,
+                                                                                     st->reverse ? 1 : 0, st->complement ? 1 : 0);
+            KERNEL_CHECK();
+            automaton_segment_kernel<kHeavyWarps, kActCapHeavy><<<unsigned(n_seg), kHeavyWarps * 32, 0, s>>>(
+                B, plan.ap, n_seg, n_matches, n_events, st->reverse ? 1 : 0, st->complement ? 1 : 0);
+            count_launch();
+        }
         KERNEL_CHECK();
         count_launch();
         // compaction into CSR families

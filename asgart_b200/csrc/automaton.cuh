@@ -55,6 +55,7 @@ struct AutoBuffers {
     u64 *a_ls, *a_le, *a_rs, *a_re, *a_death;  // arm store, indexed like matches
     // active list of the warp kernel (arms that can still be extended), same capacity, creation order preserved
     u32* act_arm;   // index into the segment's arm store
+    u64* act_ls;
     u64* act_rs;
     u64* act_re;
     i64* act_thr;   // max(G, trunc(0.1 * left length)), refreshed when the arm is extended
@@ -97,25 +98,97 @@ __global__ void automaton_kernel(AutoBuffers B, AutoParams P, u64 n_segments, u3
 //   phase 3  NewArm ops appended in match order (ballot + prefix popcount)                                   :145-163
 // Arms that can no longer be extended (death < t) are dropped from the active list by an order-preserving warp
 // compaction; the arm store keeps every arm of the open family for the flush (:182-200).
-__global__ void __launch_bounds__(128) automaton_warp_kernel(AutoBuffers B, AutoParams P, u64 n_segments, u32 reversed_flag,
-                                                             u32 complemented_flag) {
-    const u64 sidx = (u64(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-    if (sidx >= n_segments) return;  // whole warps leave together
+// The critical path is the longest segment (a 50 kbp duplication = 5000 events in sequence), so per-event latency is
+// what matters: the active list lives in shared memory (it moves to its global slice only beyond kActCap arms, until
+// the next flush), and the first match of every event is prefetched together with the batch of 32 event records.
+// Segments whose matches add up to kHeavySegment or more get a whole block of kHeavyWarps warps: warp 0 runs the event loop
+// exactly as in the one-warp case and wakes the helper warps (named barriers 1/2) only for events whose
+// matches x active-arms product is large; phase 1 of such an event is then spread over all warps.
+constexpr int kActCapLight = 128;
+constexpr int kActCapHeavy = 768;
+constexpr int kHeavyWarps = 8;
+constexpr u64 kHeavySegment = 512;
+constexpr u64 kHeavyEvent = 4096;  // cnt * active arms
+
+struct AutoCmd {
+    u64 t, m0, snap;
+    u32 cnt, op;  // op: 1 = classify matches, 0 = exit
+    u32 in_smem;
+};
+
+template <int W, int CAP>
+__global__ void __launch_bounds__(W * 32) automaton_segment_kernel(AutoBuffers B, AutoParams P, u64 n_segments, u64 n_matches, u64 n_events,
+                                                                   u32 reversed_flag, u32 complemented_flag) {
+    __shared__ u64 s_rs[CAP], s_re[CAP], s_ls[CAP], s_death[CAP];
+    __shared__ i64 s_thr[CAP];
+    __shared__ u32 s_arm[CAP];
+    __shared__ AutoCmd s_cmd;
+    const u64 sidx = blockIdx.x;
+    if (sidx >= n_segments) return;
+    const u64 e0 = B.seg_first[sidx], e1 = B.seg_first[sidx + 1];
+    const u64 slot0 = B.ev_moff[e0];
+    const u64 seg_matches = (e1 < n_events ? B.ev_moff[e1] : n_matches) - slot0;
+    if ((W > 1) != (seg_matches >= kHeavySegment)) return;  // the other launch owns this segment (whole block leaves)
     const unsigned lane = lane_id();
+    const unsigned warp = threadIdx.x >> 5;
     const unsigned lt = lanemask_lt();
     const unsigned FULL = 0xffffffffu;
-    const u64 e0 = B.seg_first[sidx], e1 = B.seg_first[sidx + 1];
+    const u64* matches = B.matches;
+    i64* op_target = B.op_target;
+    u32* g_arm = B.act_arm + slot0; u64* g_rs = B.act_rs + slot0; u64* g_re = B.act_re + slot0; u64* g_ls = B.act_ls + slot0;
+    i64* g_thr = B.act_thr + slot0; u64* g_death = B.act_death + slot0;
+
+    // classify matches [r_begin, cnt) step r_step*32 of one event against the snapshot of the active list
+    auto classify = [&](u64 t, u64 m0, u32 cnt, u64 snap, bool smem, u32 w_first, u32 w_step) {
+        const u64* c_rs = smem ? s_rs : g_rs; const u64* c_re = smem ? s_re : g_re;
+        const i64* c_thr = smem ? s_thr : g_thr; const u64* c_death = smem ? s_death : g_death;
+        for (u32 r0 = w_first * 32; r0 < cnt; r0 += w_step * 32) {
+            const u32 r = r0 + lane;
+            const bool valid = r < cnt;
+            const u64 ms = valid ? matches[m0 + r] : 0, me = ms + P.k;
+            i64 target = -1;
+            bool searching = valid;
+            for (u64 a = 0; a < snap; ++a) {
+                if (__ballot_sync(FULL, searching) == 0) break;
+                const u64 re = c_re[a];
+                if (searching && c_death[a] >= t && me > re && d_ss_core(c_rs[a], re, ms, me) < c_thr[a]) { target = i64(a); searching = false; }
+            }
+            if (valid) op_target[m0 + r] = target;
+        }
+    };
+
+    if (W > 1 && warp > 0) {  // helper warps
+        for (;;) {
+            asm volatile("bar.sync 1, %0;" ::"r"(W * 32));
+            const AutoCmd cmd = s_cmd;
+            if (cmd.op == 0) return;
+            classify(cmd.t, cmd.m0, cmd.cnt, cmd.snap, cmd.in_smem != 0, warp, W);
+            asm volatile("bar.sync 2, %0;" ::"r"(W * 32));
+        }
+    }
+
+    // ---- warp 0: the event loop
     const u32 c = B.ev_chunk[e0];
     const ChunkDev ch = B.chunks[c];
     const u64 Tc = B.chunk_tc[c];
-    const u64 slot0 = B.ev_moff[e0];
     u64* a_ls = B.a_ls + slot0; u64* a_le = B.a_le + slot0; u64* a_rs = B.a_rs + slot0; u64* a_re = B.a_re + slot0;
-    u32* act_arm = B.act_arm + slot0; u64* act_rs = B.act_rs + slot0; u64* act_re = B.act_re + slot0;
-    i64* act_thr = B.act_thr + slot0; u64* act_death = B.act_death + slot0;
-    i64* op_target = B.op_target;
-    const u64* matches = B.matches;
+    u32* act_arm = s_arm; u64* act_rs = s_rs; u64* act_re = s_re; u64* act_ls = s_ls; i64* act_thr = s_thr; u64* act_death = s_death;
+    bool in_smem = true;
     u64 n_arms = 0, fam_start = 0, n_act = 0, max_death = 0, act_min_death = ~u64(0), cursor = slot0;
     const i64 Gi = i64(P.G);
+
+    auto to_smem = [&]() {
+        act_arm = s_arm; act_rs = s_rs; act_re = s_re; act_ls = s_ls; act_thr = s_thr; act_death = s_death;
+        in_smem = true;
+    };
+    auto to_global = [&]() {  // copy the live entries to the segment's global slice and continue there
+        for (u64 a = lane; a < n_act; a += 32) {
+            g_arm[a] = act_arm[a]; g_rs[a] = act_rs[a]; g_re[a] = act_re[a]; g_ls[a] = act_ls[a]; g_thr[a] = act_thr[a]; g_death[a] = act_death[a];
+        }
+        act_arm = g_arm; act_rs = g_rs; act_re = g_re; act_ls = g_ls; act_thr = g_thr; act_death = g_death;
+        in_smem = false;
+        __syncwarp();
+    };
 
     auto flush = [&]() {
         bool first = true;
@@ -143,6 +216,7 @@ __global__ void __launch_bounds__(128) automaton_warp_kernel(AutoBuffers B, Auto
         n_act = 0;
         max_death = 0;
         act_min_death = ~u64(0);
+        to_smem();
         __syncwarp();
     };
 
@@ -150,17 +224,17 @@ __global__ void __launch_bounds__(128) automaton_warp_kernel(AutoBuffers B, Auto
         u64 w = 0, mn = ~u64(0);
         for (u64 base = 0; base < n_act; base += 32) {
             const u64 a = base + lane;
-            u32 arm = 0; u64 rs = 0, re = 0, death = 0; i64 thr = 0;
+            u32 arm = 0; u64 rs = 0, re = 0, ls = 0, death = 0; i64 thr = 0;
             bool keep = false;
             if (a < n_act) {
-                arm = act_arm[a]; rs = act_rs[a]; re = act_re[a]; thr = act_thr[a]; death = act_death[a];
+                arm = act_arm[a]; rs = act_rs[a]; re = act_re[a]; ls = act_ls[a]; thr = act_thr[a]; death = act_death[a];
                 keep = death >= t;
             }
             const unsigned m = __ballot_sync(FULL, keep);
             __syncwarp();  // all reads of this block of 32 done before anyone overwrites (w <= base)
             if (keep) {
                 const u64 d = w + __popc(m & lt);
-                act_arm[d] = arm; act_rs[d] = rs; act_re[d] = re; act_thr[d] = thr; act_death[d] = death;
+                act_arm[d] = arm; act_rs[d] = rs; act_re[d] = re; act_ls[d] = ls; act_thr[d] = thr; act_death[d] = death;
                 mn = death < mn ? death : mn;
             }
             w += __popc(m);
@@ -173,35 +247,83 @@ __global__ void __launch_bounds__(128) automaton_warp_kernel(AutoBuffers B, Auto
     };
 
     for (u64 eb = e0; eb < e1; eb += 32) {
-        u64 my_t = 0, my_i = 0, my_moff = 0; u32 my_cnt = 0;
-        if (eb + lane < e1) { my_t = B.ev_t[eb + lane]; my_i = B.ev_i[eb + lane]; my_moff = B.ev_moff[eb + lane]; my_cnt = B.ev_cnt[eb + lane]; }
+        u64 my_t = 0, my_i = 0, my_moff = 0, my_m0 = 0; u32 my_cnt = 0;
+        if (eb + lane < e1) {
+            my_t = B.ev_t[eb + lane]; my_i = B.ev_i[eb + lane]; my_moff = B.ev_moff[eb + lane]; my_cnt = B.ev_cnt[eb + lane];
+            my_m0 = matches[my_moff];
+        }
         const int nev = int(min(u64(32), e1 - eb));
         for (int j = 0; j < nev; ++j) {
             const u64 t = __shfl_sync(FULL, my_t, j), i = __shfl_sync(FULL, my_i, j), m0 = __shfl_sync(FULL, my_moff, j);
+            const u64 first_ms = __shfl_sync(FULL, my_m0, j);
             const u32 cnt = __shfl_sync(FULL, my_cnt, j);
             if (n_arms > fam_start && max_death < t) flush();
             if (n_act > 0 && act_min_death < t) compact(t);
+            if (in_smem && n_act + cnt > CAP) to_global();
+            if (cnt == 1) {
+                // fast path (9 events in 10): one match, lanes = active arms, first hit in creation order by ballot
+                const u64 ms = first_ms, me = ms + P.k;
+                i64 target = -1;
+                for (u64 base = 0; base < n_act; base += 32) {
+                    const u64 a = base + lane;
+                    bool hit = false;
+                    if (a < n_act) {
+                        const u64 re = act_re[a];
+                        hit = act_death[a] >= t && me > re && d_ss_core(act_rs[a], re, ms, me) < act_thr[a];
+                    }
+                    const unsigned m = __ballot_sync(FULL, hit);
+                    if (m) { target = i64(base) + (__ffs(m) - 1); break; }
+                }
+                if (target >= 0) {
+                    if (lane == 0) {
+                        const u64 a = u64(target);
+                        const u32 arm = act_arm[a];
+                        const u64 le = i + P.k;
+                        a_le[arm] = le; a_re[arm] = me;
+                        act_re[a] = me;
+                        const i64 tenth = i64(0.1 * double(le - act_ls[a]));  // src/automaton.rs:69
+                        act_thr[a] = Gi > tenth ? Gi : tenth;
+                        act_death[a] = t + P.q_ext;
+                    }
+                    if (t + P.q_ext > max_death) max_death = t + P.q_ext;
+                } else {
+                    if (lane == 0) {
+                        a_ls[n_arms] = i; a_le[n_arms] = i + P.k; a_rs[n_arms] = ms; a_re[n_arms] = me;
+                        act_arm[n_act] = u32(n_arms); act_rs[n_act] = ms; act_re[n_act] = me; act_ls[n_act] = i;
+                        const i64 tenth = i64(0.1 * double(P.k));
+                        act_thr[n_act] = Gi > tenth ? Gi : tenth;
+                        act_death[n_act] = t + P.q_new;
+                    }
+                    ++n_arms; ++n_act;
+                    if (t + P.q_new > max_death) max_death = t + P.q_new;
+                    if (t + P.q_new < act_min_death) act_min_death = t + P.q_new;
+                }
+                __syncwarp();
+                continue;
+            }
             const u64 snap = n_act;
             const bool single = cnt <= 32;
             i64 my_target = -1;
             u64 my_ms = 0;
             // phase 1
-            for (u32 r0 = 0; r0 < cnt; r0 += 32) {
-                const u32 r = r0 + lane;
-                const bool valid = r < cnt;
-                const u64 ms = valid ? matches[m0 + r] : 0, me = ms + P.k;
-                i64 target = -1;
+            if (single) {
+                const bool valid = lane < cnt;
+                const u64 ms = (cnt == 1) ? first_ms : (valid ? matches[m0 + lane] : 0), me = ms + P.k;
                 bool searching = valid;
                 for (u64 a = 0; a < snap; ++a) {
                     if (__ballot_sync(FULL, searching) == 0) break;
                     const u64 re = act_re[a];
-                    if (searching && act_death[a] >= t && me > re && d_ss_core(act_rs[a], re, ms, me) < act_thr[a]) {
-                        target = i64(a);
-                        searching = false;
-                    }
+                    if (searching && act_death[a] >= t && me > re && d_ss_core(act_rs[a], re, ms, me) < act_thr[a]) { my_target = i64(a); searching = false; }
                 }
-                if (single) { my_target = target; my_ms = ms; }
-                else if (valid) op_target[m0 + r] = target;
+                my_ms = ms;
+            } else if (W > 1 && u64(cnt) * snap >= kHeavyEvent) {
+                if (lane == 0) { s_cmd.t = t; s_cmd.m0 = m0; s_cmd.snap = snap; s_cmd.cnt = cnt; s_cmd.op = 1; s_cmd.in_smem = in_smem ? 1 : 0; }
+                __syncwarp();
+                asm volatile("bar.sync 1, %0;" ::"r"(W * 32));
+                classify(t, m0, cnt, snap, in_smem, 0, W);
+                asm volatile("bar.sync 2, %0;" ::"r"(W * 32));
+            } else {
+                classify(t, m0, cnt, snap, in_smem, 0, 1);
             }
             __syncwarp();
             // phase 2: extends, last match per arm wins
@@ -213,19 +335,22 @@ __global__ void __launch_bounds__(128) automaton_warp_kernel(AutoBuffers B, Auto
                 if (single) { target = my_target; ms = my_ms; }
                 else if (valid) { target = op_target[m0 + r]; ms = matches[m0 + r]; }
                 const bool ext = valid && target >= 0;
-                const unsigned peers = __match_any_sync(FULL, ext ? target : i64(-1) - i64(lane));
-                if (ext && (31 - __clz(peers)) == int(lane)) {
-                    const u64 a = u64(target);
-                    const u32 arm = act_arm[a];
-                    const u64 le = i + P.k, re = ms + P.k;
-                    a_le[arm] = le; a_re[arm] = re;
-                    act_re[a] = re;
-                    const i64 tenth = i64(0.1 * double(le - a_ls[arm]));  // src/automaton.rs:69
-                    act_thr[a] = Gi > tenth ? Gi : tenth;
-                    act_death[a] = t + P.q_ext;
+                const unsigned any = __ballot_sync(FULL, ext);
+                if (any) {
+                    const unsigned peers = __match_any_sync(FULL, ext ? target : i64(-1) - i64(lane));
+                    if (ext && (31 - __clz(peers)) == int(lane)) {
+                        const u64 a = u64(target);
+                        const u32 arm = act_arm[a];
+                        const u64 le = i + P.k, re = ms + P.k;
+                        a_le[arm] = le; a_re[arm] = re;
+                        act_re[a] = re;
+                        const i64 tenth = i64(0.1 * double(le - act_ls[a]));  // src/automaton.rs:69
+                        act_thr[a] = Gi > tenth ? Gi : tenth;
+                        act_death[a] = t + P.q_ext;
+                    }
+                    any_ext = true;
+                    __syncwarp();  // a later round may extend the same arm again: keep rounds ordered
                 }
-                any_ext = any_ext || (__ballot_sync(FULL, ext) != 0);
-                __syncwarp();  // a later round may extend the same arm again: keep rounds ordered
             }
             // phase 3: new arms in match order
             for (u32 r0 = 0; r0 < cnt; r0 += 32) {
@@ -240,7 +365,7 @@ __global__ void __launch_bounds__(128) automaton_warp_kernel(AutoBuffers B, Auto
                     const u64 off = __popc(m & lt);
                     const u64 arm = n_arms + off, a = n_act + off;
                     a_ls[arm] = i; a_le[arm] = i + P.k; a_rs[arm] = ms; a_re[arm] = ms + P.k;
-                    act_arm[a] = u32(arm); act_rs[a] = ms; act_re[a] = ms + P.k;
+                    act_arm[a] = u32(arm); act_rs[a] = ms; act_re[a] = ms + P.k; act_ls[a] = i;
                     const i64 tenth = i64(0.1 * double(P.k));
                     act_thr[a] = Gi > tenth ? Gi : tenth;
                     act_death[a] = t + P.q_new;
@@ -256,6 +381,11 @@ __global__ void __launch_bounds__(128) automaton_warp_kernel(AutoBuffers B, Auto
         }
     }
     if (n_arms > fam_start && max_death + 1 <= Tc) flush();
+    if (W > 1) {  // release the helpers
+        if (lane == 0) s_cmd.op = 0;
+        __syncwarp();
+        asm volatile("bar.sync 1, %0;" ::"r"(W * 32));
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ post-steps

@@ -180,6 +180,32 @@ struct Sum2Op {
     __device__ __forceinline__ Sum2 operator()(const Sum2& x, const Sum2& y) const { return Sum2(x.a + y.a, x.b + y.b); }
 };
 
+// one warp per event: stream SA[lo, lo+raw), keep the survivors of the two filters in SA order
+template <typename IdxT>
+__global__ void __launch_bounds__(256) emit_matches_kernel(const IdxT* __restrict__ SA, const u64* __restrict__ ev_probe,
+                                                           const u64* __restrict__ ev_moff, const IdxT* __restrict__ ev_lo,
+                                                           const IdxT* __restrict__ ev_raw, u64 n_events,
+                                                           const ChunkDev* __restrict__ chunks, u32 n_chunks, u32 s, u32 reverse,
+                                                           u64* __restrict__ matches) {
+    const u64 e = (u64(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    if (e >= n_events) return;
+    const unsigned lane = lane_id(), lt = lanemask_lt();
+    const u64 g = ev_probe[e];
+    const ChunkDev ch = chunks[chunk_of_probe(chunks, n_chunks, g)];
+    const u64 i = (g - ch.probe_base + 1) * s;
+    const u64 b = u64(ev_lo[e]), end = b + u64(ev_raw[e]);
+    u64 w = ev_moff[e];
+    for (u64 j0 = b; j0 < end; j0 += 32) {
+        const u64 j = j0 + lane;
+        u64 x = 0;
+        bool keep = false;
+        if (j < end) { x = u64(SA[j]); keep = match_survives(x, i, ch.c0, ch.len, reverse != 0); }
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        if (keep) matches[w + __popc(m & lt)] = x;
+        w += __popc(m);
+    }
+}
+
 // equal range only (no filters) — test hook behind asgart_b200_ctx_probe_ranges
 template <typename IdxT>
 __global__ void probe_ranges_kernel(const ProbeParams<IdxT> P, i64* __restrict__ out_lo, i64* __restrict__ out_hi) {
