@@ -156,6 +156,12 @@ class Context:
         self._check(self.L.asgart_b200_ctx_download_sa(self.h, _ptr(sa)))
         return sa
 
+    def check_sa(self) -> int:
+        """sufcheck on the device: number of violations (0 = the index is a valid suffix array of the strand)."""
+        bad = C.c_int64()
+        self._check(self.L.asgart_b200_ctx_check_sa(self.h, C.byref(bad)))
+        return bad.value
+
     def download_lut(self) -> Tuple[np.ndarray, np.ndarray]:
         lo = np.empty(_lib.LUT_SIZE, dtype=np.int64)
         hi = np.empty(_lib.LUT_SIZE, dtype=np.int64)

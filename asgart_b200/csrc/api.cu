@@ -14,8 +14,8 @@
 namespace ab200 {
 thread_local LaunchCounter* g_launch_counter = nullptr;
 
-struct Index32 { DevBuf<u32> sa, lut_lo, lut_hi; };
-struct Index64 { DevBuf<u64> sa, lut_lo, lut_hi; };
+struct Index32 { DevBuf<u32> sa, lut_lo, lut_hi, deep; int deep_depth = 0; };
+struct Index64 { DevBuf<u64> sa, lut_lo, lut_hi, deep; int deep_depth = 0; };
 
 struct ChunkPlan {
     std::vector<ChunkDev> host;
@@ -123,6 +123,7 @@ int pick_bits(const asgart_b200_ctx* ctx) {
     return (ctx->n1 < 0xFFFFFFFEull) ? 32 : 64;
 }
 
+// LUT from the finished suffix array (used when the index is uploaded, or the initial keys were shorter than 8 symbols)
 template <typename IdxT>
 void build_lut(asgart_b200_ctx* ctx) {
     auto& ix = IxOf<IdxT>::get(ctx);
@@ -130,11 +131,62 @@ void build_lut(asgart_b200_ctx* ctx) {
     ix.lut_hi.alloc(kLutSize, ctx->stream);
     ix.lut_lo.zero();
     ix.lut_hi.zero();
+    ix.deep.release();
+    ix.deep_depth = 0;
     lut_build_kernel<IdxT><<<unsigned(ceil_div(ctx->n1, 256)), 256, 0, ctx->stream>>>(ctx->d_pt.p, ix.sa.p, ctx->n1, ix.lut_lo.p,
                                                                                       ix.lut_hi.p);
     KERNEL_CHECK();
     count_launch();
 }
+
+// 8-mer LUT and deep table as by-products of the suffix-array build's sorted initial keys
+template <typename IdxT>
+struct LutHook : SaKeyHook {
+    asgart_b200_ctx* ctx;
+    bool done = false;
+    double ms = 0;
+    explicit LutHook(asgart_b200_ctx* c) : ctx(c) {}
+    void on_sorted_keys(const u64* d_keys, u64 n, int b, int p0, const uint16_t* h_code, cudaStream_t stream) override {
+        if (p0 < 8 || n != ctx->n1) return;
+        auto& ix = IxOf<IdxT>::get(ctx);
+        EventTimer t(stream);
+        t.start();
+        LutCodeMap map;
+        memset(&map, 255, sizeof map);
+        const char* s5 = "ACGNT";
+        const char* s4 = "ACGT";
+        for (int d = 0; d < 5; ++d) if (h_code[u8(s5[d])] && h_code[u8(s5[d])] < 16) map.d5[h_code[u8(s5[d])]] = u8(d);
+        for (int d = 0; d < 4; ++d) if (h_code[u8(s4[d])] && h_code[u8(s4[d])] < 16) map.d4[h_code[u8(s4[d])]] = u8(d);
+        // depth: buckets of a few suffixes (4^depth <= n), at most 14 symbols (1 GiB of u32 starts), inside the initial key
+        int depth = 0;
+        while (depth < 14 && depth < p0 && (u64(1) << (2 * (depth + 1))) <= n) ++depth;
+        if (depth < 4) depth = 0;
+        ix.lut_lo.alloc(kLutSize, stream);
+        ix.lut_hi.alloc(kLutSize, stream);
+        ix.lut_lo.zero();
+        ix.lut_hi.zero();
+        const u64 M = depth ? (u64(1) << (2 * depth)) + 1 : 0;
+        ix.deep.alloc(M, stream);
+        ix.deep.zero();
+        ix.deep_depth = depth;
+        lut_from_keys_kernel<IdxT><<<unsigned(ceil_div(n, 256)), 256, 0, stream>>>(d_keys, n, b, p0, map, depth, ix.lut_lo.p, ix.lut_hi.p,
+                                                                                  ix.deep.p);
+        KERNEL_CHECK();
+        count_launch();
+        if (depth) {
+            // unseen slots take the start of the next seen one (empty bucket); the last entry closes the table at n1
+            IdxT* dp = ix.deep.p;
+            const IdxT n1v = IdxT(n);
+            CUDA_CHECK(cudaMemcpyAsync(dp + (M - 1), &n1v, sizeof(IdxT), cudaMemcpyHostToDevice, stream));
+            device_scan<IdxT, MaxOp>([dp, M, n1v] __device__(u64 kx) { const IdxT v = dp[M - 1 - kx]; return v ? IdxT(n1v + 1 - v) : IdxT(0); },
+                                     [dp, M, n1v] __device__(u64 kx, IdxT, IdxT inc) { dp[M - 1 - kx] = inc ? IdxT(n1v + 1 - inc) : n1v; }, M,
+                                     (IdxT*)nullptr, stream);
+        }
+        t.stop();
+        ms = t.ms();
+        done = true;
+    }
+};
 
 template <typename IdxT>
 void build_index_t(asgart_b200_ctx* ctx) {
@@ -142,19 +194,20 @@ void build_index_t(asgart_b200_ctx* ctx) {
     EventTimer tsa(ctx->stream), tlut(ctx->stream);
     tsa.start();
     ix.sa.alloc(ctx->n1, ctx->stream);
+    LutHook<IdxT> hook(ctx);
     {
         DevBuf<IdxT> rank(ctx->n1, ctx->stream);
         SaStats ss;
         ss.sort = &ctx->t_sort; ss.gather = &ctx->t_gather; ss.rank = &ctx->t_rank; ss.scatter = &ctx->t_scatter;
-        build_suffix_array<IdxT>(ctx->d_text.p, ctx->n1, ix.sa.p, rank.p, ctx->stream, &ss);
+        build_suffix_array<IdxT>(ctx->d_text.p, ctx->n1, ix.sa.p, rank.p, ctx->stream, &ss, &hook);
         ctx->st.sa_rounds = ss.rounds;
     }
     tsa.stop();
     tlut.start();
-    build_lut<IdxT>(ctx);
+    if (!hook.done) build_lut<IdxT>(ctx);
     tlut.stop();
-    ctx->st.ms_sa_build += tsa.ms();
-    ctx->st.ms_lut += tlut.ms();
+    ctx->st.ms_sa_build += tsa.ms() - hook.ms;
+    ctx->st.ms_lut += tlut.ms() + hook.ms;
 }
 
 template <typename T>
@@ -193,6 +246,39 @@ void upload_from_i64(const i64* h, T* d, u64 n, cudaStream_t s) {
         count_launch();
         CUDA_CHECK(cudaStreamSynchronize(s));
     }
+}
+
+template <typename IdxT>
+i64 check_sa_t(asgart_b200_ctx* ctx) {
+    auto& ix = IxOf<IdxT>::get(ctx);
+    const u64 n1 = ctx->n1;
+    cudaStream_t s = ctx->stream;
+    DevBuf<IdxT> isa(n1, s);
+    DevBuf<unsigned long long> bad(1, s);
+    bad.zero();
+    CUDA_CHECK(cudaMemsetAsync(isa.p, 0xFF, n1 * sizeof(IdxT), s));
+    const IdxT* sa = ix.sa.p;
+    IdxT* ip = isa.p;
+    unsigned long long* bp = bad.p;
+    const u8* text = ctx->d_text.p;
+    for_each_index(n1, [=] __device__(u64 i) { const u64 x = u64(sa[i]); if (x < n1) ip[x] = IdxT(i); else atomicAdd(bp, 1ull); }, s);
+    for_each_index(n1, [=] __device__(u64 p) { const u64 r = u64(ip[p]); if (r >= n1 || u64(sa[r]) != p) atomicAdd(bp, 1ull); }, s);
+    for_each_index(n1, [=] __device__(u64 i) {
+        if (i == 0) return;
+        const u64 a = u64(sa[i - 1]), b = u64(sa[i]);
+        if (a >= n1 || b >= n1) return;  // counted above
+        const u8 ca = text[a], cb = text[b];
+        bool ok;
+        if (ca != cb) ok = ca < cb;
+        else if (a + 1 == n1) ok = true;    // the shorter suffix is a proper prefix of the other
+        else if (b + 1 == n1) ok = false;
+        else ok = u64(ip[a + 1]) < u64(ip[b + 1]);
+        if (!ok) atomicAdd(bp, 1ull);
+    }, s);
+    unsigned long long h = 0;
+    CUDA_CHECK(cudaMemcpyAsync(&h, bad.p, sizeof h, cudaMemcpyDeviceToHost, s));
+    CUDA_CHECK(cudaStreamSynchronize(s));
+    return i64(h);
 }
 
 // ---------------------------------------------------------------------------------------------- chunk plan
@@ -240,6 +326,41 @@ void ensure_needle(asgart_b200_ctx* ctx, int mode) {
 }
 
 // ---------------------------------------------------------------------------------------------- stage A
+// probe_search_kernel over [p_begin, p_end) and, when the deep table is usable (k >= its depth), probe_deferred_kernel over
+// the probes it left to the literal search. Reads the counters back (one sync).
+template <typename IdxT>
+void run_probe_kernels(asgart_b200_ctx* ctx, ProbeParams<IdxT>& P, unsigned long long* h_ctr) {
+    auto& ix = IxOf<IdxT>::get(ctx);
+    cudaStream_t s = ctx->stream;
+    const u64 np = P.p_end - P.p_begin;
+    DevBuf<u32> q6(ceil_div(kLutSize, 32), s);
+    DevBuf<u64> deferred;
+    const bool deep = ix.deep.p && ix.deep_depth > 0 && int(P.k) >= ix.deep_depth;
+    if (deep) {
+        q6.zero();
+        q6_mark_kernel<<<unsigned(ceil_div(P.k, 128)), 128, 0, s>>>(P.PT, P.n1, P.k, q6.p);
+        KERNEL_CHECK();
+        count_launch();
+        deferred.alloc(np, s);
+        P.deep = ix.deep.p; P.deep_depth = ix.deep_depth; P.q6_bits = q6.p; P.deferred = deferred.p;
+    }
+    probe_search_kernel<IdxT><<<unsigned(ceil_div(np, 256)), 256, 0, s>>>(P);
+    KERNEL_CHECK();
+    count_launch();
+    if (deep) {
+        unsigned long long n_def = 0;
+        CUDA_CHECK(cudaMemcpyAsync(&n_def, P.counters + CTR_DEFERRED, sizeof n_def, cudaMemcpyDeviceToHost, s));
+        CUDA_CHECK(cudaStreamSynchronize(s));
+        if (n_def) {
+            probe_deferred_kernel<IdxT><<<unsigned(ceil_div(n_def, 256)), 256, 0, s>>>(P, n_def);
+            KERNEL_CHECK();
+            count_launch();
+        }
+    }
+    CUDA_CHECK(cudaMemcpyAsync(h_ctr, P.counters, sizeof(unsigned long long) * CTR_COUNT, cudaMemcpyDeviceToHost, s));
+    CUDA_CHECK(cudaStreamSynchronize(s));
+}
+
 template <typename IdxT>
 void run_stage_a(asgart_b200_ctx* ctx, const ChunkPlan& plan, const asgart_b200_settings* st, u64 p_begin, u64 p_end, StageA& A) {
     auto& ix = IxOf<IdxT>::get(ctx);
@@ -261,13 +382,9 @@ void run_stage_a(asgart_b200_ctx* ctx, const ChunkPlan& plan, const asgart_b200_
     P.n1 = ctx->n1; P.k = plan.k; P.s = plan.s; P.reverse = st->reverse ? 1 : 0; P.max_card = st->max_cardinality;
     P.p_begin = p_begin; P.p_end = p_end;
     P.out_lo = out_lo.p; P.out_raw = out_raw.p; P.out_surv = out_surv.p; P.proc_bits = A.bits.p; P.counters = counters.p;
-    ctx->t_probe.begin();
-    probe_search_kernel<IdxT><<<unsigned(ceil_div(np, 256)), 256, 0, s>>>(P);
-    KERNEL_CHECK();
-    count_launch();
     unsigned long long h_ctr[CTR_COUNT];
-    CUDA_CHECK(cudaMemcpyAsync(h_ctr, counters.p, sizeof h_ctr, cudaMemcpyDeviceToHost, s));
-    CUDA_CHECK(cudaStreamSynchronize(s));
+    ctx->t_probe.begin();
+    run_probe_kernels<IdxT>(ctx, P, h_ctr);
     ctx->t_probe.end(1, h_ctr[CTR_ALG_BYTES]);
     ctx->st.n_probes += np;
     ctx->st.n_searched += h_ctr[CTR_SEARCHED];
@@ -317,7 +434,7 @@ void run_post(asgart_b200_ctx* ctx, DevBuf<asgart_b200_protosd>& d_sds, DevBuf<u
     if (n_fam == 0 || post_mask == 0) return;
     DevBuf<u8> keep(n_sds, s);
     if (post_mask & ASGART_B200_POST_FILTER_NS) {
-        n_content_kernel<<<unsigned(ceil_div(n_sds * 32, 256)), 256, 0, s>>>(ctx->d_text.p, d_sds.p, n_sds, keep.p);
+        n_content_kernel<<<unsigned(n_sds), 256, 0, s>>>(ctx->d_text.p, d_sds.p, n_sds, keep.p);
         KERNEL_CHECK();
         count_launch();
     }
@@ -554,8 +671,8 @@ void asgart_b200_ctx_destroy(asgart_b200_ctx* ctx) {
     if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
     if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
     ctx->d_text.release(); ctx->d_pt.release(); ctx->d_pn.release();
-    ctx->ix32.sa.release(); ctx->ix32.lut_lo.release(); ctx->ix32.lut_hi.release();
-    ctx->ix64.sa.release(); ctx->ix64.lut_lo.release(); ctx->ix64.lut_hi.release();
+    ctx->ix32 = Index32();
+    ctx->ix64 = Index64();
     cudaStreamSynchronize(ctx->stream);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -644,6 +761,15 @@ int32_t asgart_b200_ctx_download_sa(asgart_b200_ctx* ctx, int64_t* SA) {
     });
 }
 
+int32_t asgart_b200_ctx_check_sa(asgart_b200_ctx* ctx, int64_t* n_bad) {
+    return guarded(ctx, [&]() -> int32_t {
+        if (!ctx->have_index) return fail(ctx, ASGART_B200_ESTATE, "check_sa before build_index");
+        if (!n_bad) return fail(ctx, ASGART_B200_EINVAL, "null output");
+        if (ctx->idx_bits == 32) *n_bad = check_sa_t<u32>(ctx); else *n_bad = check_sa_t<u64>(ctx);
+        return ASGART_B200_OK;
+    });
+}
+
 int32_t asgart_b200_ctx_download_lut(asgart_b200_ctx* ctx, int64_t* lo, int64_t* hi) {
     return guarded(ctx, [&]() -> int32_t {
         if (!ctx->have_index) return fail(ctx, ASGART_B200_ESTATE, "download_lut before build_index");
@@ -681,9 +807,12 @@ int32_t asgart_b200_ctx_probe_ranges(asgart_b200_ctx* ctx, const asgart_b200_chu
             P.SA = ix.sa.p; P.lut_lo = ix.lut_lo.p; P.lut_hi = ix.lut_hi.p;
             P.chunks = plan.dev.p; P.n_chunks = 1; P.n1 = ctx->n1; P.k = plan.k; P.s = plan.s;
             P.p_begin = 0; P.p_end = u64(n_probes);
-            probe_ranges_kernel<IdxT><<<unsigned(ceil_div(u64(n_probes), 256)), 256, 0, ctx->stream>>>(P, d_lo.p, d_hi.p);
-            KERNEL_CHECK();
-            count_launch();
+            P.rng_lo = d_lo.p; P.rng_hi = d_hi.p;
+            DevBuf<unsigned long long> counters(CTR_COUNT, ctx->stream);
+            counters.zero();
+            P.counters = counters.p;
+            unsigned long long h_ctr[CTR_COUNT];
+            run_probe_kernels<IdxT>(ctx, P, h_ctr);
         };
         if (ctx->idx_bits == 32) launch(u32(0)); else launch(u64(0));
         CUDA_CHECK(cudaMemcpyAsync(lo, d_lo.p, n_probes * sizeof(i64), cudaMemcpyDeviceToHost, ctx->stream));

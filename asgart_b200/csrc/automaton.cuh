@@ -389,18 +389,23 @@ __global__ void __launch_bounds__(W * 32) automaton_segment_kernel(AutoBuffers B
 }
 
 // ------------------------------------------------------------------------------------------------ post-steps
-// FilterNs: count of N over strand[p ..= p+len] for both arms (src/structs.rs:454-467), one warp per duplicon
-__global__ void n_content_kernel(const u8* __restrict__ text, const asgart_b200_protosd* __restrict__ sds, u64 n_sds,
-                                 u8* __restrict__ keep) {
-    const u64 j = (u64(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+// FilterNs: count of N over strand[p ..= p+len] for both arms (src/structs.rs:454-467), one block per duplicon
+__global__ void __launch_bounds__(256) n_content_kernel(const u8* __restrict__ text, const asgart_b200_protosd* __restrict__ sds, u64 n_sds,
+                                                        u8* __restrict__ keep) {
+    __shared__ u64 s_l[8], s_r[8];
+    const u64 j = blockIdx.x;
     if (j >= n_sds) return;
     const asgart_b200_protosd sd = sds[j];
     u64 cl = 0, cr = 0;
-    for (u64 p = sd.left + lane_id(); p <= sd.left + sd.left_length; p += 32) { u8 c = text[p]; cl += (c == 'N' || c == 'n'); }
-    for (u64 p = sd.right + lane_id(); p <= sd.right + sd.right_length; p += 32) { u8 c = text[p]; cr += (c == 'N' || c == 'n'); }
+    for (u64 p = sd.left + threadIdx.x; p <= sd.left + sd.left_length; p += 256) { u8 c = text[p]; cl += (c == 'N' || c == 'n'); }
+    for (u64 p = sd.right + threadIdx.x; p <= sd.right + sd.right_length; p += 256) { u8 c = text[p]; cr += (c == 'N' || c == 'n'); }
     cl = warp_sum_u64(cl);
     cr = warp_sum_u64(cr);
-    if (lane_id() == 0) {
+    if (lane_id() == 0) { s_l[threadIdx.x >> 5] = cl; s_r[threadIdx.x >> 5] = cr; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        cl = cr = 0;
+        for (int w = 0; w < 8; ++w) { cl += s_l[w]; cr += s_r[w]; }
         const float l = float(cl) / float(sd.left_length);   // f32 arithmetic like the reference
         const float r = float(cr) / float(sd.right_length);
         keep[j] = fmaxf(l, r) <= 0.2f ? 1 : 0;

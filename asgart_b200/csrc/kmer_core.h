@@ -101,6 +101,20 @@ AB_HD bool lut_slot(uint64_t win_hi, uint32_t& slot) {
     return ok;
 }
 
+// deep table slot: the first `depth` symbols (depth <= 16) read as a base-4 number, digits A,C,G,T = 0..3 (lexicographic).
+// Returns false when any of them is N, '$' or padding: such probes take the reference's own 8-mer bucket.
+AB_HD bool deep_slot(uint64_t win_hi, int depth, uint32_t& slot) {
+    uint32_t s = 0;
+    bool ok = true;
+    for (int j = 0; j < depth; ++j) {
+        const uint32_t nib = uint32_t(win_hi >> (60 - 4 * j)) & 15u;
+        ok = ok && (nib == CODE_A || nib == CODE_C || nib == CODE_G || nib == CODE_T);
+        s = s * 4u + (nib == CODE_T ? 3u : nib - CODE_A);
+    }
+    slot = s;
+    return ok;
+}
+
 // superslice::Ext::equal_range_by restated (third-party crate "1.0", call site src/searcher.rs:164): lower and upper
 // bound in lock step over `len` slots, `size -= half`, one final probe each. f(ix) -> -1/0/+1.
 // Kept literal because the reference's comparator is non-monotone near the end of the strand (quirk Q6,

@@ -60,12 +60,15 @@ constexpr int kInitThreads = 256;
 constexpr int kInitItems = 16;
 constexpr int kInitTile = kInitThreads * kInitItems;
 
-// key[i] = codes of T[i .. i+p0) packed most-significant-first, b bits each; vals[i] = i
+// key[i] = codes of T[i .. i+p0) packed most-significant-first, b bits each; vals[i] = i.
+// Each thread rolls the key over 16 consecutive positions; the tile's keys go through shared memory (padded against
+// bank conflicts) so that they leave the SM as coalesced stores.
 template <typename IdxT>
 __global__ void __launch_bounds__(kInitThreads) init_keys_kernel(const u8* __restrict__ text, u64 n, const uint16_t* __restrict__ code,
                                                                   int b, int p0, u64* __restrict__ keys, IdxT* __restrict__ vals) {
     __shared__ uint16_t sc[kInitTile + 64];   // codes reach 256 when every byte value occurs
     __shared__ uint16_t scode[256];
+    __shared__ u64 skey[kInitTile + kInitThreads];
     scode[threadIdx.x] = code[threadIdx.x];
     __syncthreads();
     const u64 base = u64(blockIdx.x) * kInitTile;
@@ -80,28 +83,19 @@ __global__ void __launch_bounds__(kInitThreads) init_keys_kernel(const u8* __res
     for (int j = 0; j < p0; ++j) key = (key << b) | sc[t0 + j];
 #pragma unroll
     for (int j = 0; j < kInitItems; ++j) {
-        u64 p = base + t0 + j;
-        if (p < n) { keys[p] = key; vals[p] = IdxT(p); }
+        skey[t0 + j + threadIdx.x] = key;   // element e lives at e + e / kInitItems
         key = ((key << b) & mask) | sc[t0 + j + p0];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < kInitItems; ++j) {
+        const u32 e = j * kInitThreads + threadIdx.x;
+        const u64 p = base + e;
+        if (p < n) { keys[p] = skey[e + e / kInitItems]; vals[p] = IdxT(p); }
     }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// scan accumulator of the re-ranking passes: two running maxima (positions of the latest old / new group head) and
-// three running sums (compaction counters)
-template <typename IdxT>
-struct RankAcc {
-    IdxT a, b, c, d, e;
-    RankAcc() = default;
-    __host__ __device__ explicit RankAcc(int) : a(0), b(0), c(0), d(0), e(0) {}
-    __host__ __device__ RankAcc(IdxT a_, IdxT b_, IdxT c_, IdxT d_, IdxT e_) : a(a_), b(b_), c(c_), d(d_), e(e_) {}
-};
-struct RankAccOp {
-    template <typename T> __device__ __forceinline__ T operator()(const T& x, const T& y) const {
-        return T(x.a > y.a ? x.a : y.a, x.b > y.b ? x.b : y.b, x.c + y.c, x.d + y.d, x.e + y.e);
-    }
-};
-
 // composite (group, key2) keys of the large-group radix path
 template <typename IdxT> struct CompKey;
 template <> struct CompKey<u32> {
@@ -201,10 +195,18 @@ __global__ void run_key_kernel(const u8* __restrict__ text, const uint16_t* __re
     Gx[x] = GS[c];  // every member of the pure-x group carries the same head index
 }
 
+// Optional observer of the initial sort: the keys of all suffixes (first p0 symbols, b bits each, codes by h_code[byte])
+// in sorted order — every table that depends only on a bounded prefix of the suffixes (the k-mer lookup tables of the
+// probe search) is a by-product of this array and needs no gather through the finished suffix array.
+struct SaKeyHook {
+    virtual void on_sorted_keys(const u64* d_keys, u64 n, int b, int p0, const uint16_t* h_code, cudaStream_t stream) = 0;
+    virtual ~SaKeyHook() = default;
+};
+
 template <typename IdxT>
-void build_suffix_array(const u8* d_text, u64 n, IdxT* d_sa, IdxT* d_rank, cudaStream_t stream, SaStats* st) {
+void build_suffix_array(const u8* d_text, u64 n, IdxT* d_sa, IdxT* d_rank, cudaStream_t stream, SaStats* st, SaKeyHook* hook = nullptr) {
     using KeyT = typename CompKey<IdxT>::type;
-    using Acc = RankAcc<IdxT>;
+    using Acc = FlagAcc<IdxT>;
     if (n == 0) return;
     auto sync_read = [&](void* dst, const void* src, size_t bytes) {
         CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, stream));
@@ -252,33 +254,34 @@ void build_suffix_array(const u8* d_text, u64 n, IdxT* d_sa, IdxT* d_rank, cudaS
     u64 UA = 0, US = 0, NGA = 0;
     DevBuf<IdxT> GA, IA, HSA;
     {
-        DevBuf<u64> keysA(n, stream), keysB(n, stream);
-        DevBuf<IdxT> valsA(n, stream), valsB(n, stream);
-        init_keys_kernel<IdxT><<<unsigned(ceil_div(n, u64(kInitTile))), kInitThreads, 0, stream>>>(d_text, n, d_code.p, b, p0,
-                                                                                                  keysA.p, valsA.p);
-        KERNEL_CHECK();
-        count_launch();
         std::vector<int> shifts;
         for (int s = 0; s < b * p0; s += 8) shifts.push_back(s);
+        // the sorted suffix indices must end up in d_sa itself: with an even number of passes they start there
+        DevBuf<u64> keysA(n, stream), keysB(n, stream);
+        DevBuf<IdxT> valsT(n, stream);
         u64 *k = keysA.p, *ka = keysB.p;
-        IdxT *v = valsA.p, *va = valsB.p;
+        IdxT *v = (shifts.size() % 2 == 0) ? d_sa : valsT.p, *va = (shifts.size() % 2 == 0) ? valsT.p : d_sa;
+        init_keys_kernel<IdxT><<<unsigned(ceil_div(n, u64(kInitTile))), kInitThreads, 0, stream>>>(d_text, n, d_code.p, b, p0, k, v);
+        KERNEL_CHECK();
+        count_launch();
         radix_sort_pairs<u64, IdxT>(k, ka, v, va, n, shifts.data(), int(shifts.size()), stream, st ? st->sort : nullptr,
                                     st ? st->scatter : nullptr);
 
+        if (hook) hook->on_sorted_keys(k, n, b, p0, h_code, stream);
         DevBuf<Acc> d_total(1, stream);
         const u64* kk = k;
-        const IdxT* vv = v;
+        const IdxT* vv = v;   // == d_sa
         auto in = [kk, n, rep_unit, sym_mask] __device__(u64 i) {
             const u64 cur = kk[i];
             const bool head = i == 0 || kk[i - 1] != cur;
             const bool tail = i + 1 == n || kk[i + 1] != cur;
             const bool uns = !(head && tail);
             const bool pure = cur == (cur & sym_mask) * rep_unit;
-            return Acc(head ? IdxT(i) : IdxT(0), IdxT(0), (uns && !pure) ? IdxT(1) : IdxT(0), (uns && pure) ? IdxT(1) : IdxT(0),
-                       (uns && !pure && head) ? IdxT(1) : IdxT(0));
+            return (head ? FS_MARK_A : 0u) | ((uns && !pure) ? FS_CNT_C : 0u) | ((uns && pure) ? FS_CNT_D : 0u) |
+                   ((uns && !pure && head) ? FS_CNT_E : 0u);
         };
         if (st && st->rank) st->rank->begin();
-        ScanPlan<Acc, RankAccOp> plan;
+        FlagScanPlan<IdxT> plan;
         plan.prepare(in, n, d_total.p, stream);
         Acc tot;
         sync_read(&tot, d_total.p, sizeof tot);
@@ -292,7 +295,6 @@ void build_suffix_array(const u8* d_text, u64 n, IdxT* d_sa, IdxT* d_rank, cudaS
             const bool tail = i + 1 == n || kk[i + 1] != cur;
             const IdxT idx = vv[i];
             d_rank[idx] = inc.a;
-            d_sa[i] = idx;
             if (head && tail) return;
             if (cur == (cur & sym_mask) * rep_unit) { gs[exc.d] = inc.a; is[exc.d] = idx; }
             else {
@@ -339,11 +341,10 @@ void build_suffix_array(const u8* d_text, u64 n, IdxT* d_sa, IdxT* d_rank, cudaS
             if (c > 0) { const u64 prev = kk[c - 1]; head_new = prev != cur; head_old = (prev >> (kb0 + 1)) != (cur >> (kb0 + 1)); }
             if (c + 1 < USc) tail_new = kk[c + 1] != cur;
             const bool surv = !(head_new && tail_new);
-            return Acc(head_old ? IdxT(c) : IdxT(0), head_new ? IdxT(c) : IdxT(0), surv ? IdxT(1) : IdxT(0),
-                       (surv && head_new) ? IdxT(1) : IdxT(0), IdxT(0));
+            return (head_old ? FS_MARK_A : 0u) | (head_new ? FS_MARK_B : 0u) | (surv ? FS_CNT_C : 0u) | ((surv && head_new) ? FS_CNT_D : 0u);
         };
         if (st && st->rank) st->rank->begin();
-        ScanPlan<Acc, RankAccOp> plan;
+        FlagScanPlan<IdxT> plan;
         plan.prepare(in, US, d_total.p, stream);
         Acc tot;
         sync_read(&tot, d_total.p, sizeof tot);
@@ -447,11 +448,10 @@ void build_suffix_array(const u8* d_text, u64 n, IdxT* d_sa, IdxT* d_rank, cudaS
             if (c > 0) { head_old = gg[c - 1] != g; head_new = head_old || k2[c - 1] != kv; }
             if (c + 1 < Uc) tail_new = gg[c + 1] != g || k2[c + 1] != kv;
             const bool surv = !(head_new && tail_new);
-            return Acc(head_old ? IdxT(c) : IdxT(0), head_new ? IdxT(c) : IdxT(0), surv ? IdxT(1) : IdxT(0),
-                       (surv && head_new) ? IdxT(1) : IdxT(0), IdxT(0));
+            return (head_old ? FS_MARK_A : 0u) | (head_new ? FS_MARK_B : 0u) | (surv ? FS_CNT_C : 0u) | ((surv && head_new) ? FS_CNT_D : 0u);
         };
         if (st && st->rank) st->rank->begin();
-        ScanPlan<Acc, RankAccOp> plan;
+        FlagScanPlan<IdxT> plan;
         plan.prepare(in, U, d_total.p, stream);
         Acc tot;
         sync_read(&tot, d_total.p, sizeof tot);

@@ -74,6 +74,73 @@ __device__ __forceinline__ u32 chunk_of_probe(const ChunkDev* __restrict__ ch, u
     return lo;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Lookup tables as by-products of the suffix-array build's initial sort (sa_build.cuh, SaKeyHook): the sorted keys hold
+// the first p0 symbols of every suffix in suffix order, so bucket boundaries need no gather through SA and text.
+struct LutCodeMap {
+    u8 d5[16];  // dense symbol code -> base-5 digit A,C,G,N,T = 0..4 (255: '$' or padding)
+    u8 d4[16];  // dense symbol code -> base-4 digit A,C,G,T = 0..3 (255 otherwise)
+};
+
+__device__ __forceinline__ bool key_slot5(u64 key, int b, int p0, const LutCodeMap& m, u32& slot) {
+    u32 s = 0;
+    bool ok = true;
+    const u32 mask = (1u << b) - 1u;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const u32 d = m.d5[u32(key >> (b * (p0 - 1 - j))) & mask];
+        ok = ok && d != 255u;
+        s = s * 5u + d;
+    }
+    slot = s;
+    return ok;
+}
+__device__ __forceinline__ bool key_slot4(u64 key, int b, int p0, int depth, const LutCodeMap& m, u32& slot) {
+    u32 s = 0;
+    bool ok = true;
+    const u32 mask = (1u << b) - 1u;
+    for (int j = 0; j < depth; ++j) {
+        const u32 d = m.d4[u32(key >> (b * (p0 - 1 - j))) & mask];
+        ok = ok && d != 255u;
+        s = s * 4u + d;
+    }
+    slot = s;
+    return ok;
+}
+
+// 8-mer LUT (Searcher::new, src/searcher.rs:99-143) and, when depth > 0, the first suffix of every ACGT-only
+// `depth`-mer (0 = not seen; position 0 is always the '$' suffix) from the sorted initial keys. Needs p0 >= 8, depth.
+template <typename IdxT>
+__global__ void lut_from_keys_kernel(const u64* __restrict__ keys, u64 n1, int b, int p0, const LutCodeMap map, int depth,
+                                     IdxT* __restrict__ lut_lo, IdxT* __restrict__ lut_hi, IdxT* __restrict__ deep) {
+    const u64 i = u64(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n1) return;
+    const u64 cur = keys[i];
+    const u64 prev = i > 0 ? keys[i - 1] : 0;
+    u32 cs = 0, ps = 0;
+    const bool cur_ok = key_slot5(cur, b, p0, map, cs);
+    const bool prev_ok = i > 0 && key_slot5(prev, b, p0, map, ps);
+    if (cur_ok && (!prev_ok || ps != cs)) lut_lo[cs] = IdxT(i);
+    if (prev_ok && (!cur_ok || ps != cs)) lut_hi[ps] = IdxT(i);
+    if (i + 1 == n1 && cur_ok) lut_hi[cs] = IdxT(n1);
+    if (depth > 0) {
+        const bool c4 = key_slot4(cur, b, p0, depth, map, cs);
+        const bool p4 = i > 0 && key_slot4(prev, b, p0, depth, map, ps);
+        if (c4 && (!p4 || ps != cs)) deep[cs] = IdxT(i);
+    }
+}
+
+// slots of the 8-mer LUT whose bucket holds one of the last k-1 suffixes: there the reference's comparator is forced
+// to Less (src/searcher.rs:165-166, quirk Q6) and only its literal bisection reproduces its answer
+__global__ void q6_mark_kernel(const u64* __restrict__ PT, u64 n1, u32 k, u32* __restrict__ q6_bits) {
+    const u64 t = u64(blockIdx.x) * blockDim.x + threadIdx.x;
+    const u64 first = n1 >= k ? n1 - k + 1 : 0;
+    const u64 x = first + t;
+    if (x >= n1) return;
+    u32 slot;
+    if (lut_slot(load_window(PT, x).hi, slot)) atomicOr(&q6_bits[slot >> 5], 1u << (slot & 31u));
+}
+
 template <typename IdxT>
 struct ProbeParams {
     const u64* PT;  // packed strand
@@ -81,6 +148,9 @@ struct ProbeParams {
     const IdxT* SA;
     const IdxT* lut_lo;
     const IdxT* lut_hi;
+    const IdxT* deep;     // deep table: 4^deep_depth + 1 non-decreasing bucket starts, or null
+    int deep_depth;
+    const u32* q6_bits;   // 5^8 bits
     const ChunkDev* chunks;
     u32 n_chunks;
     u64 n1;
@@ -93,10 +163,14 @@ struct ProbeParams {
     IdxT* out_raw;
     u32* out_surv;
     u32* proc_bits;   // bit (g - p_begin): iteration processed (neither N-skipped nor over the cardinality cap)
-    unsigned long long* counters;  // [0] searched [1] skipped_n [2] skipped_card [3] matches [4] algorithmic bytes
+    unsigned long long* counters;  // [0] searched [1] skipped_n [2] skipped_card [3] matches [4] algorithmic bytes [5] deferred
+    u64* deferred;    // probes left to the literal kernel (capacity p_end - p_begin)
+    // test hook (asgart_b200_ctx_probe_ranges): equal ranges only, no N test, no filters
+    i64* rng_lo;
+    i64* rng_hi;
 };
 
-enum { CTR_SEARCHED = 0, CTR_SKIP_N = 1, CTR_SKIP_CARD = 2, CTR_MATCHES = 3, CTR_ALG_BYTES = 4, CTR_COUNT = 8 };
+enum { CTR_SEARCHED = 0, CTR_SKIP_N = 1, CTR_SKIP_CARD = 2, CTR_MATCHES = 3, CTR_ALG_BYTES = 4, CTR_DEFERRED = 5, CTR_COUNT = 8 };
 
 __device__ __forceinline__ u64 warp_sum_u64(u64 v) {
 #pragma unroll
@@ -104,69 +178,162 @@ __device__ __forceinline__ u64 warp_sum_u64(u64 v) {
     return v;
 }
 
-template <typename IdxT>
-__global__ void __launch_bounds__(256) probe_search_kernel(const ProbeParams<IdxT> P) {
-    const u64 g = P.p_begin + u64(blockIdx.x) * blockDim.x + threadIdx.x;
-    const bool in_range = g < P.p_end;
+struct ProbeState {
     bool processed = false, searched = false, skip_n = false, skip_card = false;
     u64 lo = 0, hi = 0, surv = 0, alg = 0;
-    if (in_range) {
-        const ChunkDev ch = P.chunks[chunk_of_probe(P.chunks, P.n_chunks, g)];
-        const u64 i = (g - ch.probe_base + 1) * P.s;
-        const u64 q = ch.needle_start + i;
-        const int k = int(P.k);
-        const Win pw_raw = load_window(P.PN, q);
-        if ((pw_raw.hi >> 60) == CODE_N) {
-            skip_n = true;  // src/automaton.rs:100-102
-        } else {
-            searched = true;
-            const Win pw0 = mask_window(pw_raw, k < 32 ? k : 32);
-            u32 slot = 0;
-            u64 lstart = 0, rstart = 0;
-            if (lut_slot(pw_raw.hi, slot)) { lstart = u64(P.lut_lo[slot]); rstart = u64(P.lut_hi[slot]); }
-            const IdxT* __restrict__ sub = P.SA + lstart;
-            const u64 n1 = P.n1;
-            const u64* __restrict__ PT = P.PT;
-            const u64* __restrict__ PN = P.PN;
-            u64 r0, r1;
-            equal_range_lockstep(rstart - lstart, [&](u64 ix) -> int {
-                const u64 x = u64(sub[ix]);
-                if (x + u64(k) > n1) return -1;  // src/searcher.rs:165-166 (Q6)
-                return cmp_kmer(PT, x, PN, q, k, pw0);
-            }, r0, r1);
-            if (r1 < r0) r1 = r0;  // only reachable through Q6; the reference would panic on the slice
-            lo = lstart + r0;
-            hi = lstart + r1;
-            alg = 24ull * (ceil_log2_u64(rstart - lstart + 1) + 1) + 8ull * (hi - lo);
-            // filters + cardinality (src/automaton.rs:105-117)
-            const bool rev = P.reverse != 0;
-            for (u64 j = lo; j < hi; ++j) {
-                if (match_survives(u64(P.SA[j]), i, ch.c0, ch.len, rev)) {
-                    if (++surv > P.max_card) break;
-                }
-            }
-            if (surv > P.max_card) { skip_card = true; surv = 0; } else processed = true;
+};
+
+// filters + cardinality (src/automaton.rs:105-117) over SA[lo, hi), then the per-probe outputs
+template <typename IdxT>
+__device__ __forceinline__ void probe_finish(const ProbeParams<IdxT>& P, const ChunkDev& ch, u64 g, u64 i, u64 bucket8, ProbeState& S) {
+    S.searched = true;
+    S.alg = 24ull * (ceil_log2_u64(bucket8 + 1) + 1) + 8ull * (S.hi - S.lo);
+    const u64 o = g - P.p_begin;
+    if (P.rng_lo) { P.rng_lo[o] = i64(S.lo); P.rng_hi[o] = i64(S.hi); return; }
+    const bool rev = P.reverse != 0;
+    for (u64 j = S.lo; j < S.hi; ++j) {
+        if (match_survives(u64(P.SA[j]), i, ch.c0, ch.len, rev)) {
+            if (++S.surv > P.max_card) break;
         }
-        const u64 o = g - P.p_begin;
-        P.out_lo[o] = IdxT(lo);
-        P.out_raw[o] = IdxT(hi - lo);
-        P.out_surv[o] = u32(surv);
     }
-    const unsigned bits = __ballot_sync(0xffffffffu, processed);
-    const unsigned n_searched = __popc(__ballot_sync(0xffffffffu, searched));
-    const unsigned n_skip_n = __popc(__ballot_sync(0xffffffffu, skip_n));
-    const unsigned n_skip_card = __popc(__ballot_sync(0xffffffffu, skip_card));
-    const u64 w_surv = warp_sum_u64(surv);
-    const u64 w_alg = warp_sum_u64(alg);
+    if (S.surv > P.max_card) { S.skip_card = true; S.surv = 0; } else S.processed = true;
+    P.out_lo[o] = IdxT(S.lo);
+    P.out_raw[o] = IdxT(S.hi - S.lo);
+    P.out_surv[o] = u32(S.surv);
+}
+
+// the reference's own search: 8-mer bucket, then the literal lock-step bisection with the forced-Less comparator
+template <typename IdxT>
+__device__ __forceinline__ void probe_literal(const ProbeParams<IdxT>& P, const ChunkDev& ch, u64 g, u64 i, u64 q, const Win& pw_raw,
+                                              ProbeState& S) {
+    const int k = int(P.k);
+    const Win pw0 = mask_window(pw_raw, k < 32 ? k : 32);
+    u32 slot = 0;
+    u64 lstart = 0, rstart = 0;
+    if (lut_slot(pw_raw.hi, slot)) { lstart = u64(P.lut_lo[slot]); rstart = u64(P.lut_hi[slot]); }
+    const IdxT* __restrict__ sub = P.SA + lstart;
+    const u64 n1 = P.n1;
+    const u64* __restrict__ PT = P.PT;
+    const u64* __restrict__ PN = P.PN;
+    u64 r0, r1;
+    equal_range_lockstep(rstart - lstart, [&](u64 ix) -> int {
+        const u64 x = u64(sub[ix]);
+        if (x + u64(k) > n1) return -1;  // src/searcher.rs:165-166 (Q6)
+        return cmp_kmer(PT, x, PN, q, k, pw0);
+    }, r0, r1);
+    if (r1 < r0) r1 = r0;  // only reachable through Q6; the reference would panic on the slice
+    S.lo = lstart + r0;
+    S.hi = lstart + r1;
+    probe_finish(P, ch, g, i, rstart - lstart, S);
+}
+
+template <typename IdxT>
+__device__ __forceinline__ void probe_account(const ProbeParams<IdxT>& P, const ProbeState& S) {
+    const unsigned n_searched = __popc(__ballot_sync(0xffffffffu, S.searched));
+    const unsigned n_skip_n = __popc(__ballot_sync(0xffffffffu, S.skip_n));
+    const unsigned n_skip_card = __popc(__ballot_sync(0xffffffffu, S.skip_card));
+    const u64 w_surv = warp_sum_u64(S.surv);
+    const u64 w_alg = warp_sum_u64(S.alg);
     if (lane_id() == 0) {
-        const u64 word = (P.p_begin + u64(blockIdx.x) * blockDim.x + (threadIdx.x & ~31u) - P.p_begin) >> 5;
-        if (P.p_begin + word * 32 < P.p_end) P.proc_bits[word] = bits;
         if (n_searched) atomicAdd(&P.counters[CTR_SEARCHED], (unsigned long long)n_searched);
         if (n_skip_n) atomicAdd(&P.counters[CTR_SKIP_N], (unsigned long long)n_skip_n);
         if (n_skip_card) atomicAdd(&P.counters[CTR_SKIP_CARD], (unsigned long long)n_skip_card);
         if (w_surv) atomicAdd(&P.counters[CTR_MATCHES], (unsigned long long)w_surv);
         if (w_alg) atomicAdd(&P.counters[CTR_ALG_BYTES], (unsigned long long)w_alg);
     }
+}
+
+constexpr int kProbeLinear = 8;  // deep buckets up to this size are compared in one go instead of bisected
+
+// One lane per probe position. Probes whose first deep_depth bases are all ACGT start from the deep table's bucket
+// (a few suffixes) and compare them all at once; the equal range of a monotone comparator does not depend on how it is
+// searched, so this is the reference's answer whenever its own 8-mer bucket holds none of the last k-1 suffixes. Every
+// other probe (N among the first bases, flagged bucket, no deep table) is handed to probe_literal, in this kernel when
+// P.deferred is null and in probe_deferred_kernel otherwise (keeps the long bisections out of the short warps).
+template <typename IdxT>
+__global__ void __launch_bounds__(256) probe_search_kernel(const ProbeParams<IdxT> P) {
+    const u64 g = P.p_begin + u64(blockIdx.x) * blockDim.x + threadIdx.x;
+    const bool in_range = g < P.p_end;
+    ProbeState S;
+    bool defer = false;
+    if (in_range) {
+        const ChunkDev ch = P.chunks[chunk_of_probe(P.chunks, P.n_chunks, g)];
+        const u64 i = (g - ch.probe_base + 1) * P.s;
+        const u64 q = ch.needle_start + i;
+        const int k = int(P.k);
+        const Win pw_raw = load_window(P.PN, q);
+        u32 slot4 = 0, slot8 = 0;
+        if (!P.rng_lo && (pw_raw.hi >> 60) == CODE_N) {
+            S.skip_n = true;  // src/automaton.rs:100-102
+            const u64 o = g - P.p_begin;
+            P.out_lo[o] = 0; P.out_raw[o] = 0; P.out_surv[o] = 0;
+        } else if (P.deep && deep_slot(pw_raw.hi, P.deep_depth, slot4) && lut_slot(pw_raw.hi, slot8) &&
+                   !((P.q6_bits[slot8 >> 5] >> (slot8 & 31u)) & 1u)) {
+            const u64 lo0 = u64(P.deep[slot4]), hi0 = u64(P.deep[slot4 + 1]);
+            const u64 bucket8 = u64(P.lut_hi[slot8]) - u64(P.lut_lo[slot8]);
+            const Win pw0 = mask_window(pw_raw, k < 32 ? k : 32);
+            const IdxT* __restrict__ sub = P.SA + lo0;
+            const u64* __restrict__ PT = P.PT;
+            const u64* __restrict__ PN = P.PN;
+            const u64 B = hi0 - lo0;
+            if (B <= kProbeLinear) {
+                u64 xs[kProbeLinear];
+#pragma unroll
+                for (int j = 0; j < kProbeLinear; ++j) xs[j] = u64(j) < B ? u64(sub[j]) : 0;
+                Win ws[kProbeLinear];
+#pragma unroll
+                for (int j = 0; j < kProbeLinear; ++j) ws[j] = load_window(PT, xs[j]);
+                u32 lt = 0, le = 0;
+#pragma unroll
+                for (int j = 0; j < kProbeLinear; ++j) {
+                    if (u64(j) < B) {
+                        int c = cmp_window(mask_window(ws[j], k < 32 ? k : 32), pw0);
+                        if (c == 0 && k > 32) c = cmp_kmer(PT, xs[j], PN, q, k, pw0);
+                        lt += c < 0; le += c <= 0;
+                    }
+                }
+                S.lo = lo0 + lt; S.hi = lo0 + le;
+            } else {
+                u64 r0, r1;
+                equal_range_lockstep(B, [&](u64 ix) -> int { return cmp_kmer(PT, u64(sub[ix]), PN, q, k, pw0); }, r0, r1);
+                S.lo = lo0 + r0; S.hi = lo0 + r1;
+            }
+            probe_finish(P, ch, g, i, bucket8, S);
+        } else if (P.deferred) {
+            defer = true;
+        } else {
+            probe_literal(P, ch, g, i, q, pw_raw, S);
+        }
+    }
+    const unsigned dm = __ballot_sync(0xffffffffu, defer);
+    if (dm) {
+        unsigned long long base = 0;
+        if (lane_id() == 0) base = atomicAdd(&P.counters[CTR_DEFERRED], (unsigned long long)__popc(dm));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (defer) P.deferred[base + __popc(dm & lanemask_lt())] = g;
+    }
+    const unsigned bits = __ballot_sync(0xffffffffu, S.processed);
+    if (lane_id() == 0 && !P.rng_lo) {
+        const u64 word = (u64(blockIdx.x) * blockDim.x + (threadIdx.x & ~31u)) >> 5;
+        if (P.p_begin + word * 32 < P.p_end) P.proc_bits[word] = bits;
+    }
+    probe_account(P, S);
+}
+
+// the probes probe_search_kernel left over, one lane each
+template <typename IdxT>
+__global__ void __launch_bounds__(256) probe_deferred_kernel(const ProbeParams<IdxT> P, u64 n_deferred) {
+    const u64 j = u64(blockIdx.x) * blockDim.x + threadIdx.x;
+    ProbeState S;
+    if (j < n_deferred) {
+        const u64 g = P.deferred[j];
+        const ChunkDev ch = P.chunks[chunk_of_probe(P.chunks, P.n_chunks, g)];
+        const u64 i = (g - ch.probe_base + 1) * P.s;
+        const u64 q = ch.needle_start + i;
+        probe_literal(P, ch, g, i, q, load_window(P.PN, q), S);
+        if (S.processed) { const u64 o = g - P.p_begin; atomicOr(&P.proc_bits[o >> 5], 1u << (o & 31u)); }
+    }
+    probe_account(P, S);
 }
 
 // pair of running sums: match offset and event index
@@ -204,33 +371,6 @@ __global__ void __launch_bounds__(256) emit_matches_kernel(const IdxT* __restric
         if (keep) matches[w + __popc(m & lt)] = x;
         w += __popc(m);
     }
-}
-
-// equal range only (no filters) — test hook behind asgart_b200_ctx_probe_ranges
-template <typename IdxT>
-__global__ void probe_ranges_kernel(const ProbeParams<IdxT> P, i64* __restrict__ out_lo, i64* __restrict__ out_hi) {
-    const u64 g = P.p_begin + u64(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (g >= P.p_end) return;
-    const ChunkDev ch = P.chunks[0];
-    const u64 i = (g + 1) * P.s;
-    const u64 q = ch.needle_start + i;
-    const int k = int(P.k);
-    const Win pw_raw = load_window(P.PN, q);
-    const Win pw0 = mask_window(pw_raw, k < 32 ? k : 32);
-    u32 slot = 0;
-    u64 lstart = 0, rstart = 0;
-    if (lut_slot(pw_raw.hi, slot)) { lstart = u64(P.lut_lo[slot]); rstart = u64(P.lut_hi[slot]); }
-    const IdxT* __restrict__ sub = P.SA + lstart;
-    const u64 n1 = P.n1;
-    u64 r0, r1;
-    equal_range_lockstep(rstart - lstart, [&](u64 ix) -> int {
-        const u64 x = u64(sub[ix]);
-        if (x + u64(k) > n1) return -1;
-        return cmp_kmer(P.PT, x, P.PN, q, k, pw0);
-    }, r0, r1);
-    if (r1 < r0) r1 = r0;
-    out_lo[g] = i64(lstart + r0);
-    out_hi[g] = i64(lstart + r1);
 }
 
 }  // namespace ab200

@@ -108,6 +108,11 @@ ASGART_B200_API int32_t asgart_b200_ctx_set_index_bits(asgart_b200_ctx *ctx, int
 /* test hooks: use a suffix array built elsewhere (still builds the LUT on the device) / read the index back */
 ASGART_B200_API int32_t asgart_b200_ctx_upload_sa(asgart_b200_ctx *ctx, const int64_t *SA);
 ASGART_B200_API int32_t asgart_b200_ctx_download_sa(asgart_b200_ctx *ctx, int64_t *SA);
+/* On-device restatement of sufcheck (libdivsufsort/lib/utils.c:159-241; the reference's only self-check,
+ * examples/suftest.c:146-157): SA must be a permutation of [0, n] and every adjacent pair must be in suffix order
+ * (first symbols, then the ranks of the two suffixes one symbol further on). *n_bad = number of violations (0 = valid).
+ * Lets a genome-scale index be validated without a CPU-side suffix array. */
+ASGART_B200_API int32_t asgart_b200_ctx_check_sa(asgart_b200_ctx *ctx, int64_t *n_bad);
 /* LUT as 5^8 (lo, hi) pairs indexed by the 8-mer read as a base-5 number with digits A=0,C=1,G=2,N=3,T=4 (first
  * letter most significant). Empty buckets have lo == hi (value unspecified). */
 #define ASGART_B200_LUT_SIZE 390625

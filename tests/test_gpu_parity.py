@@ -113,15 +113,23 @@ def _slot_of_key(k):
     return s
 
 
+@pytest.mark.parametrize("source", ["upload", "build"])
 @pytest.mark.parametrize("bits", [32, 64])
-def test_lut_and_probe_ranges(bits):
+def test_lut_and_probe_ranges(bits, source):
+    """upload: LUT from the finished SA, literal search only. build: LUT + deep table from the sorted initial keys of the
+    SA build, probes go through the deep-table path and the deferred literal path."""
     text = cases.stress_text(5, n=50000)
     strand = np.concatenate([text, np.frombuffer(b"$", dtype=np.uint8)])
     sa = oracle.best_suffix_array(strand)
     with ab.Context(0) as ctx:
         ctx.set_index_bits(bits)
         ctx.load_strand(strand)
-        ctx.upload_sa(sa)
+        if source == "upload":
+            ctx.upload_sa(sa)
+        else:
+            ctx.build_index()
+            assert np.array_equal(ctx.download_sa(), sa)
+        assert ctx.check_sa() == 0
         lo, hi = ctx.download_lut()
         keys, olo, ohi = oracle.lut(strand, sa)
         slots = np.array([_slot_of_key(k) for k in keys])
@@ -148,6 +156,55 @@ def test_lut_and_probe_ranges(bits):
                 want = osr.search(needle[i:i + k].tobytes())
                 assert ghi[p] - glo[p] == len(want), (kw, p)
                 assert np.array_equal(sa[glo[p]:ghi[p]], want), (kw, p)
+
+
+def test_q6_forced_less_with_deep_table():
+    """Quirk Q6 on the device: the last k-1 suffixes compare Less whatever they hold (src/searcher.rs:165-166). The tail of
+    this text shares its 8-mers with most probes, so most 8-mer buckets are flagged and must take the literal bisection,
+    the others take the deep table; ranges and families must equal the oracle's either way."""
+    rng = np.random.default_rng(3)
+    unit = kat.rand_dna(rng, 11)
+    text = np.concatenate([kat.rand_dna(rng, 3000), np.tile(unit, 400), kat.rand_dna(rng, 9)])
+    strand = np.concatenate([text, np.frombuffer(b"$", dtype=np.uint8)])
+    sa = oracle.best_suffix_array(strand)
+    osr = oracle.OracleSearcher(strand, sa)
+    with ab.Context(0) as ctx:
+        ctx.load_strand(strand)
+        ctx.build_index()
+        assert np.array_equal(ctx.download_sa(), sa)
+        for kw in (dict(probe_size=20, gap_size=100, min_length=200, max_cardinality=100000),
+                   dict(probe_size=20, gap_size=100, min_length=200, max_cardinality=100000, reverse=True, complement=True),
+                   dict(probe_size=12, gap_size=50, min_length=200, max_cardinality=100000)):
+            st = _rs(kw)
+            want = oracle.search(strand, sa, [(0, len(text))], _osettings(st), oracle.POST_ALL, threads=1)
+            got = ctx.search([(0, len(text))], st, ab.POST_ALL)
+            assert got.as_lists() == want.families.as_lists(), kw
+            if not st.reverse:
+                k, s = st.probe_size, st.probe_size // 2
+                nprobes = -(-(len(text) - k - s) // s)
+                glo, ghi = ctx.probe_ranges((0, len(text)), st, nprobes)
+                for p in range(nprobes):
+                    i = (p + 1) * s
+                    w = osr.search(text[i:i + k].tobytes())
+                    assert ghi[p] - glo[p] == len(w) and np.array_equal(sa[glo[p]:ghi[p]], w), (kw, p)
+
+
+def test_check_sa_detects_corruption():
+    text = cases.stress_text(21, n=30000)
+    strand = np.concatenate([text, np.frombuffer(b"$", dtype=np.uint8)])
+    sa = oracle.best_suffix_array(strand)
+    with ab.Context(0) as ctx:
+        ctx.load_strand(strand)
+        ctx.upload_sa(sa)
+        assert ctx.check_sa() == 0
+        bad = sa.copy()
+        bad[[100, 101]] = bad[[101, 100]]          # one adjacent swap: order violation
+        ctx.upload_sa(bad)
+        assert ctx.check_sa() > 0
+        dup = sa.copy()
+        dup[500] = dup[501]                        # not a permutation
+        ctx.upload_sa(dup)
+        assert ctx.check_sa() > 0
 
 
 # ------------------------------------------------------------------------------------------------ search + automaton
@@ -268,3 +325,67 @@ def test_run_files_json_identical_to_oracle(tmp_path):
         assert js == want
         assert json.loads(js)["settings"]["max_gap_size"] == 120
     assert len(json.loads(ab.search_duplications([str(fa)], ab.RunSettings()))["families"]) > 0
+
+
+# ------------------------------------------------------------------------------------------------ full-size configs
+def _full_config(config):
+    flags = {1: dict(), 2: dict(reverse=True, complement=True, skip_masked=True),
+             3: dict(reverse=True, complement=True, max_cardinality=500), 4: dict(reverse=True, complement=True)}[config]
+    st = ab.RunSettings(**flags)
+    g, fr = ab.synth_genome(config, threads=os.cpu_count() or 8)
+    prep = ab.Prepared.from_memory(ab.normalise(g, st.skip_masked), fr, f"synthC{config}.fa")
+    return st, prep
+
+
+def _index_properties(ctx, prep):
+    """Size-independent properties of the index: on-device sufcheck, SA[0] = n, LUT buckets disjoint and inside [0, n]."""
+    assert ctx.check_sa() == 0
+    lo, hi = ctx.download_lut()
+    ne = hi > lo
+    assert (lo[ne] >= 1).all() and (hi[ne] <= len(prep.strand)).all()
+    order = np.argsort(lo[ne], kind="stable")
+    assert (hi[ne][order][:-1] <= lo[ne][order][1:]).all()      # slots are in suffix order and do not overlap
+    return int((hi[ne] - lo[ne]).sum())
+
+
+def test_full_size_c2_equals_oracle():
+    """BASELINE configs[1] at full size (57 Mbp, -RC -S): families identical to the CPU oracle's (reference libdivsufsort
+    SA when oracle/_ref is present), plus the index properties."""
+    st, prep = _full_config(2)
+    strand = np.array(prep.strand)
+    with ab.Context(0) as ctx:
+        ctx.load_strand(strand)
+        ctx.build_index()
+        in_lut = _index_properties(ctx, prep)
+        assert in_lut <= len(strand) - 8
+        got = ctx.search(prep.chunks, st, ab.POST_ALL)
+        sa = oracle.best_suffix_array(strand)
+        assert np.array_equal(ctx.download_sa(), sa)
+        want = oracle.search(strand, sa, prep.chunks, _osettings(st), oracle.POST_ALL, threads=os.cpu_count() or 8)
+        assert got.as_lists() == want.families.as_lists()
+        assert got.n_families > 50
+        # the direct pass over the same index finds the direct plants and none of the RC ones
+        st_d = ab.RunSettings(skip_masked=True)
+        got_d = ctx.search(prep.chunks, st_d, ab.POST_ALL)
+        want_d = oracle.search(strand, sa, prep.chunks, _osettings(st_d), oracle.POST_ALL, threads=os.cpu_count() or 8)
+        assert got_d.as_lists() == want_d.families.as_lists()
+
+
+@pytest.mark.parametrize("config", [1, 3] + ([4] if os.environ.get("ASGART_B200_BIG") else []))
+def test_full_size_properties(config):
+    """Full-size C1 / C3 (and C4 = 3.1 Gbp with ASGART_B200_BIG=1): on-device sufcheck, and a search whose result does not
+    depend on how the probe range is sharded (1 vs 3 shards)."""
+    st, prep = _full_config(config)
+    with ab.Context(0) as ctx:
+        ctx.load_strand(np.array(prep.strand))
+        ctx.build_index()
+        _index_properties(ctx, prep)
+        whole = ctx.search(prep.chunks, st, ab.POST_ALL)
+        parts = [ctx.search_shard(prep.chunks, st, r, 3) for r in range(3)]
+        sharded = ctx.finish(prep.chunks, st, parts, ab.POST_ALL)
+        assert whole.as_lists() == sharded.as_lists()
+        assert whole.n_families > 10
+        for fam in whole.as_lists():
+            for (l, r, ll, rl, rev, comp) in fam:
+                assert l < r and ll >= 1 and rl >= st.min_duplication_length
+                assert rev == st.reverse and comp == st.complement
