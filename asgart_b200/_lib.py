@@ -72,6 +72,7 @@ SYMBOLS = [
     "asgart_b200_ctx_download_sa", "asgart_b200_ctx_check_sa", "asgart_b200_ctx_download_lut", "asgart_b200_ctx_search",
     "asgart_b200_ctx_probe_ranges", "asgart_b200_ctx_search_shard", "asgart_b200_partial_size",
     "asgart_b200_partial_serialize", "asgart_b200_partial_free", "asgart_b200_ctx_finish",
+    "asgart_b200_ctx_search_shard_dev", "asgart_b200_ctx_finish_dev",
     "asgart_b200_result_n_families", "asgart_b200_result_n_sds", "asgart_b200_result_family_offsets",
     "asgart_b200_result_sds", "asgart_b200_result_free", "asgart_b200_ctx_post_steps", "asgart_b200_ctx_stats",
     "asgart_b200_ctx_reset_stats", "asgart_b200_ctx_timer_start", "asgart_b200_ctx_timer_stop", "asgart_b200_prepare_files", "asgart_b200_prepare_memory",
@@ -116,6 +117,8 @@ def load() -> C.CDLL:
         "asgart_b200_partial_size": (i64, [vp]),
         "asgart_b200_partial_serialize": (i32, [vp, vp, i64]),
         "asgart_b200_partial_free": (None, [vp]),
+        "asgart_b200_ctx_search_shard_dev": (i32, [vp, vp, i64, PS, i32, i32, C.POINTER(vp), C.POINTER(i64), vp]),
+        "asgart_b200_ctx_finish_dev": (i32, [vp, vp, i64, PS, C.POINTER(vp), vp, i32, u32, C.POINTER(vp)]),
         "asgart_b200_ctx_finish": (i32, [vp, vp, i64, PS, C.POINTER(vp), C.POINTER(i64), i32, u32, C.POINTER(vp)]),
         "asgart_b200_result_n_families": (i64, [vp]),
         "asgart_b200_result_n_sds": (i64, [vp]),

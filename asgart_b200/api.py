@@ -226,6 +226,26 @@ class Context:
                                                   post_mask, C.byref(rh)))
         return self._take(rh)
 
+    def search_shard_dev(self, chunks, settings: RunSettings, shard: int, n_shards: int):
+        """Stage A over this rank's probe range, partial kept in HBM: (device pointer, bytes, meta uint64[4])."""
+        ch = _chunks_array(chunks)
+        st = settings.to_c()
+        ptr, nbytes = C.c_void_p(), C.c_int64()
+        meta = np.zeros(4, dtype=np.uint64)
+        self._check(self.L.asgart_b200_ctx_search_shard_dev(self.h, _ptr(ch), len(ch), C.byref(st), shard, n_shards,
+                                                            C.byref(ptr), C.byref(nbytes), _ptr(meta)))
+        return ptr.value or 0, nbytes.value, meta
+
+    def finish_dev(self, chunks, settings: RunSettings, blob_ptrs: Sequence[int], metas: np.ndarray, post_mask: int = POST_ALL) -> Families:
+        ch = _chunks_array(chunks)
+        st = settings.to_c()
+        metas = np.ascontiguousarray(metas, dtype=np.uint64).reshape(-1, 4)
+        ptrs = (C.c_void_p * len(blob_ptrs))(*blob_ptrs)
+        rh = C.c_void_p()
+        self._check(self.L.asgart_b200_ctx_finish_dev(self.h, _ptr(ch), len(ch), C.byref(st), ptrs, _ptr(metas), len(blob_ptrs),
+                                                      post_mask, C.byref(rh)))
+        return self._take(rh)
+
     def post_steps(self, fam: Families, post_mask: int) -> Families:
         off = np.ascontiguousarray(fam.fam_offsets, dtype=np.uint64)
         sds = np.ascontiguousarray(fam.sds, dtype=PROTOSD_DTYPE)

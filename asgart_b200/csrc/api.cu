@@ -13,6 +13,8 @@
 
 namespace ab200 {
 thread_local LaunchCounter* g_launch_counter = nullptr;
+HostStalls g_host_stalls;
+thread_local DevicePool* g_device_pool = nullptr;
 
 struct Index32 { DevBuf<u32> sa, lut_lo, lut_hi, deep; int deep_depth = 0; };
 struct Index64 { DevBuf<u64> sa, lut_lo, lut_hi, deep; int deep_depth = 0; };
@@ -50,6 +52,7 @@ struct asgart_b200_partial {
 };
 
 struct asgart_b200_ctx {
+    DevicePool pool;   // first member: destroyed last, after every buffer that came from it
     int device = 0;
     cudaStream_t stream = nullptr;
     std::string err;
@@ -58,6 +61,7 @@ struct asgart_b200_ctx {
     int want_bits = 0, idx_bits = 0;
     DevBuf<u8> d_text;
     DevBuf<u64> d_pt, d_pn;
+    DevBuf<u8> shard_blob;   // device-resident partial of the last search_shard_dev call
     int pn_mode = -1;
     Index32 ix32;
     Index64 ix64;
@@ -75,9 +79,10 @@ struct ApiGuard {
     asgart_b200_ctx* c;
     explicit ApiGuard(asgart_b200_ctx* ctx) : c(ctx) {
         g_launch_counter = &ctx->launches;
+        g_device_pool = &ctx->pool;
         CUDA_CHECK(cudaSetDevice(ctx->device));
     }
-    ~ApiGuard() { g_launch_counter = nullptr; }
+    ~ApiGuard() { g_launch_counter = nullptr; g_device_pool = nullptr; }
 };
 
 template <typename F>
@@ -169,7 +174,9 @@ struct LutHook : SaKeyHook {
         ix.deep.alloc(M, stream);
         ix.deep.zero();
         ix.deep_depth = depth;
-        lut_from_keys_kernel<IdxT><<<unsigned(ceil_div(n, 256)), 256, 0, stream>>>(d_keys, n, b, p0, map, depth, ix.lut_lo.p, ix.lut_hi.p,
+        DevBuf<LutCodeMap> d_map(1, stream);
+        CUDA_CHECK(cudaMemcpyAsync(d_map.p, &map, sizeof map, cudaMemcpyHostToDevice, stream));
+        lut_from_keys_kernel<IdxT><<<unsigned(ceil_div(n, 256)), 256, 0, stream>>>(d_keys, n, b, p0, d_map.p, depth, ix.lut_lo.p, ix.lut_hi.p,
                                                                                   ix.deep.p);
         KERNEL_CHECK();
         count_launch();
@@ -352,7 +359,7 @@ void run_probe_kernels(asgart_b200_ctx* ctx, ProbeParams<IdxT>& P, unsigned long
         CUDA_CHECK(cudaMemcpyAsync(&n_def, P.counters + CTR_DEFERRED, sizeof n_def, cudaMemcpyDeviceToHost, s));
         CUDA_CHECK(cudaStreamSynchronize(s));
         if (n_def) {
-            probe_deferred_kernel<IdxT><<<unsigned(ceil_div(n_def, 256)), 256, 0, s>>>(P, n_def);
+            probe_deferred_kernel<IdxT><<<unsigned(ceil_div(n_def * 32, 256)), 256, 0, s>>>(P, n_def);
             KERNEL_CHECK();
             count_launch();
         }
@@ -665,12 +672,15 @@ int32_t asgart_b200_ctx_create(int32_t device, asgart_b200_ctx** out) {
 
 void asgart_b200_ctx_destroy(asgart_b200_ctx* ctx) {
     if (!ctx) return;
+    if (getenv("ASGART_B200_DEBUG_TIMING"))
+        fprintf(stderr, "[asgart_b200] host stalls: %llu cudaMallocAsync %.2f ms, %llu SA-build read-backs %.2f ms (includes the kernels they wait for)\n",
+                (unsigned long long)g_host_stalls.allocs, g_host_stalls.alloc_ms, (unsigned long long)g_host_stalls.syncs, g_host_stalls.sync_ms);
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     ctx->t_sort.destroy(); ctx->t_gather.destroy(); ctx->t_rank.destroy(); ctx->t_probe.destroy(); ctx->t_emit.destroy(); ctx->t_scatter.destroy();
     if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
     if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
-    ctx->d_text.release(); ctx->d_pt.release(); ctx->d_pn.release();
+    ctx->d_text.release(); ctx->d_pt.release(); ctx->d_pn.release(); ctx->shard_blob.release();
     ctx->ix32 = Index32();
     ctx->ix64 = Index64();
     cudaStreamSynchronize(ctx->stream);
@@ -953,6 +963,100 @@ int32_t asgart_b200_ctx_finish(asgart_b200_ctx* ctx, const asgart_b200_chunk* ch
         }
         if (nm) CUDA_CHECK(cudaMemcpyAsync(d_matches.p, matches.data(), nm * 8, cudaMemcpyHostToDevice, s));
         ctx->st.h2d_bytes += words * 4 + ne * 12 + nm * 8;
+        asgart_b200_result* r = new asgart_b200_result();
+        try {
+            run_stage_b(ctx, plan, st, d_bits.p, ne, d_probe.p, d_cnt.p, d_moff.p, d_matches.p, nm, post_mask, r);
+        } catch (...) { delete r; throw; }
+        *out = r;
+        return ASGART_B200_OK;
+    });
+}
+
+// Device-resident form of search_shard / finish: the partial stays in HBM as one blob
+//   [ processed bits (4 B x words, padded to 8) | ev_probe (8 B x events) | matches (8 B x matches) | ev_cnt (4 B x events) ]
+// so that the exchange is a plain NCCL all-gather of device memory (meta = {p_begin, p_end, events, matches} travels apart).
+static u64 blob_bytes_of(u64 pb, u64 pe, u64 ne, u64 nm) { return ceil_div(ceil_div(pe - pb, 32) * 4, 8) * 8 + ne * 8 + nm * 8 + ne * 4; }
+
+int32_t asgart_b200_ctx_search_shard_dev(asgart_b200_ctx* ctx, const asgart_b200_chunk* chunks, int64_t n_chunks,
+                                         const asgart_b200_settings* st, int32_t shard, int32_t n_shards, void** d_blob,
+                                         int64_t* blob_bytes, uint64_t* meta) {
+    return guarded(ctx, [&]() -> int32_t {
+        if (!d_blob || !blob_bytes || !meta || n_shards < 1 || shard < 0 || shard >= n_shards) return fail(ctx, ASGART_B200_EINVAL, "bad shard arguments");
+        if (!ctx->have_index) return fail(ctx, ASGART_B200_ESTATE, "search before build_index");
+        ChunkPlan plan;
+        int rc = make_plan(ctx, chunks, n_chunks, st, plan);
+        if (rc) return rc;
+        ensure_needle(ctx, plan.mode);
+        u64 b, e;
+        shard_range(plan.total_probes, shard, n_shards, b, e);
+        EventTimer ts(ctx->stream);
+        ts.start();
+        StageA A;
+        if (ctx->idx_bits == 32) run_stage_a<u32>(ctx, plan, st, b, e, A);
+        else run_stage_a<u64>(ctx, plan, st, b, e, A);
+        cudaStream_t s = ctx->stream;
+        const u64 words = ceil_div(e - b, 32), wbytes = ceil_div(words * 4, 8) * 8;
+        const u64 total = blob_bytes_of(b, e, A.n_events, A.n_matches);
+        ctx->shard_blob.alloc(std::max<u64>(total, 8), s);
+        u8* p = ctx->shard_blob.p;
+        if (words) CUDA_CHECK(cudaMemcpyAsync(p, A.bits.p, words * 4, cudaMemcpyDeviceToDevice, s));
+        p += wbytes;
+        if (A.n_events) CUDA_CHECK(cudaMemcpyAsync(p, A.ev_probe.p, A.n_events * 8, cudaMemcpyDeviceToDevice, s));
+        p += A.n_events * 8;
+        if (A.n_matches) CUDA_CHECK(cudaMemcpyAsync(p, A.matches.p, A.n_matches * 8, cudaMemcpyDeviceToDevice, s));
+        p += A.n_matches * 8;
+        if (A.n_events) CUDA_CHECK(cudaMemcpyAsync(p, A.ev_cnt.p, A.n_events * 4, cudaMemcpyDeviceToDevice, s));
+        ts.stop();
+        ctx->st.ms_search += ts.ms();   // synchronises: the blob is complete when this call returns
+        meta[0] = b; meta[1] = e; meta[2] = A.n_events; meta[3] = A.n_matches;
+        *d_blob = ctx->shard_blob.p;
+        *blob_bytes = int64_t(total);
+        return ASGART_B200_OK;
+    });
+}
+
+int32_t asgart_b200_ctx_finish_dev(asgart_b200_ctx* ctx, const asgart_b200_chunk* chunks, int64_t n_chunks, const asgart_b200_settings* st,
+                                   const void* const* d_blobs, const uint64_t* metas, int32_t n_shards, uint32_t post_mask,
+                                   asgart_b200_result** out) {
+    return guarded(ctx, [&]() -> int32_t {
+        if (!out || !d_blobs || !metas || n_shards < 1) return fail(ctx, ASGART_B200_EINVAL, "bad finish arguments");
+        *out = nullptr;
+        if (!ctx->have_strand) return fail(ctx, ASGART_B200_ESTATE, "finish before load_strand");
+        ChunkPlan plan;
+        int rc = make_plan(ctx, chunks, n_chunks, st, plan);
+        if (rc) return rc;
+        u64 expect = 0, ne = 0, nm = 0;
+        for (int r = 0; r < n_shards; ++r) {
+            const u64 pb = metas[4 * r], pe = metas[4 * r + 1];
+            if (pb != expect || pe < pb || pe > plan.total_probes || ((pb & 31) && pb != plan.total_probes) || (!d_blobs[r] && pe > pb))
+                return fail(ctx, ASGART_B200_EINVAL, "partials are not the consecutive shards of this plan");
+            expect = pe;
+            ne += metas[4 * r + 2]; nm += metas[4 * r + 3];
+        }
+        if (expect != plan.total_probes) return fail(ctx, ASGART_B200_EINVAL, "partials do not cover all probes");
+        cudaStream_t s = ctx->stream;
+        const u64 words = ceil_div(plan.total_probes, 32);
+        DevBuf<u32> d_bits(words, s), d_cnt(ne, s);
+        DevBuf<u64> d_probe(ne, s), d_moff(ne, s), d_matches(nm, s);
+        u64 e0 = 0, m0 = 0;
+        for (int r = 0; r < n_shards; ++r) {
+            const u64 pb = metas[4 * r], pe = metas[4 * r + 1], re = metas[4 * r + 2], rm = metas[4 * r + 3];
+            const u64 w = ceil_div(pe - pb, 32), wbytes = ceil_div(w * 4, 8) * 8;
+            const u8* p = static_cast<const u8*>(d_blobs[r]);
+            if (w) CUDA_CHECK(cudaMemcpyAsync(d_bits.p + (pb >> 5), p, w * 4, cudaMemcpyDeviceToDevice, s));
+            p += wbytes;
+            if (re) CUDA_CHECK(cudaMemcpyAsync(d_probe.p + e0, p, re * 8, cudaMemcpyDeviceToDevice, s));
+            p += re * 8;
+            if (rm) CUDA_CHECK(cudaMemcpyAsync(d_matches.p + m0, p, rm * 8, cudaMemcpyDeviceToDevice, s));
+            p += rm * 8;
+            if (re) CUDA_CHECK(cudaMemcpyAsync(d_cnt.p + e0, p, re * 4, cudaMemcpyDeviceToDevice, s));
+            e0 += re; m0 += rm;
+        }
+        if (ne) {
+            const u32* cp = d_cnt.p; u64* mp = d_moff.p;
+            device_scan<u64, SumOp>([cp] __device__(u64 e) { return u64(cp[e]); }, [mp] __device__(u64 e, u64 exc, u64) { mp[e] = exc; },
+                                    ne, (u64*)nullptr, s);
+        }
         asgart_b200_result* r = new asgart_b200_result();
         try {
             run_stage_b(ctx, plan, st, d_bits.p, ne, d_probe.p, d_cnt.p, d_moff.p, d_matches.p, nm, post_mask, r);

@@ -5,7 +5,7 @@
 //   device_scan        exclusive scan of the digit-major table hist[digit][tile] -> global offset of every (digit, tile)
 //   rs_scatter_kernel  stable in-tile ranking (ballot match + shared atomics), tile reordered in shared memory so that
 //                      each digit's run leaves the SM as contiguous, coalesced stores          reads+writes keys, values
-// Keys are u64 or U128 (two u64 words; used when suffix indices need more than 32 bits), values u32 or u64.
+// Keys are u32, u64 or U128 (two u64 words; used when suffix indices need more than 32 bits), values u32 or u64.
 // HBM traffic per pass and element: 2*sizeof(Key) + sizeof(Key) [histogram re-read] + 2*sizeof(Val).
 #pragma once
 #include "common.cuh"
@@ -19,6 +19,7 @@ struct U128 {
 __host__ __device__ __forceinline__ bool operator==(const U128& a, const U128& b) { return a.hi == b.hi && a.lo == b.lo; }
 __host__ __device__ __forceinline__ bool operator!=(const U128& a, const U128& b) { return !(a == b); }
 
+__device__ __forceinline__ u32 rs_digit(u32 k, int shift) { return (k >> shift) & 255u; }
 __device__ __forceinline__ u32 rs_digit(u64 k, int shift) { return u32(k >> shift) & 255u; }
 __device__ __forceinline__ u32 rs_digit(const U128& k, int shift) {
     if (shift >= 64) return u32(k.hi >> (shift - 64)) & 255u;

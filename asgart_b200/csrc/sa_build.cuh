@@ -22,6 +22,7 @@
 #include "common.cuh"
 #include "radix_sort.cuh"
 #include "scan.cuh"
+#include "scatter.cuh"
 
 namespace ab200 {
 
@@ -209,8 +210,11 @@ void build_suffix_array(const u8* d_text, u64 n, IdxT* d_sa, IdxT* d_rank, cudaS
     using Acc = FlagAcc<IdxT>;
     if (n == 0) return;
     auto sync_read = [&](void* dst, const void* src, size_t bytes) {
+        const double t0 = host_now_ms();
         CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, stream));
         CUDA_CHECK(cudaStreamSynchronize(stream));
+        g_host_stalls.sync_ms += host_now_ms() - t0;
+        g_host_stalls.syncs++;
     };
 
     // ---- 0. alphabet
@@ -257,7 +261,7 @@ void build_suffix_array(const u8* d_text, u64 n, IdxT* d_sa, IdxT* d_rank, cudaS
         std::vector<int> shifts;
         for (int s = 0; s < b * p0; s += 8) shifts.push_back(s);
         // the sorted suffix indices must end up in d_sa itself: with an even number of passes they start there
-        DevBuf<u64> keysA(n, stream), keysB(n, stream);
+        DevBuf<u64> keysA(n + 2, stream), keysB(n + 2, stream);   // + slack: the scatter scratch carved from them is 16-byte aligned
         DevBuf<IdxT> valsT(n, stream);
         u64 *k = keysA.p, *ka = keysB.p;
         IdxT *v = (shifts.size() % 2 == 0) ? d_sa : valsT.p, *va = (shifts.size() % 2 == 0) ? valsT.p : d_sa;
@@ -289,12 +293,15 @@ void build_suffix_array(const u8* d_text, u64 n, IdxT* d_sa, IdxT* d_rank, cudaS
         GA.alloc(UA, stream); IA.alloc(UA, stream); HSA.alloc(NGA, stream);
         GS.alloc(US, stream); IS.alloc(US, stream);
         IdxT *ga = GA.p, *ia = IA.p, *hsa = HSA.p, *gs = GS.p, *is = IS.p;
+        // rank by sorted position goes to the dead half of the value ping-pong, then to text order by the sliced scatter
+        // (the other dead buffer, the alternate keys, is its partition scratch)
+        IdxT* rpos = valsT.p;
         plan.finish(in, [=] __device__(u64 i, const Acc& exc, const Acc& inc) {
             const u64 cur = kk[i];
             const bool head = i == 0 || kk[i - 1] != cur;
             const bool tail = i + 1 == n || kk[i + 1] != cur;
             const IdxT idx = vv[i];
-            d_rank[idx] = inc.a;
+            rpos[i] = inc.a;
             if (head && tail) return;
             if (cur == (cur & sym_mask) * rep_unit) { gs[exc.d] = inc.a; is[exc.d] = idx; }
             else {
@@ -302,7 +309,10 @@ void build_suffix_array(const u8* d_text, u64 n, IdxT* d_sa, IdxT* d_rank, cudaS
                 if (head) hsa[exc.e] = exc.c;
             }
         });
-        if (st && st->rank) st->rank->end(3, 0);
+        static_assert(sizeof(u64) >= 2 * sizeof(IdxT) || sizeof(IdxT) == 8, "alternate key buffer holds the scatter scratch");
+        IdxT* scr = sizeof(IdxT) == 4 ? reinterpret_cast<IdxT*>(ka) : nullptr;
+        inverse_scatter<IdxT>(d_sa, rpos, n, d_rank, n, scr, scr ? scr + (n + 3) / 4 * 4 : nullptr, stream);
+        if (st && st->rank) st->rank->end(4, 0);
     }
 
     // ---- 3. run round: suffixes starting a run of >= p0 equal symbols are ordered by (symbol after the run, run length)

@@ -111,22 +111,31 @@ __device__ __forceinline__ bool key_slot4(u64 key, int b, int p0, int depth, con
 // 8-mer LUT (Searcher::new, src/searcher.rs:99-143) and, when depth > 0, the first suffix of every ACGT-only
 // `depth`-mer (0 = not seen; position 0 is always the '$' suffix) from the sorted initial keys. Needs p0 >= 8, depth.
 template <typename IdxT>
-__global__ void lut_from_keys_kernel(const u64* __restrict__ keys, u64 n1, int b, int p0, const LutCodeMap map, int depth,
-                                     IdxT* __restrict__ lut_lo, IdxT* __restrict__ lut_hi, IdxT* __restrict__ deep) {
+__global__ void __launch_bounds__(256) lut_from_keys_kernel(const u64* __restrict__ keys, u64 n1, int b, int p0, const LutCodeMap* __restrict__ map, int depth,
+                                                            IdxT* __restrict__ lut_lo, IdxT* __restrict__ lut_hi, IdxT* __restrict__ deep) {
+    __shared__ LutCodeMap smap;   // dynamically indexed: a by-value kernel parameter would be copied to every thread's stack, so it comes by pointer
+    if (threadIdx.x < 16) { smap.d5[threadIdx.x] = map->d5[threadIdx.x]; smap.d4[threadIdx.x] = map->d4[threadIdx.x]; }
+    __syncthreads();
     const u64 i = u64(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= n1) return;
     const u64 cur = keys[i];
-    const u64 prev = i > 0 ? keys[i - 1] : 0;
-    u32 cs = 0, ps = 0;
-    const bool cur_ok = key_slot5(cur, b, p0, map, cs);
-    const bool prev_ok = i > 0 && key_slot5(prev, b, p0, map, ps);
-    if (cur_ok && (!prev_ok || ps != cs)) lut_lo[cs] = IdxT(i);
-    if (prev_ok && (!cur_ok || ps != cs)) lut_hi[ps] = IdxT(i);
-    if (i + 1 == n1 && cur_ok) lut_hi[cs] = IdxT(n1);
+    const u64 prev = i > 0 ? keys[i - 1] : ~cur;
+    // slots only change where the leading symbols do: decode the (rare) boundaries only
+    const int s8 = b * (p0 - 8);
+    if ((cur >> s8) != (prev >> s8) || i + 1 == n1) {
+        u32 cs = 0, ps = 0;
+        const bool cur_ok = key_slot5(cur, b, p0, smap, cs);
+        const bool prev_ok = i > 0 && key_slot5(prev, b, p0, smap, ps);
+        if (cur_ok && (!prev_ok || ps != cs)) lut_lo[cs] = IdxT(i);
+        if (prev_ok && (!cur_ok || ps != cs)) lut_hi[ps] = IdxT(i);
+        if (i + 1 == n1 && cur_ok) lut_hi[cs] = IdxT(n1);
+    }
     if (depth > 0) {
-        const bool c4 = key_slot4(cur, b, p0, depth, map, cs);
-        const bool p4 = i > 0 && key_slot4(prev, b, p0, depth, map, ps);
-        if (c4 && (!p4 || ps != cs)) deep[cs] = IdxT(i);
+        const int sd = b * (p0 - depth);
+        if ((cur >> sd) != (prev >> sd)) {
+            u32 cs = 0;
+            if (key_slot4(cur, b, p0, depth, smap, cs)) deep[cs] = IdxT(i);
+        }
     }
 }
 
@@ -183,13 +192,21 @@ struct ProbeState {
     u64 lo = 0, hi = 0, surv = 0, alg = 0;
 };
 
-// filters + cardinality (src/automaton.rs:105-117) over SA[lo, hi), then the per-probe outputs
+constexpr u64 kDeferRange = u64(1) << 63;  // deferred entry: the equal range is known (out_lo / out_raw), only the filters are left
+constexpr u64 kInlineMatches = 32;         // longer match intervals are filtered by a whole warp (probe_deferred_kernel)
+
+// per-probe outputs once the equal range [S.lo, S.hi) is known; returns false when the filters are left to a warp
+// filters + cardinality: src/automaton.rs:105-117
 template <typename IdxT>
-__device__ __forceinline__ void probe_finish(const ProbeParams<IdxT>& P, const ChunkDev& ch, u64 g, u64 i, u64 bucket8, ProbeState& S) {
+__device__ __forceinline__ bool probe_finish(const ProbeParams<IdxT>& P, const ChunkDev& ch, u64 g, u64 i, u64 bucket8, bool may_defer,
+                                             ProbeState& S) {
     S.searched = true;
     S.alg = 24ull * (ceil_log2_u64(bucket8 + 1) + 1) + 8ull * (S.hi - S.lo);
     const u64 o = g - P.p_begin;
-    if (P.rng_lo) { P.rng_lo[o] = i64(S.lo); P.rng_hi[o] = i64(S.hi); return; }
+    if (P.rng_lo) { P.rng_lo[o] = i64(S.lo); P.rng_hi[o] = i64(S.hi); return true; }
+    P.out_lo[o] = IdxT(S.lo);
+    P.out_raw[o] = IdxT(S.hi - S.lo);
+    if (may_defer && S.hi - S.lo > kInlineMatches) return false;
     const bool rev = P.reverse != 0;
     for (u64 j = S.lo; j < S.hi; ++j) {
         if (match_survives(u64(P.SA[j]), i, ch.c0, ch.len, rev)) {
@@ -197,15 +214,13 @@ __device__ __forceinline__ void probe_finish(const ProbeParams<IdxT>& P, const C
         }
     }
     if (S.surv > P.max_card) { S.skip_card = true; S.surv = 0; } else S.processed = true;
-    P.out_lo[o] = IdxT(S.lo);
-    P.out_raw[o] = IdxT(S.hi - S.lo);
     P.out_surv[o] = u32(S.surv);
+    return true;
 }
 
 // the reference's own search: 8-mer bucket, then the literal lock-step bisection with the forced-Less comparator
 template <typename IdxT>
-__device__ __forceinline__ void probe_literal(const ProbeParams<IdxT>& P, const ChunkDev& ch, u64 g, u64 i, u64 q, const Win& pw_raw,
-                                              ProbeState& S) {
+__device__ __forceinline__ u64 probe_literal(const ProbeParams<IdxT>& P, u64 q, const Win& pw_raw, ProbeState& S) {
     const int k = int(P.k);
     const Win pw0 = mask_window(pw_raw, k < 32 ? k : 32);
     u32 slot = 0;
@@ -224,7 +239,7 @@ __device__ __forceinline__ void probe_literal(const ProbeParams<IdxT>& P, const 
     if (r1 < r0) r1 = r0;  // only reachable through Q6; the reference would panic on the slice
     S.lo = lstart + r0;
     S.hi = lstart + r1;
-    probe_finish(P, ch, g, i, rstart - lstart, S);
+    return rstart - lstart;
 }
 
 template <typename IdxT>
@@ -248,14 +263,15 @@ constexpr int kProbeLinear = 8;  // deep buckets up to this size are compared in
 // One lane per probe position. Probes whose first deep_depth bases are all ACGT start from the deep table's bucket
 // (a few suffixes) and compare them all at once; the equal range of a monotone comparator does not depend on how it is
 // searched, so this is the reference's answer whenever its own 8-mer bucket holds none of the last k-1 suffixes. Every
-// other probe (N among the first bases, flagged bucket, no deep table) is handed to probe_literal, in this kernel when
-// P.deferred is null and in probe_deferred_kernel otherwise (keeps the long bisections out of the short warps).
+// other probe (N among the first bases, flagged bucket, no deep table) takes probe_literal, in this kernel when
+// P.deferred is null and in probe_deferred_kernel otherwise (keeps the long bisections out of the short warps); probes
+// with long match intervals leave the filter pass to that kernel as well.
 template <typename IdxT>
 __global__ void __launch_bounds__(256) probe_search_kernel(const ProbeParams<IdxT> P) {
     const u64 g = P.p_begin + u64(blockIdx.x) * blockDim.x + threadIdx.x;
     const bool in_range = g < P.p_end;
     ProbeState S;
-    bool defer = false;
+    u64 defer = 0;
     if (in_range) {
         const ChunkDev ch = P.chunks[chunk_of_probe(P.chunks, P.n_chunks, g)];
         const u64 i = (g - ch.probe_base + 1) * P.s;
@@ -298,19 +314,20 @@ __global__ void __launch_bounds__(256) probe_search_kernel(const ProbeParams<Idx
                 equal_range_lockstep(B, [&](u64 ix) -> int { return cmp_kmer(PT, u64(sub[ix]), PN, q, k, pw0); }, r0, r1);
                 S.lo = lo0 + r0; S.hi = lo0 + r1;
             }
-            probe_finish(P, ch, g, i, bucket8, S);
+            if (!probe_finish(P, ch, g, i, bucket8, P.deferred != nullptr, S)) defer = g | kDeferRange;
         } else if (P.deferred) {
-            defer = true;
+            defer = g | (u64(1) << 62);  // bit 62 only marks the entry as present (g may be 0)
         } else {
-            probe_literal(P, ch, g, i, q, pw_raw, S);
+            const u64 bucket8 = probe_literal(P, q, pw_raw, S);
+            probe_finish(P, ch, g, i, bucket8, false, S);
         }
     }
-    const unsigned dm = __ballot_sync(0xffffffffu, defer);
+    const unsigned dm = __ballot_sync(0xffffffffu, defer != 0);
     if (dm) {
         unsigned long long base = 0;
         if (lane_id() == 0) base = atomicAdd(&P.counters[CTR_DEFERRED], (unsigned long long)__popc(dm));
         base = __shfl_sync(0xffffffffu, base, 0);
-        if (defer) P.deferred[base + __popc(dm & lanemask_lt())] = g;
+        if (defer) P.deferred[base + __popc(dm & lanemask_lt())] = defer;
     }
     const unsigned bits = __ballot_sync(0xffffffffu, S.processed);
     if (lane_id() == 0 && !P.rng_lo) {
@@ -320,20 +337,47 @@ __global__ void __launch_bounds__(256) probe_search_kernel(const ProbeParams<Idx
     probe_account(P, S);
 }
 
-// the probes probe_search_kernel left over, one lane each
+// The probes probe_search_kernel left over, one warp each: the lanes run the literal search in lock step (same
+// addresses: one transaction per load) and share the filter pass over the match interval.
 template <typename IdxT>
 __global__ void __launch_bounds__(256) probe_deferred_kernel(const ProbeParams<IdxT> P, u64 n_deferred) {
-    const u64 j = u64(blockIdx.x) * blockDim.x + threadIdx.x;
+    const u64 j = (u64(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    if (j >= n_deferred) return;
+    const u64 e = P.deferred[j];
+    const u64 g = e & ~(kDeferRange | (u64(1) << 62));
+    const u64 o = g - P.p_begin;
+    const ChunkDev ch = P.chunks[chunk_of_probe(P.chunks, P.n_chunks, g)];
+    const u64 i = (g - ch.probe_base + 1) * P.s;
+    const u64 q = ch.needle_start + i;
     ProbeState S;
-    if (j < n_deferred) {
-        const u64 g = P.deferred[j];
-        const ChunkDev ch = P.chunks[chunk_of_probe(P.chunks, P.n_chunks, g)];
-        const u64 i = (g - ch.probe_base + 1) * P.s;
-        const u64 q = ch.needle_start + i;
-        probe_literal(P, ch, g, i, q, load_window(P.PN, q), S);
-        if (S.processed) { const u64 o = g - P.p_begin; atomicOr(&P.proc_bits[o >> 5], 1u << (o & 31u)); }
+    u64 alg = 0;
+    if (e & kDeferRange) {
+        S.lo = u64(P.out_lo[o]); S.hi = S.lo + u64(P.out_raw[o]);   // searched and accounted by probe_search_kernel
+    } else {
+        const u64 bucket8 = probe_literal(P, q, load_window(P.PN, q), S);
+        alg = 24ull * (ceil_log2_u64(bucket8 + 1) + 1) + 8ull * (S.hi - S.lo);
+        if (P.rng_lo) {
+            if (lane_id() == 0) { P.rng_lo[o] = i64(S.lo); P.rng_hi[o] = i64(S.hi); }
+            return;
+        }
     }
-    probe_account(P, S);
+    const bool rev = P.reverse != 0;
+    u64 surv = 0;
+    for (u64 j0 = S.lo; j0 < S.hi && surv <= P.max_card; j0 += 32) {
+        const u64 jj = j0 + lane_id();
+        const bool keep = jj < S.hi && match_survives(u64(P.SA[jj]), i, ch.c0, ch.len, rev);
+        surv += __popc(__ballot_sync(0xffffffffu, keep));
+    }
+    if (lane_id() == 0) {
+        const bool skip_card = surv > P.max_card;
+        if (skip_card) surv = 0;
+        P.out_lo[o] = IdxT(S.lo); P.out_raw[o] = IdxT(S.hi - S.lo); P.out_surv[o] = u32(surv);
+        if (!skip_card) atomicOr(&P.proc_bits[o >> 5], 1u << (o & 31u));
+        if (!(e & kDeferRange)) atomicAdd(&P.counters[CTR_SEARCHED], 1ull);
+        if (skip_card) atomicAdd(&P.counters[CTR_SKIP_CARD], 1ull);
+        if (surv) atomicAdd(&P.counters[CTR_MATCHES], (unsigned long long)surv);
+        if (alg) atomicAdd(&P.counters[CTR_ALG_BYTES], (unsigned long long)alg);
+    }
 }
 
 // pair of running sums: match offset and event index

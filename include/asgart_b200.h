@@ -143,6 +143,18 @@ ASGART_B200_API int32_t asgart_b200_ctx_finish(asgart_b200_ctx *ctx, const asgar
                                                const asgart_b200_settings *settings, const uint8_t *const *partials,
                                                const int64_t *partial_sizes, int32_t n_shards, uint32_t post_mask,
                                                asgart_b200_result **out);
+/* Device-resident form of the same exchange (what asgart_b200/dist.py uses under NCCL): the partial stays in HBM as one
+ * blob owned by the context (valid until its next search_shard_dev call), meta[4] = {p_begin, p_end, events, matches}.
+ * finish_dev takes, per shard, a device pointer to that shard's blob (any device memory of this GPU, e.g. the output of
+ * an NCCL all-gather) and its 4 meta words. */
+ASGART_B200_API int32_t asgart_b200_ctx_search_shard_dev(asgart_b200_ctx *ctx, const asgart_b200_chunk *chunks,
+                                                         int64_t n_chunks, const asgart_b200_settings *settings,
+                                                         int32_t shard, int32_t n_shards, void **d_blob,
+                                                         int64_t *blob_bytes, uint64_t *meta);
+ASGART_B200_API int32_t asgart_b200_ctx_finish_dev(asgart_b200_ctx *ctx, const asgart_b200_chunk *chunks, int64_t n_chunks,
+                                                   const asgart_b200_settings *settings, const void *const *d_blobs,
+                                                   const uint64_t *metas, int32_t n_shards, uint32_t post_mask,
+                                                   asgart_b200_result **out);
 
 /* results */
 ASGART_B200_API int64_t asgart_b200_result_n_families(const asgart_b200_result *r);

@@ -308,6 +308,18 @@ def test_sharded_search_equals_single(n_shards):
             single = ctx.search(prep.chunks, st, ab.POST_ALL).as_lists()
             parts = [ctx.search_shard(prep.chunks, st, r, n_shards) for r in range(n_shards)]
             assert ctx.finish(prep.chunks, st, parts, ab.POST_ALL).as_lists() == single, label
+            # device-resident form (what the NCCL path exchanges): blobs cloned to torch memory, as an all-gather leaves them
+            import torch
+            from asgart_b200.dist import _DevMem
+            blobs, metas = [], []
+            for r in range(n_shards):
+                ptr, nbytes, meta = ctx.search_shard_dev(prep.chunks, st, r, n_shards)
+                blobs.append(torch.as_tensor(_DevMem(ptr, nbytes), device="cuda:0").clone() if nbytes else
+                             torch.zeros(8, dtype=torch.uint8, device="cuda:0"))
+                metas.append(meta)
+            torch.cuda.synchronize()
+            got = ctx.finish_dev(prep.chunks, st, [b.data_ptr() for b in blobs], np.stack(metas), ab.POST_ALL)
+            assert got.as_lists() == single, label
 
 
 def test_run_files_json_identical_to_oracle(tmp_path):

@@ -15,6 +15,7 @@ def main():
     config = int(sys.argv[1]) if len(sys.argv) > 1 else 2
     scale_n = int(sys.argv[2]) if len(sys.argv) > 2 else 0
     reps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
+    device = int(sys.argv[4]) if len(sys.argv) > 4 else 0
     flags = {1: dict(), 2: dict(reverse=True, complement=True, skip_masked=True), 3: dict(reverse=True, complement=True),
              4: dict(reverse=True, complement=True), 0: dict()}[config]
     st = ab.RunSettings(**flags)
@@ -23,7 +24,7 @@ def main():
     prep = ab.Prepared.from_memory(ab.normalise(g, st.skip_masked), fr)
     print(f"generated n={len(g)} in {time.time() - t0:.2f}s; chunks={len(prep.chunks)}", flush=True)
     strand = np.array(prep.strand)
-    with ab.Context(0) as ctx:
+    with ab.Context(device) as ctx:
         for r in range(reps):
             ctx.reset_stats()
             t0 = time.time()

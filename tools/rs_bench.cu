@@ -11,7 +11,7 @@
 #include "../asgart_b200/csrc/common.cuh"
 #include "../asgart_b200/csrc/scan.cuh"
 
-namespace ab200 { thread_local LaunchCounter* g_launch_counter = nullptr; }
+namespace ab200 { thread_local LaunchCounter* g_launch_counter = nullptr; HostStalls g_host_stalls; thread_local DevicePool* g_device_pool = nullptr; }
 using namespace ab200;
 
 __device__ __forceinline__ u32 digit_of(u64 k, int shift) { return u32(k >> shift) & 255u; }
