@@ -550,8 +550,7 @@ void run_stage_b(asgart_b200_ctx* ctx, const ChunkPlan& plan, const asgart_b200_
         DevBuf<i64> op_target(n_matches, s);
         DevBuf<u64> a_ls(n_matches, s), a_le(n_matches, s), a_rs(n_matches, s), a_re(n_matches, s), a_death(n_matches, s);
         DevBuf<u32> act_arm(n_matches, s);
-        DevBuf<u64> act_rs(n_matches, s), act_re(n_matches, s), act_death(n_matches, s), act_ls(n_matches, s);
-        DevBuf<i64> act_thr(n_matches, s);
+        DevBuf<u64> act_wlo(n_matches, s), act_whi(n_matches, s), act_death(n_matches, s), act_ls(n_matches, s);
         DevBuf<asgart_b200_protosd> out_sd(n_matches, s);
         DevBuf<u8> out_flag(n_matches, s);
         out_flag.zero();
@@ -559,7 +558,7 @@ void run_stage_b(asgart_b200_ctx* ctx, const ChunkPlan& plan, const asgart_b200_
         B.ev_i = ev_i.p; B.ev_t = ev_t.p; B.ev_moff = ev_moff; B.ev_cnt = ev_cnt; B.ev_chunk = ev_chunk.p;
         B.seg_first = seg_first.p; B.matches = matches; B.op_target = op_target.p;
         B.a_ls = a_ls.p; B.a_le = a_le.p; B.a_rs = a_rs.p; B.a_re = a_re.p; B.a_death = a_death.p;
-        B.act_arm = act_arm.p; B.act_ls = act_ls.p; B.act_rs = act_rs.p; B.act_re = act_re.p; B.act_thr = act_thr.p; B.act_death = act_death.p;
+        B.act_arm = act_arm.p; B.act_ls = act_ls.p; B.act_wlo = act_wlo.p; B.act_whi = act_whi.p; B.act_death = act_death.p;
         B.out_sd = out_sd.p; B.out_flag = out_flag.p; B.chunk_tc = tc.p; B.chunks = plan.dev.p;
         if (getenv("ASGART_B200_AUTOMATON_V1"))  // thread-per-segment reference kernel, kept for A/B checks
             automaton_kernel<<<unsigned(ceil_div(n_seg, 64)), 64, 0, s>>>(B, plan.ap, n_seg, st->reverse ? 1 : 0, st->complement ? 1 : 0);

@@ -56,9 +56,8 @@ struct AutoBuffers {
     // active list of the warp kernel (arms that can still be extended), same capacity, creation order preserved
     u32* act_arm;   // index into the segment's arm store
     u64* act_ls;
-    u64* act_rs;
-    u64* act_re;
-    i64* act_thr;   // max(G, trunc(0.1 * left length)), refreshed when the arm is extended
+    u64* act_wlo;   // a match at ms extends the arm iff wlo <= ms < whi (and the arm is active):
+    u64* act_whi;   //   wlo = right.end - k + 1, whi = right.end + max(G, trunc(0.1 * left length))   (see arm_window)
     u64* act_death;
     asgart_b200_protosd* out_sd;               // slot array, indexed like matches
     u8* out_flag;                              // 0 empty, 1 duplicon, 3 duplicon that opens a family
@@ -116,11 +115,20 @@ struct AutoCmd {
     u32 in_smem;
 };
 
+// try_extend_arms (src/automaton.rs:66-85) as a window test. With m.end > a.right.end, d_ss (:207-216) is 0 when
+// m.start <= a.right.end and m.start - a.right.end otherwise (arms are at least k long), so
+//   d_ss(a.right, m) < thr  and  m.end > a.right.end    <=>    a.right.end - k < m.start < a.right.end + thr,
+// thr = max(G, trunc(0.1 * left length)) > 0 (:69, the f64 product truncated like `as i64`).
+__device__ __forceinline__ void arm_window(u64 re, u64 left_len, u64 k, i64 G, u64& wlo, u64& whi) {
+    const i64 tenth = i64(0.1 * double(left_len));
+    wlo = re - k + 1;
+    whi = re + u64(G > tenth ? G : tenth);
+}
+
 template <int W, int CAP>
 __global__ void __launch_bounds__(W * 32) automaton_segment_kernel(AutoBuffers B, AutoParams P, u64 n_segments, u64 n_matches, u64 n_events,
                                                                    u32 reversed_flag, u32 complemented_flag) {
-    __shared__ u64 s_rs[CAP], s_re[CAP], s_ls[CAP], s_death[CAP];
-    __shared__ i64 s_thr[CAP];
+    __shared__ u64 s_wlo[CAP], s_whi[CAP], s_ls[CAP], s_death[CAP];
     __shared__ u32 s_arm[CAP];
     __shared__ AutoCmd s_cmd;
     const u64 sidx = blockIdx.x;
@@ -135,23 +143,22 @@ __global__ void __launch_bounds__(W * 32) automaton_segment_kernel(AutoBuffers B
     const unsigned FULL = 0xffffffffu;
     const u64* matches = B.matches;
     i64* op_target = B.op_target;
-    u32* g_arm = B.act_arm + slot0; u64* g_rs = B.act_rs + slot0; u64* g_re = B.act_re + slot0; u64* g_ls = B.act_ls + slot0;
-    i64* g_thr = B.act_thr + slot0; u64* g_death = B.act_death + slot0;
+    u32* g_arm = B.act_arm + slot0; u64* g_wlo = B.act_wlo + slot0; u64* g_whi = B.act_whi + slot0; u64* g_ls = B.act_ls + slot0;
+    u64* g_death = B.act_death + slot0;
 
     // classify matches [r_begin, cnt) step r_step*32 of one event against the snapshot of the active list
     auto classify = [&](u64 t, u64 m0, u32 cnt, u64 snap, bool smem, u32 w_first, u32 w_step) {
-        const u64* c_rs = smem ? s_rs : g_rs; const u64* c_re = smem ? s_re : g_re;
-        const i64* c_thr = smem ? s_thr : g_thr; const u64* c_death = smem ? s_death : g_death;
+        const u64* c_wlo = smem ? s_wlo : g_wlo; const u64* c_whi = smem ? s_whi : g_whi;
+        const u64* c_death = smem ? s_death : g_death;
         for (u32 r0 = w_first * 32; r0 < cnt; r0 += w_step * 32) {
             const u32 r = r0 + lane;
             const bool valid = r < cnt;
-            const u64 ms = valid ? matches[m0 + r] : 0, me = ms + P.k;
+            const u64 ms = valid ? matches[m0 + r] : 0;
             i64 target = -1;
             bool searching = valid;
             for (u64 a = 0; a < snap; ++a) {
                 if (__ballot_sync(FULL, searching) == 0) break;
-                const u64 re = c_re[a];
-                if (searching && c_death[a] >= t && me > re && d_ss_core(c_rs[a], re, ms, me) < c_thr[a]) { target = i64(a); searching = false; }
+                if (searching && ms >= c_wlo[a] && ms < c_whi[a] && c_death[a] >= t) { target = i64(a); searching = false; }
             }
             if (valid) op_target[m0 + r] = target;
         }
@@ -172,20 +179,28 @@ __global__ void __launch_bounds__(W * 32) automaton_segment_kernel(AutoBuffers B
     const ChunkDev ch = B.chunks[c];
     const u64 Tc = B.chunk_tc[c];
     u64* a_ls = B.a_ls + slot0; u64* a_le = B.a_le + slot0; u64* a_rs = B.a_rs + slot0; u64* a_re = B.a_re + slot0;
-    u32* act_arm = s_arm; u64* act_rs = s_rs; u64* act_re = s_re; u64* act_ls = s_ls; i64* act_thr = s_thr; u64* act_death = s_death;
+    u32* act_arm = s_arm; u64* act_wlo = s_wlo; u64* act_whi = s_whi; u64* act_ls = s_ls; u64* act_death = s_death;
     bool in_smem = true;
     u64 n_arms = 0, fam_start = 0, n_act = 0, max_death = 0, act_min_death = ~u64(0), cursor = slot0;
     const i64 Gi = i64(P.G);
+    bool chain_live = false;                        // the previous event had one match and it went to the first active arm
+    u64 last_t = 0, last_ms = 0; u32 last_cnt = 0;   // last event of the previous batch of 32
+    u64 new_wlo_off, new_whi_off;   // window of a fresh arm relative to its match start: [ms + 1, ms + k + thr(k))
+    {
+        u64 wl, wh;
+        arm_window(P.k, P.k, P.k, Gi, wl, wh);
+        new_wlo_off = wl; new_whi_off = wh;   // computed for ms = 0: re = k
+    }
 
     auto to_smem = [&]() {
-        act_arm = s_arm; act_rs = s_rs; act_re = s_re; act_ls = s_ls; act_thr = s_thr; act_death = s_death;
+        act_arm = s_arm; act_wlo = s_wlo; act_whi = s_whi; act_ls = s_ls; act_death = s_death;
         in_smem = true;
     };
     auto to_global = [&]() {  // copy the live entries to the segment's global slice and continue there
         for (u64 a = lane; a < n_act; a += 32) {
-            g_arm[a] = act_arm[a]; g_rs[a] = act_rs[a]; g_re[a] = act_re[a]; g_ls[a] = act_ls[a]; g_thr[a] = act_thr[a]; g_death[a] = act_death[a];
+            g_arm[a] = act_arm[a]; g_wlo[a] = act_wlo[a]; g_whi[a] = act_whi[a]; g_ls[a] = act_ls[a]; g_death[a] = act_death[a];
         }
-        act_arm = g_arm; act_rs = g_rs; act_re = g_re; act_ls = g_ls; act_thr = g_thr; act_death = g_death;
+        act_arm = g_arm; act_wlo = g_wlo; act_whi = g_whi; act_ls = g_ls; act_death = g_death;
         in_smem = false;
         __syncwarp();
     };
@@ -224,17 +239,17 @@ __global__ void __launch_bounds__(W * 32) automaton_segment_kernel(AutoBuffers B
         u64 w = 0, mn = ~u64(0);
         for (u64 base = 0; base < n_act; base += 32) {
             const u64 a = base + lane;
-            u32 arm = 0; u64 rs = 0, re = 0, ls = 0, death = 0; i64 thr = 0;
+            u32 arm = 0; u64 wlo = 0, whi = 0, ls = 0, death = 0;
             bool keep = false;
             if (a < n_act) {
-                arm = act_arm[a]; rs = act_rs[a]; re = act_re[a]; ls = act_ls[a]; thr = act_thr[a]; death = act_death[a];
+                arm = act_arm[a]; wlo = act_wlo[a]; whi = act_whi[a]; ls = act_ls[a]; death = act_death[a];
                 keep = death >= t;
             }
             const unsigned m = __ballot_sync(FULL, keep);
             __syncwarp();  // all reads of this block of 32 done before anyone overwrites (w <= base)
             if (keep) {
                 const u64 d = w + __popc(m & lt);
-                act_arm[d] = arm; act_rs[d] = rs; act_re[d] = re; act_ls[d] = ls; act_thr[d] = thr; act_death[d] = death;
+                act_arm[d] = arm; act_wlo[d] = wlo; act_whi[d] = whi; act_ls[d] = ls; act_death[d] = death;
                 mn = death < mn ? death : mn;
             }
             w += __popc(m);
@@ -246,6 +261,17 @@ __global__ void __launch_bounds__(W * 32) automaton_segment_kernel(AutoBuffers B
         __syncwarp();
     };
 
+    // ExtendArm applied to active entry a (:136-143)
+    auto extend = [&](u64 a, u64 i, u64 ms, u64 t) {
+        const u32 arm = act_arm[a];
+        const u64 le = i + P.k, re = ms + P.k;
+        a_le[arm] = le; a_re[arm] = re;
+        u64 wl, wh;
+        arm_window(re, le - act_ls[a], P.k, Gi, wl, wh);
+        act_wlo[a] = wl; act_whi[a] = wh;
+        act_death[a] = t + P.q_ext;
+    };
+
     for (u64 eb = e0; eb < e1; eb += 32) {
         u64 my_t = 0, my_i = 0, my_moff = 0, my_m0 = 0; u32 my_cnt = 0;
         if (eb + lane < e1) {
@@ -253,7 +279,34 @@ __global__ void __launch_bounds__(W * 32) automaton_segment_kernel(AutoBuffers B
             my_m0 = matches[my_moff];
         }
         const int nev = int(min(u64(32), e1 - eb));
+        // Chain test, independent of the automaton's state: event e "chains" when it and its predecessor carry one match
+        // each and, provided the predecessor extended (or created) some arm, that arm is still active at e and e's match
+        // falls into its window: t_e <= t_(e-1) + q_new and ms_(e-1) < ms_e < ms_(e-1) + k + G (the arm's true window is
+        // at least this wide). If that arm is the first of the active list it wins the match whatever else is active, the
+        // event changes nothing else, and a run of chained events collapses into its last one.
+        unsigned chain_mask;
+        {
+            u64 p_t = __shfl_up_sync(FULL, my_t, 1), p_ms = __shfl_up_sync(FULL, my_m0, 1);
+            u32 p_cnt = __shfl_up_sync(FULL, my_cnt, 1);
+            if (lane == 0) { p_t = last_t; p_ms = last_ms; p_cnt = last_cnt; }
+            const bool ch_ok = eb + lane < e1 && my_cnt == 1 && p_cnt == 1 && my_t <= p_t + P.q_new && my_m0 > p_ms &&
+                               my_m0 < p_ms + P.k + P.G;
+            chain_mask = __ballot_sync(FULL, ch_ok);
+            last_t = __shfl_sync(FULL, my_t, 31); last_ms = __shfl_sync(FULL, my_m0, 31); last_cnt = __shfl_sync(FULL, my_cnt, 31);
+        }
         for (int j = 0; j < nev; ++j) {
+            if (chain_live && ((chain_mask >> j) & 1u)) {
+                // run of chained events starting at j: only the last one leaves a trace (on the first active arm)
+                const unsigned rest = ~(chain_mask >> j);
+                const int run = rest ? (__ffs(rest) - 1) : (32 - j);
+                const int last = j + run - 1;
+                const u64 t = __shfl_sync(FULL, my_t, last), i = __shfl_sync(FULL, my_i, last), ms = __shfl_sync(FULL, my_m0, last);
+                if (lane == 0) extend(0, i, ms, t);
+                if (t + P.q_ext > max_death) max_death = t + P.q_ext;
+                __syncwarp();
+                j = last;
+                continue;
+            }
             const u64 t = __shfl_sync(FULL, my_t, j), i = __shfl_sync(FULL, my_i, j), m0 = __shfl_sync(FULL, my_moff, j);
             const u64 first_ms = __shfl_sync(FULL, my_m0, j);
             const u32 cnt = __shfl_sync(FULL, my_cnt, j);
@@ -262,45 +315,34 @@ __global__ void __launch_bounds__(W * 32) automaton_segment_kernel(AutoBuffers B
             if (in_smem && n_act + cnt > CAP) to_global();
             if (cnt == 1) {
                 // fast path (9 events in 10): one match, lanes = active arms, first hit in creation order by ballot
-                const u64 ms = first_ms, me = ms + P.k;
+                const u64 ms = first_ms;
                 i64 target = -1;
                 for (u64 base = 0; base < n_act; base += 32) {
                     const u64 a = base + lane;
                     bool hit = false;
-                    if (a < n_act) {
-                        const u64 re = act_re[a];
-                        hit = act_death[a] >= t && me > re && d_ss_core(act_rs[a], re, ms, me) < act_thr[a];
-                    }
+                    if (a < n_act) hit = ms >= act_wlo[a] && ms < act_whi[a] && act_death[a] >= t;
                     const unsigned m = __ballot_sync(FULL, hit);
                     if (m) { target = i64(base) + (__ffs(m) - 1); break; }
                 }
                 if (target >= 0) {
-                    if (lane == 0) {
-                        const u64 a = u64(target);
-                        const u32 arm = act_arm[a];
-                        const u64 le = i + P.k;
-                        a_le[arm] = le; a_re[arm] = me;
-                        act_re[a] = me;
-                        const i64 tenth = i64(0.1 * double(le - act_ls[a]));  // src/automaton.rs:69
-                        act_thr[a] = Gi > tenth ? Gi : tenth;
-                        act_death[a] = t + P.q_ext;
-                    }
+                    if (lane == 0) extend(u64(target), i, ms, t);
                     if (t + P.q_ext > max_death) max_death = t + P.q_ext;
                 } else {
                     if (lane == 0) {
-                        a_ls[n_arms] = i; a_le[n_arms] = i + P.k; a_rs[n_arms] = ms; a_re[n_arms] = me;
-                        act_arm[n_act] = u32(n_arms); act_rs[n_act] = ms; act_re[n_act] = me; act_ls[n_act] = i;
-                        const i64 tenth = i64(0.1 * double(P.k));
-                        act_thr[n_act] = Gi > tenth ? Gi : tenth;
+                        a_ls[n_arms] = i; a_le[n_arms] = i + P.k; a_rs[n_arms] = ms; a_re[n_arms] = ms + P.k;
+                        act_arm[n_act] = u32(n_arms); act_wlo[n_act] = ms + new_wlo_off; act_whi[n_act] = ms + new_whi_off; act_ls[n_act] = i;
                         act_death[n_act] = t + P.q_new;
                     }
+                    target = i64(n_act);
                     ++n_arms; ++n_act;
                     if (t + P.q_new > max_death) max_death = t + P.q_new;
                     if (t + P.q_new < act_min_death) act_min_death = t + P.q_new;
                 }
+                chain_live = target == 0;
                 __syncwarp();
                 continue;
             }
+            chain_live = false;
             const u64 snap = n_act;
             const bool single = cnt <= 32;
             i64 my_target = -1;
@@ -308,12 +350,11 @@ __global__ void __launch_bounds__(W * 32) automaton_segment_kernel(AutoBuffers B
             // phase 1
             if (single) {
                 const bool valid = lane < cnt;
-                const u64 ms = (cnt == 1) ? first_ms : (valid ? matches[m0 + lane] : 0), me = ms + P.k;
+                const u64 ms = valid ? matches[m0 + lane] : 0;
                 bool searching = valid;
                 for (u64 a = 0; a < snap; ++a) {
                     if (__ballot_sync(FULL, searching) == 0) break;
-                    const u64 re = act_re[a];
-                    if (searching && act_death[a] >= t && me > re && d_ss_core(act_rs[a], re, ms, me) < act_thr[a]) { my_target = i64(a); searching = false; }
+                    if (searching && ms >= act_wlo[a] && ms < act_whi[a] && act_death[a] >= t) { my_target = i64(a); searching = false; }
                 }
                 my_ms = ms;
             } else if (W > 1 && u64(cnt) * snap >= kHeavyEvent) {
@@ -338,16 +379,7 @@ __global__ void __launch_bounds__(W * 32) automaton_segment_kernel(AutoBuffers B
                 const unsigned any = __ballot_sync(FULL, ext);
                 if (any) {
                     const unsigned peers = __match_any_sync(FULL, ext ? target : i64(-1) - i64(lane));
-                    if (ext && (31 - __clz(peers)) == int(lane)) {
-                        const u64 a = u64(target);
-                        const u32 arm = act_arm[a];
-                        const u64 le = i + P.k, re = ms + P.k;
-                        a_le[arm] = le; a_re[arm] = re;
-                        act_re[a] = re;
-                        const i64 tenth = i64(0.1 * double(le - act_ls[a]));  // src/automaton.rs:69
-                        act_thr[a] = Gi > tenth ? Gi : tenth;
-                        act_death[a] = t + P.q_ext;
-                    }
+                    if (ext && (31 - __clz(peers)) == int(lane)) extend(u64(target), i, ms, t);
                     any_ext = true;
                     __syncwarp();  // a later round may extend the same arm again: keep rounds ordered
                 }
@@ -365,9 +397,7 @@ __global__ void __launch_bounds__(W * 32) automaton_segment_kernel(AutoBuffers B
                     const u64 off = __popc(m & lt);
                     const u64 arm = n_arms + off, a = n_act + off;
                     a_ls[arm] = i; a_le[arm] = i + P.k; a_rs[arm] = ms; a_re[arm] = ms + P.k;
-                    act_arm[a] = u32(arm); act_rs[a] = ms; act_re[a] = ms + P.k; act_ls[a] = i;
-                    const i64 tenth = i64(0.1 * double(P.k));
-                    act_thr[a] = Gi > tenth ? Gi : tenth;
+                    act_arm[a] = u32(arm); act_wlo[a] = ms + new_wlo_off; act_whi[a] = ms + new_whi_off; act_ls[a] = i;
                     act_death[a] = t + P.q_new;
                 }
                 if (m) { any_new = true; n_arms += __popc(m); n_act += __popc(m); }
