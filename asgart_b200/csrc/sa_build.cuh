@@ -261,7 +261,7 @@ void build_suffix_array(const u8* d_text, u64 n, IdxT* d_sa, IdxT* d_rank, cudaS
         std::vector<int> shifts;
         for (int s = 0; s < b * p0; s += 8) shifts.push_back(s);
         // the sorted suffix indices must end up in d_sa itself: with an even number of passes they start there
-        DevBuf<u64> keysA(n + 2, stream), keysB(n + 2, stream);   // + slack: the scatter scratch carved from them is 16-byte aligned
+        DevBuf<u64> keysA(n, stream), keysB(n, stream);
         DevBuf<IdxT> valsT(n, stream);
         u64 *k = keysA.p, *ka = keysB.p;
         IdxT *v = (shifts.size() % 2 == 0) ? d_sa : valsT.p, *va = (shifts.size() % 2 == 0) ? valsT.p : d_sa;
@@ -294,7 +294,6 @@ void build_suffix_array(const u8* d_text, u64 n, IdxT* d_sa, IdxT* d_rank, cudaS
         GS.alloc(US, stream); IS.alloc(US, stream);
         IdxT *ga = GA.p, *ia = IA.p, *hsa = HSA.p, *gs = GS.p, *is = IS.p;
         // rank by sorted position goes to the dead half of the value ping-pong, then to text order by the sliced scatter
-        // (the other dead buffer, the alternate keys, is its partition scratch)
         IdxT* rpos = valsT.p;
         plan.finish(in, [=] __device__(u64 i, const Acc& exc, const Acc& inc) {
             const u64 cur = kk[i];
@@ -309,9 +308,7 @@ void build_suffix_array(const u8* d_text, u64 n, IdxT* d_sa, IdxT* d_rank, cudaS
                 if (head) hsa[exc.e] = exc.c;
             }
         });
-        static_assert(sizeof(u64) >= 2 * sizeof(IdxT) || sizeof(IdxT) == 8, "alternate key buffer holds the scatter scratch");
-        IdxT* scr = sizeof(IdxT) == 4 ? reinterpret_cast<IdxT*>(ka) : nullptr;
-        inverse_scatter<IdxT>(d_sa, rpos, n, d_rank, n, scr, scr ? scr + (n + 3) / 4 * 4 : nullptr, stream);
+        inverse_scatter<IdxT>(d_sa, rpos, n, d_rank, n, stream);
         if (st && st->rank) st->rank->end(4, 0);
     }
 

@@ -7,12 +7,12 @@
 // with four sweeps over 57 M elements. So:
 //   out fits one slice          -> plain scatter
 //   a few slices (<= kSweepMax) -> one sweep over (idx, val) per slice, each writing only its slice's targets
-//   more                        -> one radix partition pass of the pairs by slice number (16 MB slices, up to 256 of them),
-//                                  then one in-order scatter from few blocks: 51 G elem/s at 250 M targets with 148 x 4
-//                                  blocks, but only 26 G elem/s with 148 x 16 (too many partial lines in flight)
+//   more                        -> plain scatter. Tried and dropped: one radix partition pass of the pairs by slice number
+//                                  followed by an in-order scatter (profiles/r1_scatter_bench.log): the in-order scatter
+//                                  reaches 26-51 G elem/s only, and with the partition pass the whole is slower than the
+//                                  plain scatter at 249 M (15.0 vs 15.5 ms for the re-ranking) and at 3.1 G targets (229 vs 193 ms).
 #pragma once
 #include "common.cuh"
-#include "radix_sort.cuh"
 
 namespace ab200 {
 
@@ -38,37 +38,19 @@ __global__ void __launch_bounds__(256) scatter_slice_kernel(const IdxT* __restri
     }
 }
 
-// scratch_idx / scratch_val: n elements each (may be null: the partition path then allocates them)
 template <typename IdxT>
-void inverse_scatter(const IdxT* idx, const IdxT* val, u64 n, IdxT* out, u64 out_len, IdxT* scratch_idx, IdxT* scratch_val,
-                     cudaStream_t stream) {
+void inverse_scatter(const IdxT* idx, const IdxT* val, u64 n, IdxT* out, u64 out_len, cudaStream_t stream) {
     if (n == 0) return;
     const u64 slice = kScatterSliceBytes / sizeof(IdxT);
-    const u64 K = ceil_div(out_len, slice);
+    u64 sweeps = ceil_div(out_len, slice);
+    if (sweeps > u64(kSweepMax)) sweeps = 1;
     const unsigned grid = unsigned(std::min<u64>(ceil_div(n, 256 * (16 / sizeof(IdxT))), u64(kNumSMs) * 16));
-    if (K <= u64(kSweepMax) || sizeof(IdxT) != 4) {
-        const u64 sweeps = sizeof(IdxT) != 4 && K > u64(kSweepMax) ? 1 : K;   // 64-bit indices beyond the sweep range: plain scatter
-        for (u64 k = 0; k < sweeps; ++k) {
-            const u64 lo = out_len * k / sweeps, hi = out_len * (k + 1) / sweeps;
-            scatter_slice_kernel<IdxT><<<grid, 256, 0, stream>>>(idx, val, n, out, lo, hi);
-            KERNEL_CHECK();
-        }
-        count_launch(sweeps);
-        return;
-    }
-    if constexpr (sizeof(IdxT) == 4) {
-        // partition by slice number = idx >> shift, at most 256 slices (one radix pass; slices grow beyond 48 MB past 3.2 G targets)
-        int shift = 22;
-        while ((out_len - 1) >> shift > 255) ++shift;
-        DevBuf<u32> own_i, own_v;
-        if (!scratch_idx) { own_i.alloc(n, stream); scratch_idx = own_i.p; }
-        if (!scratch_val) { own_v.alloc(n, stream); scratch_val = own_v.p; }
-        u32 *k = const_cast<u32*>(idx), *ka = scratch_idx, *v = const_cast<u32*>(val), *va = scratch_val;
-        radix_sort_pairs<u32, u32>(k, ka, v, va, n, &shift, 1, stream);   // one pass: reads (idx, val), writes the scratch pair
-        scatter_slice_kernel<u32><<<kNumSMs * 4, 256, 0, stream>>>(k, v, n, out, 0, out_len);
+    for (u64 k = 0; k < sweeps; ++k) {
+        const u64 lo = out_len * k / sweeps, hi = out_len * (k + 1) / sweeps;
+        scatter_slice_kernel<IdxT><<<grid, 256, 0, stream>>>(idx, val, n, out, lo, hi);
         KERNEL_CHECK();
-        count_launch(1);
     }
+    count_launch(sweeps);
 }
 
 }  // namespace ab200
