@@ -58,6 +58,7 @@ class Stats(C.Structure):
                                      "bytes_sa_scatter", "n_probes", "n_searched",
                                      "n_skipped_n", "n_skipped_card", "n_matches", "n_events", "n_segments", "sa_rounds",
                                      "sa_index_bits", "h2d_bytes", "d2h_bytes")]
+        + [("ms_sa_scatter_main", C.c_double), ("launches_sa_scatter_main", C.c_uint64), ("bytes_sa_scatter_main", C.c_uint64)]
     )
 
     def as_dict(self):

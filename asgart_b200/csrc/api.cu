@@ -66,7 +66,7 @@ struct asgart_b200_ctx {
     Index32 ix32;
     Index64 ix64;
     asgart_b200_stats st{};
-    FamilyTimer t_sort, t_gather, t_rank, t_probe, t_emit, t_scatter;
+    FamilyTimer t_sort, t_gather, t_rank, t_probe, t_emit, t_scatter, t_scatter_main;
     cudaEvent_t ev_a = nullptr, ev_b = nullptr;
     LaunchCounter launches;
 };
@@ -205,7 +205,7 @@ void build_index_t(asgart_b200_ctx* ctx) {
     {
         DevBuf<IdxT> rank(ctx->n1, ctx->stream);
         SaStats ss;
-        ss.sort = &ctx->t_sort; ss.gather = &ctx->t_gather; ss.rank = &ctx->t_rank; ss.scatter = &ctx->t_scatter;
+        ss.sort = &ctx->t_sort; ss.gather = &ctx->t_gather; ss.rank = &ctx->t_rank; ss.scatter = &ctx->t_scatter; ss.scatter_main = &ctx->t_scatter_main;
         build_suffix_array<IdxT>(ctx->d_text.p, ctx->n1, ix.sa.p, rank.p, ctx->stream, &ss, &hook);
         ctx->st.sa_rounds = ss.rounds;
     }
@@ -614,14 +614,17 @@ void shard_range(u64 total, int shard, int n_shards, u64& b, u64& e) {
 }
 
 void fold_family_timers(asgart_b200_ctx* ctx) {
-    ctx->t_sort.drain(); ctx->t_gather.drain(); ctx->t_rank.drain(); ctx->t_probe.drain(); ctx->t_emit.drain(); ctx->t_scatter.drain();
+    ctx->t_sort.drain(); ctx->t_gather.drain(); ctx->t_rank.drain(); ctx->t_probe.drain(); ctx->t_emit.drain(); ctx->t_scatter.drain(); ctx->t_scatter_main.drain();
     asgart_b200_stats& S = ctx->st;
     S.ms_sa_sort = ctx->t_sort.total_ms; S.launches_sa_sort = ctx->t_sort.launches; S.bytes_sa_sort = ctx->t_sort.bytes;
     S.ms_sa_gather = ctx->t_gather.total_ms; S.launches_sa_gather = ctx->t_gather.launches; S.bytes_sa_gather = ctx->t_gather.bytes;
     S.ms_sa_rank = ctx->t_rank.total_ms;
     S.ms_probe = ctx->t_probe.total_ms; S.launches_probe = ctx->t_probe.launches; S.bytes_probe = ctx->t_probe.bytes;
     S.ms_emit = ctx->t_emit.total_ms;
-    S.ms_sa_scatter = ctx->t_scatter.total_ms; S.launches_sa_scatter = ctx->t_scatter.launches; S.bytes_sa_scatter = ctx->t_scatter.bytes;
+    S.ms_sa_scatter_main = ctx->t_scatter_main.total_ms; S.launches_sa_scatter_main = ctx->t_scatter_main.launches;
+    S.bytes_sa_scatter_main = ctx->t_scatter_main.bytes;
+    S.ms_sa_scatter = ctx->t_scatter.total_ms + S.ms_sa_scatter_main; S.launches_sa_scatter = ctx->t_scatter.launches + S.launches_sa_scatter_main;
+    S.bytes_sa_scatter = ctx->t_scatter.bytes + S.bytes_sa_scatter_main;
     S.launches_total = ctx->launches.total;
     S.sa_index_bits = u64(ctx->idx_bits);
 }
@@ -657,7 +660,7 @@ int32_t asgart_b200_ctx_create(int32_t device, asgart_b200_ctx** out) {
         u64 thr = ~u64(0);
         CUDA_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
         ctx->t_sort.init(ctx->stream); ctx->t_gather.init(ctx->stream); ctx->t_rank.init(ctx->stream);
-        ctx->t_probe.init(ctx->stream); ctx->t_emit.init(ctx->stream); ctx->t_scatter.init(ctx->stream);
+        ctx->t_probe.init(ctx->stream); ctx->t_emit.init(ctx->stream); ctx->t_scatter.init(ctx->stream); ctx->t_scatter_main.init(ctx->stream);
         CUDA_CHECK(cudaEventCreate(&ctx->ev_a)); CUDA_CHECK(cudaEventCreate(&ctx->ev_b));
     } catch (const CudaError& e) {
         int code = e.code;
@@ -676,7 +679,7 @@ void asgart_b200_ctx_destroy(asgart_b200_ctx* ctx) {
                 (unsigned long long)g_host_stalls.allocs, g_host_stalls.alloc_ms, (unsigned long long)g_host_stalls.syncs, g_host_stalls.sync_ms);
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    ctx->t_sort.destroy(); ctx->t_gather.destroy(); ctx->t_rank.destroy(); ctx->t_probe.destroy(); ctx->t_emit.destroy(); ctx->t_scatter.destroy();
+    ctx->t_sort.destroy(); ctx->t_gather.destroy(); ctx->t_rank.destroy(); ctx->t_probe.destroy(); ctx->t_emit.destroy(); ctx->t_scatter.destroy(); ctx->t_scatter_main.destroy();
     if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
     if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
     ctx->d_text.release(); ctx->d_pt.release(); ctx->d_pn.release(); ctx->shard_blob.release();
@@ -1112,7 +1115,7 @@ void asgart_b200_ctx_reset_stats(asgart_b200_ctx* ctx) {
     if (!ctx) return;
     try {
         cudaSetDevice(ctx->device);
-        ctx->t_sort.reset(); ctx->t_gather.reset(); ctx->t_rank.reset(); ctx->t_probe.reset(); ctx->t_emit.reset(); ctx->t_scatter.reset();
+        ctx->t_sort.reset(); ctx->t_gather.reset(); ctx->t_rank.reset(); ctx->t_probe.reset(); ctx->t_emit.reset(); ctx->t_scatter.reset(); ctx->t_scatter_main.reset();
     } catch (...) {}
     ctx->launches.total = 0;
     ctx->st = asgart_b200_stats{};

@@ -28,7 +28,8 @@ namespace ab200 {
 
 struct SaStats {
     FamilyTimer* sort = nullptr;    // radix passes
-    FamilyTimer* scatter = nullptr; // rs_scatter_kernel alone
+    FamilyTimer* scatter = nullptr; // rs_scatter_kernel alone (sorts of the run round and the doubling rounds)
+    FamilyTimer* scatter_main = nullptr; // rs_scatter_kernel of the initial sort: every launch moves all n suffixes
     FamilyTimer* gather = nullptr;  // rank[I + h] gathers
     FamilyTimer* rank = nullptr;    // re-rank / compaction scans
     u64 rounds = 0;
@@ -269,7 +270,7 @@ void build_suffix_array(const u8* d_text, u64 n, IdxT* d_sa, IdxT* d_rank, cudaS
         KERNEL_CHECK();
         count_launch();
         radix_sort_pairs<u64, IdxT>(k, ka, v, va, n, shifts.data(), int(shifts.size()), stream, st ? st->sort : nullptr,
-                                    st ? st->scatter : nullptr);
+                                    st ? st->scatter_main : nullptr);
 
         if (hook) hook->on_sorted_keys(k, n, b, p0, h_code, stream);
         DevBuf<Acc> d_total(1, stream);

@@ -183,6 +183,9 @@ typedef struct asgart_b200_stats {
     uint64_t n_probes, n_searched, n_skipped_n, n_skipped_card, n_matches, n_events, n_segments;
     uint64_t sa_rounds, sa_index_bits;
     uint64_t h2d_bytes, d2h_bytes;
+    /* rs_scatter_kernel launches of the initial sort only (every launch moves all n+1 suffixes: the roofline kernel) */
+    double ms_sa_scatter_main;
+    uint64_t launches_sa_scatter_main, bytes_sa_scatter_main;
 } asgart_b200_stats;
 ASGART_B200_API int32_t asgart_b200_ctx_stats(const asgart_b200_ctx *ctx, asgart_b200_stats *out);
 ASGART_B200_API void asgart_b200_ctx_reset_stats(asgart_b200_ctx *ctx);
