@@ -81,6 +81,7 @@ SYMBOLS = [
     "asgart_b200_prepared_fragment", "asgart_b200_prepared_free", "asgart_b200_to_json", "asgart_b200_free_string",
     "asgart_b200_out_filename", "asgart_b200_run_files", "asgart_b200_synth_length", "asgart_b200_synth_fill",
     "asgart_b200_synth_fragments",
+    "asgart_b200_build_index_group", "asgart_b200_dist_unique_id", "asgart_b200_ctx_dist_init", "asgart_b200_ctx_dist_shutdown",
 ]
 
 _lib = None
@@ -108,6 +109,10 @@ def load() -> C.CDLL:
         "asgart_b200_ctx_load_strand": (i32, [vp, vp, i64]),
         "asgart_b200_ctx_build_index": (i32, [vp]),
         "asgart_b200_ctx_set_index_bits": (i32, [vp, i32]),
+        "asgart_b200_build_index_group": (i32, [C.POINTER(vp), i32]),
+        "asgart_b200_dist_unique_id": (i32, [vp, i64]),
+        "asgart_b200_ctx_dist_init": (i32, [vp, i32, i32, vp, i64]),
+        "asgart_b200_ctx_dist_shutdown": (i32, [vp]),
         "asgart_b200_ctx_upload_sa": (i32, [vp, vp]),
         "asgart_b200_ctx_download_sa": (i32, [vp, vp]),
         "asgart_b200_ctx_check_sa": (i32, [vp, vp]),

@@ -99,6 +99,27 @@ def r_divsufsort(dna, device: Optional[int] = None, index_bits: int = 0) -> np.n
     return sa
 
 
+def dist_unique_id() -> bytes:
+    """Rank 0's id for Context.dist_init (send it to the other ranks, e.g. with torch.distributed.broadcast)."""
+    L = _lib.load()
+    buf = np.zeros(128, dtype=np.uint8)
+    n = L.asgart_b200_dist_unique_id(_ptr(buf), len(buf))
+    if n <= 0:
+        raise AsgartB200Error(n, "cannot create a NCCL unique id (libnccl.so.2 missing?)")
+    return buf[:n].tobytes()
+
+
+def build_index_group(ctxs: Sequence["Context"]):
+    """Sharded index build by several contexts of this process (host threads; devices need peer access, or may all be
+    the same device). Every context must have the same strand loaded; all end up with the whole index."""
+    L = _lib.load()
+    arr = (C.c_void_p * len(ctxs))(*[c.h for c in ctxs])
+    rc = L.asgart_b200_build_index_group(arr, len(ctxs))
+    if rc != 0:
+        msgs = [L.asgart_b200_ctx_last_error(c.h).decode() for c in ctxs]
+        raise AsgartB200Error(rc, "; ".join(m for m in msgs if m))
+
+
 class Context:
     """One device context: strand + index resident in HBM, searches run against it."""
 
@@ -145,6 +166,14 @@ class Context:
 
     def build_index(self):
         self._check(self.L.asgart_b200_ctx_build_index(self.h))
+
+    def dist_init(self, rank: int, world: int, unique_id: bytes):
+        """Join a group of `world` processes (one per GPU): build_index becomes a collective, sharded build."""
+        buf = np.frombuffer(unique_id, dtype=np.uint8).copy()
+        self._check(self.L.asgart_b200_ctx_dist_init(self.h, rank, world, _ptr(buf), len(buf)))
+
+    def dist_shutdown(self):
+        self._check(self.L.asgart_b200_ctx_dist_shutdown(self.h))
 
     def upload_sa(self, sa: np.ndarray):
         sa = np.ascontiguousarray(sa, dtype=np.int64)

@@ -4,10 +4,12 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "automaton.cuh"
 #include "common.cuh"
+#include "dist_group.cuh"
 #include "sa_build.cuh"
 #include "search.cuh"
 
@@ -69,6 +71,13 @@ struct asgart_b200_ctx {
     FamilyTimer t_sort, t_gather, t_rank, t_probe, t_emit, t_scatter, t_scatter_main;
     cudaEvent_t ev_a = nullptr, ev_b = nullptr;
     LaunchCounter launches;
+    // sharded index build: the group this context is a member of (null: builds alone) and this member's slice of the
+    // block-cyclic rank array, kept between builds so that the peers' mappings of it stay valid
+    SaGroup* group = nullptr;
+    bool group_owned = false;
+    void* rank_slice = nullptr;
+    size_t rank_slice_bytes = 0;
+    std::vector<void*> retired_slices;
 };
 
 namespace ab200 { namespace detail {
@@ -151,7 +160,8 @@ struct LutHook : SaKeyHook {
     bool done = false;
     double ms = 0;
     explicit LutHook(asgart_b200_ctx* c) : ctx(c) {}
-    void on_sorted_keys(const u64* d_keys, u64 n, int b, int p0, const uint16_t* h_code, cudaStream_t stream) override {
+    void on_sorted_keys(const u64* d_keys, u64 n_local, u64 base, u64 n, int b, int p0, const uint16_t* h_code, cudaStream_t stream,
+                        SaGroup* grp) override {
         if (p0 < 8 || n != ctx->n1) return;
         auto& ix = IxOf<IdxT>::get(ctx);
         EventTimer t(stream);
@@ -176,10 +186,18 @@ struct LutHook : SaKeyHook {
         ix.deep_depth = depth;
         DevBuf<LutCodeMap> d_map(1, stream);
         CUDA_CHECK(cudaMemcpyAsync(d_map.p, &map, sizeof map, cudaMemcpyHostToDevice, stream));
-        lut_from_keys_kernel<IdxT><<<unsigned(ceil_div(n, 256)), 256, 0, stream>>>(d_keys, n, b, p0, d_map.p, depth, ix.lut_lo.p, ix.lut_hi.p,
-                                                                                  ix.deep.p);
-        KERNEL_CHECK();
-        count_launch();
+        if (n_local) {
+            lut_from_keys_kernel<IdxT><<<unsigned(ceil_div(n_local, 256)), 256, 0, stream>>>(d_keys, n_local, base, b, p0, d_map.p, depth,
+                                                                                            ix.lut_lo.p, ix.lut_hi.p, ix.deep.p);
+            KERNEL_CHECK();
+            count_launch();
+        }
+        if (grp) {
+            // every slot was seen by exactly one member (zero elsewhere; slot values are >= 1): the maximum merges the tables
+            grp->allreduce_max_dev(ix.lut_lo.p, kLutSize, int(sizeof(IdxT)), stream);
+            grp->allreduce_max_dev(ix.lut_hi.p, kLutSize, int(sizeof(IdxT)), stream);
+            if (depth) grp->allreduce_max_dev(ix.deep.p, M, int(sizeof(IdxT)), stream);
+        }
         if (depth) {
             // unseen slots take the start of the next seen one (empty bucket); the last entry closes the table at n1
             IdxT* dp = ix.deep.p;
@@ -202,13 +220,32 @@ void build_index_t(asgart_b200_ctx* ctx) {
     tsa.start();
     ix.sa.alloc(ctx->n1, ctx->stream);
     LutHook<IdxT> hook(ctx);
-    {
+    SaStats ss;
+    ss.sort = &ctx->t_sort; ss.gather = &ctx->t_gather; ss.rank = &ctx->t_rank; ss.scatter = &ctx->t_scatter; ss.scatter_main = &ctx->t_scatter_main;
+    SaGroup* grp = (ctx->group && ctx->group->world > 1) ? ctx->group : nullptr;
+    if (!grp) {
         DevBuf<IdxT> rank(ctx->n1, ctx->stream);
-        SaStats ss;
-        ss.sort = &ctx->t_sort; ss.gather = &ctx->t_gather; ss.rank = &ctx->t_rank; ss.scatter = &ctx->t_scatter; ss.scatter_main = &ctx->t_scatter_main;
         build_suffix_array<IdxT>(ctx->d_text.p, ctx->n1, ix.sa.p, rank.p, ctx->stream, &ss, &hook);
-        ctx->st.sa_rounds = ss.rounds;
+    } else {
+        // this member's slice of the rank array: a cudaMalloc block of its own (its address is what the peers map)
+        RankView<IdxT> rv;
+        rv.world = u32(grp->world);
+        rv.blk_shift = RankView<IdxT>::pick_shift(ctx->n1, rv.world);
+        const size_t need = RankView<IdxT>::slice_len(ctx->n1, rv.world, rv.blk_shift) * sizeof(IdxT);
+        if (need > ctx->rank_slice_bytes) {   // same decision on every member: n1 and world are the same everywhere
+            // the previous build ended with a collective, so nobody still works on the old slice; peers may still have it
+            // mapped (CUDA IPC), so it is only freed with the context
+            if (ctx->rank_slice) ctx->retired_slices.push_back(ctx->rank_slice);
+            ctx->rank_slice = nullptr; ctx->rank_slice_bytes = 0;
+            CUDA_CHECK(cudaMalloc(&ctx->rank_slice, need));
+            ctx->rank_slice_bytes = need;
+        }
+        void* all[kMaxWorld] = {};
+        grp->exchange_ptr(ctx->rank_slice, ctx->rank_slice_bytes, all);
+        for (int r = 0; r < kMaxWorld; ++r) rv.base[r] = static_cast<IdxT*>(all[r < grp->world ? r : 0]);
+        build_suffix_array<IdxT>(ctx->d_text.p, ctx->n1, ix.sa.p, rv, ctx->stream, &ss, &hook, grp);
     }
+    ctx->st.sa_rounds = ss.rounds;
     tsa.stop();
     tlut.start();
     if (!hook.done) build_lut<IdxT>(ctx);
@@ -682,6 +719,10 @@ void asgart_b200_ctx_destroy(asgart_b200_ctx* ctx) {
     ctx->t_sort.destroy(); ctx->t_gather.destroy(); ctx->t_rank.destroy(); ctx->t_probe.destroy(); ctx->t_emit.destroy(); ctx->t_scatter.destroy(); ctx->t_scatter_main.destroy();
     if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
     if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
+    if (ctx->group_owned && ctx->group) { delete ctx->group; }
+    ctx->group = nullptr;
+    if (ctx->rank_slice) cudaFree(ctx->rank_slice);
+    for (void* p : ctx->retired_slices) cudaFree(p);
     ctx->d_text.release(); ctx->d_pt.release(); ctx->d_pn.release(); ctx->shard_blob.release();
     ctx->ix32 = Index32();
     ctx->ix64 = Index64();
@@ -736,6 +777,76 @@ int32_t asgart_b200_ctx_build_index(asgart_b200_ctx* ctx) {
         else { ctx->ix32 = Index32(); build_index_t<u64>(ctx); }
         CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
         ctx->have_index = true;
+        return ASGART_B200_OK;
+    });
+}
+
+// ---- sharded index build ------------------------------------------------------------------------------------
+int32_t asgart_b200_build_index_group(asgart_b200_ctx* const* ctxs, int32_t world) {
+    if (!ctxs || world < 1 || world > kMaxWorld) return ASGART_B200_EINVAL;
+    for (int r = 0; r < world; ++r) {
+        if (!ctxs[r] || ctxs[r]->group) return ASGART_B200_EINVAL;
+        if (!ctxs[r]->have_strand || ctxs[r]->n1 != ctxs[0]->n1) return fail(ctxs[r], ASGART_B200_ESTATE, "every member needs the same strand loaded");
+    }
+    // members on different devices reach each other's rank slices through peer access
+    for (int a = 0; a < world; ++a)
+        for (int b2 = 0; b2 < world; ++b2) {
+            if (ctxs[a]->device == ctxs[b2]->device) continue;
+            int can = 0;
+            if (cudaDeviceCanAccessPeer(&can, ctxs[a]->device, ctxs[b2]->device) != cudaSuccess || !can)
+                return fail(ctxs[a], ASGART_B200_EINVAL, "no peer access between the devices of the group");
+            cudaSetDevice(ctxs[a]->device);
+            cudaError_t e = cudaDeviceEnablePeerAccess(ctxs[b2]->device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(ctxs[a], ASGART_B200_ECUDA, cudaGetErrorString(e));
+            cudaGetLastError();
+        }
+    ThreadGroupShared shared(world);
+    std::vector<int32_t> rc(world, ASGART_B200_OK);
+    std::vector<std::thread> threads;
+    for (int r = 0; r < world; ++r)
+        threads.emplace_back([&, r] {
+            asgart_b200_ctx* ctx = ctxs[r];
+            ThreadGroup member(&shared, r, ctx->stream);
+            ctx->group = &member;
+            rc[r] = asgart_b200_ctx_build_index(ctx);
+            if (rc[r] != ASGART_B200_OK) shared.fail();
+            ctx->group = nullptr;
+        });
+    for (auto& t : threads) t.join();
+    for (int r = 0; r < world; ++r)
+        if (rc[r] != ASGART_B200_OK) return rc[r];
+    return ASGART_B200_OK;
+}
+
+int32_t asgart_b200_dist_unique_id(uint8_t* out, int64_t cap) {
+    if (!out || cap < int64_t(sizeof(ncclUniqueId))) return ASGART_B200_EINVAL;
+    if (!nccl_api().load()) return ASGART_B200_ECUDA;
+    ncclUniqueId id;
+    if (nccl_api().GetUniqueId(&id) != ncclSuccess) return ASGART_B200_ECUDA;
+    memcpy(out, &id, sizeof id);
+    return int32_t(sizeof id);
+}
+
+int32_t asgart_b200_ctx_dist_init(asgart_b200_ctx* ctx, int32_t rank, int32_t world, const uint8_t* unique_id, int64_t id_bytes) {
+    return guarded(ctx, [&]() -> int32_t {
+        if (world < 1 || world > kMaxWorld || rank < 0 || rank >= world || !unique_id || id_bytes != int64_t(sizeof(ncclUniqueId)))
+            return fail(ctx, ASGART_B200_EINVAL, "bad rank/world/unique id");
+        if (ctx->group) return fail(ctx, ASGART_B200_ESTATE, "context already belongs to a group");
+        if (!nccl_api().load()) return fail(ctx, ASGART_B200_ECUDA, nccl_api().error.c_str());
+        ncclUniqueId id;
+        memcpy(&id, unique_id, sizeof id);
+        ctx->group = new NcclGroup(rank, world, id, ctx->stream);
+        ctx->group_owned = true;
+        return ASGART_B200_OK;
+    });
+}
+
+int32_t asgart_b200_ctx_dist_shutdown(asgart_b200_ctx* ctx) {
+    return guarded(ctx, [&]() -> int32_t {
+        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        if (ctx->group_owned && ctx->group) delete ctx->group;
+        ctx->group = nullptr;
+        ctx->group_owned = false;
         return ASGART_B200_OK;
     });
 }

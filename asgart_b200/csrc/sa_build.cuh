@@ -13,6 +13,12 @@
 //   3. doubling rounds h = p0, 2p0, ...: key2 = rank[I + h] + 1 (0 past the end)  [random gather],
 //      radix sort of the work list by (G, key2), re-rank, write SA for suffixes that became unique, drop them,
 //      until the work list is empty.
+// Sharded form (SaGroup, sa_group.h; world > 1): every member scans the whole text (1 byte per position), keeps the
+// suffixes whose key prefix falls into its range (ranges cut from a histogram of the first 12 key bits so that they hold
+// ~n/world suffixes each) and runs steps 1-3 on them; group heads and SA slots are global indices (range base + local
+// position). The rank array is block-cyclic over the members (RankView): the initial ranks and every re-ranking are
+// stored straight into the owner's memory and the gather of step 3 reads from it (NVLink peer access). Two collectives
+// per doubling round keep reads and writes of rank[] apart; the SA pieces are exchanged once at the end.
 // Index width is a template parameter: u32 when n < 2^32 - 1 (all BASELINE configs), u64 beyond (composite keys then
 // need 128 bits: U128). Both paths are exercised by the tests on small inputs.
 #pragma once
@@ -21,6 +27,7 @@
 
 #include "common.cuh"
 #include "radix_sort.cuh"
+#include "sa_group.h"
 #include "scan.cuh"
 #include "scatter.cuh"
 
@@ -97,6 +104,83 @@ __global__ void __launch_bounds__(kInitThreads) init_keys_kernel(const u8* __res
     }
 }
 
+
+// ---- sharded build: key-range selection -----------------------------------------------------------------------
+// histogram of the first `psym` symbols (b bits each) of every suffix: the members cut their key ranges from it
+__global__ void __launch_bounds__(256) key_prefix_hist_kernel(const u8* __restrict__ text, u64 n, const uint16_t* __restrict__ code, int b,
+                                                              int psym, unsigned long long* __restrict__ hist) {
+    extern __shared__ u32 kp_hist[];
+    __shared__ uint16_t scode[256];
+    const u32 nb = 1u << (b * psym);
+    for (u32 i = threadIdx.x; i < nb; i += blockDim.x) kp_hist[i] = 0;
+    scode[threadIdx.x] = code[threadIdx.x];
+    __syncthreads();
+    const u64 stride = u64(gridDim.x) * blockDim.x;
+    const u64 n_up = (n + 31) / 32 * 32;   // whole warps stay in the loop: the vote below needs all lanes
+    for (u64 p = u64(blockIdx.x) * blockDim.x + threadIdx.x; p < n_up; p += stride) {
+        u32 pre = 0;
+        for (int j = 0; j < psym; ++j) pre = (pre << b) | ((p + j < n) ? u32(scode[text[p + j]]) : 0u);
+        const bool valid = p < n;
+        // runs of one symbol put the whole warp on one counter: one add for all of them
+        const u32 first = __shfl_sync(0xffffffffu, pre, 0);
+        if (__all_sync(0xffffffffu, valid && pre == first)) { if (lane_id() == 0) atomicAdd(&kp_hist[pre], 32u); }
+        else if (valid) atomicAdd(&kp_hist[pre], 1u);
+    }
+    __syncthreads();
+    for (u32 i = threadIdx.x; i < nb; i += blockDim.x)
+        if (kp_hist[i]) atomicAdd(&hist[i], (unsigned long long)kp_hist[i]);
+}
+
+// init_keys_kernel restricted to the keys whose prefix (key >> pshift) lies in [pre_lo, pre_hi): WRITE = false counts them
+// per tile, WRITE = true writes them, in text order, behind the tile's offset.
+template <typename IdxT, bool WRITE>
+__global__ void __launch_bounds__(kInitThreads) init_keys_range_kernel(const u8* __restrict__ text, u64 n, const uint16_t* __restrict__ code, int b,
+                                                                        int p0, int pshift, u32 pre_lo, u32 pre_hi, u64* __restrict__ tile_cnt,
+                                                                        const u64* __restrict__ tile_off, u64* __restrict__ keys,
+                                                                        IdxT* __restrict__ vals) {
+    __shared__ uint16_t sc[kInitTile + 64];
+    __shared__ uint16_t scode[256];
+    __shared__ u32 wsm[32];
+    scode[threadIdx.x] = code[threadIdx.x];
+    __syncthreads();
+    const u64 base = u64(blockIdx.x) * kInitTile;
+    for (u32 i = threadIdx.x; i < kInitTile + 64; i += kInitThreads) {
+        const u64 p = base + i;
+        sc[i] = p < n ? scode[text[p]] : uint16_t(0);
+    }
+    __syncthreads();
+    const u32 t0 = threadIdx.x * kInitItems;
+    const u64 mask = (b * p0 >= 64) ? ~u64(0) : ((u64(1) << (b * p0)) - 1);
+    u64 key = 0;
+    for (int j = 0; j < p0; ++j) key = (key << b) | sc[t0 + j];
+    u64 kk[kInitItems];
+    u32 sel = 0, cnt = 0;
+#pragma unroll
+    for (int j = 0; j < kInitItems; ++j) {
+        kk[j] = key;
+        const u32 pre = u32(key >> pshift);
+        if (base + t0 + j < n && pre >= pre_lo && pre < pre_hi) { sel |= 1u << j; ++cnt; }
+        key = ((key << b) & mask) | sc[t0 + j + p0];
+    }
+    u32 total;
+    const u32 exc = block_exclusive_scan(cnt, SumOp(), total, wsm);
+    if (!WRITE) {
+        if (threadIdx.x == 0) tile_cnt[blockIdx.x] = total;
+    } else {
+        u64 w = tile_off[blockIdx.x] + exc;
+#pragma unroll
+        for (int j = 0; j < kInitItems; ++j)
+            if ((sel >> j) & 1u) { keys[w] = kk[j]; vals[w] = IdxT(base + t0 + j); ++w; }
+    }
+}
+
+// rank[suffix] = value, through the view (sharded build: most targets live in a peer's memory)
+template <typename IdxT>
+__global__ void __launch_bounds__(256) scatter_view_kernel(const IdxT* __restrict__ idx, const IdxT* __restrict__ val, u64 n, RankView<IdxT> rv) {
+    const u64 stride = u64(gridDim.x) * blockDim.x;
+    for (u64 i = u64(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) *rv.ptr(u64(idx[i])) = val[i];
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // composite (group, key2) keys of the large-group radix path
 template <typename IdxT> struct CompKey;
@@ -115,12 +199,12 @@ constexpr int kSmallGroup = 32;  // groups up to this size are sorted in place b
 
 // key2 = rank of the suffix D symbols further on (+1; 0 = past the end): the random gather of prefix doubling
 template <typename IdxT>
-__global__ void gather_rank_kernel(const IdxT* __restrict__ I, const IdxT* __restrict__ D, const IdxT* __restrict__ rank, u64 U, u64 n,
+__global__ void gather_rank_kernel(const IdxT* __restrict__ I, const IdxT* __restrict__ D, const RankView<IdxT> rank, u64 U, u64 n,
                                    IdxT* __restrict__ K2) {
     const u64 stride = u64(gridDim.x) * blockDim.x;
     for (u64 c = u64(blockIdx.x) * blockDim.x + threadIdx.x; c < U; c += stride) {
         const u64 p = u64(I[c]) + u64(D[c]);
-        K2[c] = p < n ? IdxT(rank[p] + 1) : IdxT(0);
+        K2[c] = p < n ? IdxT(*rank.ptr(p) + 1) : IdxT(0);
     }
 }
 
@@ -200,16 +284,23 @@ __global__ void run_key_kernel(const u8* __restrict__ text, const uint16_t* __re
 // Optional observer of the initial sort: the keys of all suffixes (first p0 symbols, b bits each, codes by h_code[byte])
 // in sorted order — every table that depends only on a bounded prefix of the suffixes (the k-mer lookup tables of the
 // probe search) is a by-product of this array and needs no gather through the finished suffix array.
+// Sharded build: d_keys holds this member's n_local keys, which are positions [base, base + n_local) of the n_total sorted
+// keys; ranges are cut where the first >= 4 symbols change (or the first symbol, for alphabets over 16 symbols), so a
+// bucket of 4 or more symbols never spans two members. Every member calls the hook at the same point (collectives allowed).
 struct SaKeyHook {
-    virtual void on_sorted_keys(const u64* d_keys, u64 n, int b, int p0, const uint16_t* h_code, cudaStream_t stream) = 0;
+    virtual void on_sorted_keys(const u64* d_keys, u64 n_local, u64 base, u64 n_total, int b, int p0, const uint16_t* h_code,
+                                cudaStream_t stream, SaGroup* grp) = 0;
     virtual ~SaKeyHook() = default;
 };
 
 template <typename IdxT>
-void build_suffix_array(const u8* d_text, u64 n, IdxT* d_sa, IdxT* d_rank, cudaStream_t stream, SaStats* st, SaKeyHook* hook = nullptr) {
+void build_suffix_array(const u8* d_text, u64 n, IdxT* d_sa, const RankView<IdxT> d_rank, cudaStream_t stream, SaStats* st,
+                        SaKeyHook* hook = nullptr, SaGroup* grp = nullptr) {
     using KeyT = typename CompKey<IdxT>::type;
     using Acc = FlagAcc<IdxT>;
     if (n == 0) return;
+    const int world = grp ? grp->world : 1;
+    if (world == 1) grp = nullptr;
     auto sync_read = [&](void* dst, const void* src, size_t bytes) {
         const double t0 = host_now_ms();
         CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, stream));
@@ -258,28 +349,84 @@ void build_suffix_array(const u8* d_text, u64 n, IdxT* d_sa, IdxT* d_rank, cudaS
     DevBuf<IdxT> GS, IS;
     u64 UA = 0, US = 0, NGA = 0;
     DevBuf<IdxT> GA, IA, HSA;
+    // sharded build: this member's key range (prefixes [pre_lo, pre_hi) of `psym` symbols), the global index `base` of its
+    // first suffix in the suffix array and the number n_loc of its suffixes; off[] = the pieces of all members
+    u64 base = 0, n_loc = n;
+    std::vector<u64> piece_off(world + 1, 0);
+    piece_off[world] = n;
+    int pshift = 0;
+    u32 pre_lo = 0, pre_hi = 0;
+    if (grp) {
+        const int psym = std::max(1, std::min(p0, std::min(4, 12 / b)));
+        const u32 nb = 1u << (b * psym);
+        pshift = b * p0 - b * psym;
+        DevBuf<unsigned long long> d_ph(nb, stream);
+        d_ph.zero();
+        const int blocks = int(std::min<u64>(ceil_div(n, 256), u64(kNumSMs) * 8));
+        key_prefix_hist_kernel<<<blocks, 256, nb * sizeof(u32), stream>>>(d_text, n, d_code.p, b, psym, d_ph.p);
+        KERNEL_CHECK();
+        count_launch();
+        std::vector<unsigned long long> h_ph(nb);
+        sync_read(h_ph.data(), d_ph.p, nb * sizeof(unsigned long long));
+        // member r starts at the first bin whose preceding bins hold >= r * n / world suffixes (same cut on every member)
+        std::vector<u32> cut(world + 1, nb);
+        cut[0] = 0;
+        u64 cum = 0;
+        int r = 1;
+        for (u32 bin = 0; bin < nb && r < world; ++bin) {
+            while (r < world && cum >= (n / u64(world)) * u64(r) && cum > piece_off[r - 1]) { cut[r] = bin; piece_off[r] = cum; ++r; }
+            cum += h_ph[bin];
+        }
+        for (; r < world; ++r) { cut[r] = nb; piece_off[r] = n; }
+        pre_lo = cut[grp->rank]; pre_hi = cut[grp->rank + 1];
+        base = piece_off[grp->rank];
+        n_loc = piece_off[grp->rank + 1] - base;
+    }
+    IdxT* const sa_loc = d_sa + base;
+
     {
         std::vector<int> shifts;
         for (int s = 0; s < b * p0; s += 8) shifts.push_back(s);
         // the sorted suffix indices must end up in d_sa itself: with an even number of passes they start there
-        DevBuf<u64> keysA(n, stream), keysB(n, stream);
-        DevBuf<IdxT> valsT(n, stream);
+        // (sharded: the piece d_sa + base is not 16-byte aligned, the sort runs in its own buffers and is copied over)
+        DevBuf<u64> keysA(n_loc, stream), keysB(n_loc, stream);
+        DevBuf<IdxT> valsT(n_loc, stream), valsU(grp ? n_loc : 0, stream);
         u64 *k = keysA.p, *ka = keysB.p;
-        IdxT *v = (shifts.size() % 2 == 0) ? d_sa : valsT.p, *va = (shifts.size() % 2 == 0) ? valsT.p : d_sa;
-        init_keys_kernel<IdxT><<<unsigned(ceil_div(n, u64(kInitTile))), kInitThreads, 0, stream>>>(d_text, n, d_code.p, b, p0, k, v);
-        KERNEL_CHECK();
-        count_launch();
-        radix_sort_pairs<u64, IdxT>(k, ka, v, va, n, shifts.data(), int(shifts.size()), stream, st ? st->sort : nullptr,
+        IdxT *v, *va;
+        if (!grp) {
+            v = (shifts.size() % 2 == 0) ? d_sa : valsT.p; va = (shifts.size() % 2 == 0) ? valsT.p : d_sa;
+            init_keys_kernel<IdxT><<<unsigned(ceil_div(n, u64(kInitTile))), kInitThreads, 0, stream>>>(d_text, n, d_code.p, b, p0, k, v);
+            KERNEL_CHECK();
+            count_launch();
+        } else {
+            v = valsT.p; va = valsU.p;
+            const u64 tiles = ceil_div(n, u64(kInitTile));
+            DevBuf<u64> tcnt(tiles, stream), toff(tiles, stream);
+            init_keys_range_kernel<IdxT, false><<<unsigned(tiles), kInitThreads, 0, stream>>>(d_text, n, d_code.p, b, p0, pshift, pre_lo, pre_hi,
+                                                                                             tcnt.p, nullptr, nullptr, nullptr);
+            KERNEL_CHECK();
+            const u64* tc = tcnt.p;
+            u64* to = toff.p;
+            device_scan<u64, SumOp>([tc] __device__(u64 i) { return tc[i]; }, [to] __device__(u64 i, u64 exc, u64) { to[i] = exc; }, tiles,
+                                    (u64*)nullptr, stream);
+            init_keys_range_kernel<IdxT, true><<<unsigned(tiles), kInitThreads, 0, stream>>>(d_text, n, d_code.p, b, p0, pshift, pre_lo, pre_hi,
+                                                                                            nullptr, toff.p, k, v);
+            KERNEL_CHECK();
+            count_launch(2);
+        }
+        radix_sort_pairs<u64, IdxT>(k, ka, v, va, n_loc, shifts.data(), int(shifts.size()), stream, st ? st->sort : nullptr,
                                     st ? st->scatter_main : nullptr);
+        if (grp && n_loc) CUDA_CHECK(cudaMemcpyAsync(sa_loc, v, n_loc * sizeof(IdxT), cudaMemcpyDeviceToDevice, stream));
 
-        if (hook) hook->on_sorted_keys(k, n, b, p0, h_code, stream);
+        if (hook) hook->on_sorted_keys(k, n_loc, base, n, b, p0, h_code, stream, grp);
         DevBuf<Acc> d_total(1, stream);
         const u64* kk = k;
-        const IdxT* vv = v;   // == d_sa
-        auto in = [kk, n, rep_unit, sym_mask] __device__(u64 i) {
+        const IdxT* vv = sa_loc;
+        const u64 nl = n_loc;
+        auto in = [kk, nl, rep_unit, sym_mask] __device__(u64 i) {
             const u64 cur = kk[i];
             const bool head = i == 0 || kk[i - 1] != cur;
-            const bool tail = i + 1 == n || kk[i + 1] != cur;
+            const bool tail = i + 1 == nl || kk[i + 1] != cur;
             const bool uns = !(head && tail);
             const bool pure = cur == (cur & sym_mask) * rep_unit;
             return (head ? FS_MARK_A : 0u) | ((uns && !pure) ? FS_CNT_C : 0u) | ((uns && pure) ? FS_CNT_D : 0u) |
@@ -287,7 +434,7 @@ void build_suffix_array(const u8* d_text, u64 n, IdxT* d_sa, IdxT* d_rank, cudaS
         };
         if (st && st->rank) st->rank->begin();
         FlagScanPlan<IdxT> plan;
-        plan.prepare(in, n, d_total.p, stream);
+        plan.prepare(in, n_loc, d_total.p, stream);
         Acc tot;
         sync_read(&tot, d_total.p, sizeof tot);
         UA = u64(tot.c); US = u64(tot.d); NGA = u64(tot.e);
@@ -295,21 +442,29 @@ void build_suffix_array(const u8* d_text, u64 n, IdxT* d_sa, IdxT* d_rank, cudaS
         GS.alloc(US, stream); IS.alloc(US, stream);
         IdxT *ga = GA.p, *ia = IA.p, *hsa = HSA.p, *gs = GS.p, *is = IS.p;
         // rank by sorted position goes to the dead half of the value ping-pong, then to text order by the sliced scatter
-        IdxT* rpos = valsT.p;
+        IdxT* rpos = va;
+        const IdxT b0 = IdxT(base);
         plan.finish(in, [=] __device__(u64 i, const Acc& exc, const Acc& inc) {
             const u64 cur = kk[i];
             const bool head = i == 0 || kk[i - 1] != cur;
-            const bool tail = i + 1 == n || kk[i + 1] != cur;
+            const bool tail = i + 1 == nl || kk[i + 1] != cur;
             const IdxT idx = vv[i];
-            rpos[i] = inc.a;
+            const IdxT hd = b0 + inc.a;   // the group head's index in the suffix array
+            rpos[i] = hd;
             if (head && tail) return;
-            if (cur == (cur & sym_mask) * rep_unit) { gs[exc.d] = inc.a; is[exc.d] = idx; }
+            if (cur == (cur & sym_mask) * rep_unit) { gs[exc.d] = hd; is[exc.d] = idx; }
             else {
-                ga[exc.c] = inc.a; ia[exc.c] = idx;
+                ga[exc.c] = hd; ia[exc.c] = idx;
                 if (head) hsa[exc.e] = exc.c;
             }
         });
-        inverse_scatter<IdxT>(d_sa, rpos, n, d_rank, n, stream);
+        if (!grp) inverse_scatter<IdxT>(d_sa, rpos, n, d_rank.base[0], n, stream);
+        else if (n_loc) {
+            const unsigned grid = unsigned(std::min<u64>(ceil_div(n_loc, 256), u64(kNumSMs) * 16));
+            scatter_view_kernel<IdxT><<<grid, 256, 0, stream>>>(sa_loc, rpos, n_loc, d_rank);
+            KERNEL_CHECK();
+            count_launch();
+        }
         if (st && st->rank) st->rank->end(4, 0);
     }
 
@@ -367,7 +522,7 @@ void build_suffix_array(const u8* d_text, u64 n, IdxT* d_sa, IdxT* d_rank, cudaS
             const IdxT g = gx[cur >> (kb0 + 1)];
             const IdxT idx = vv[c];
             const IdxT ng = g + (inc.b - inc.a);
-            d_rank[idx] = ng;
+            *d_rank.ptr(u64(idx)) = ng;
             if (head_new && tail_new) { d_sa[u64(g) + (c - u64(inc.a))] = idx; return; }
             const u64 val = cur & ((u64(1) << kb0) - 1);
             const u64 r = ((cur >> kb0) & 1) ? (n - val) : val;
@@ -398,8 +553,18 @@ void build_suffix_array(const u8* d_text, u64 n, IdxT* d_sa, IdxT* d_rank, cudaS
     // to be equal inside its group and rank[] orders all suffixes by at least their first H symbols
     const int kb = std::max(1, bit_width_u64(n));  // key2 in [0, n]
     u64 H = u64(p0);
-    while (U > 0) {
+    // Sharded build: a collective at the top of every round (all re-rankings of the previous round have landed in the
+    // owners' memory before anyone gathers; its sum also tells when every member's list is empty) and one before the
+    // re-ranking (everyone has finished gathering before any rank changes). Members with an empty list only take part in these.
+    auto group_sync = [&](u64 v) -> u64 {
+        CUDA_CHECK(cudaStreamSynchronize(stream));
+        grp->allreduce_sum_host(&v, 1);
+        return v;
+    };
+    while (true) {
+        if (grp ? group_sync(U) == 0 : U == 0) break;
         if (st) st->rounds++;
+        if (U == 0) { group_sync(0); H <<= 1; continue; }
         DevBuf<IdxT> K2(U, stream), large_sz(NG, stream), loff(NG + 1, stream);
         {
             if (st && st->gather) st->gather->begin();
@@ -464,6 +629,7 @@ void build_suffix_array(const u8* d_text, u64 n, IdxT* d_sa, IdxT* d_rank, cudaS
         Acc tot;
         sync_read(&tot, d_total.p, sizeof tot);
         const u64 U2 = u64(tot.c), NG2 = u64(tot.d);
+        if (grp) group_sync(0);
         DevBuf<IdxT> G2(U2, stream), I2(U2, stream), D2(U2, stream), HS2(NG2, stream);
         IdxT *g2 = G2.p, *i2 = I2.p, *d2 = D2.p, *hs2 = HS2.p;
         const IdxT Hi = IdxT(H);
@@ -473,7 +639,7 @@ void build_suffix_array(const u8* d_text, u64 n, IdxT* d_sa, IdxT* d_rank, cudaS
             const bool tail_new = c + 1 == Uc || gg[c + 1] != g || k2[c + 1] != kv;
             const IdxT idx = ii[c];
             const IdxT ng = g + (inc.b - inc.a);
-            d_rank[idx] = ng;
+            *d_rank.ptr(u64(idx)) = ng;
             if (head_new && tail_new) { d_sa[u64(g) + (c - u64(inc.a))] = idx; return; }
             g2[exc.c] = ng; i2[exc.c] = idx; d2[exc.c] = dd[c] + Hi;
             if (head_new) hs2[exc.d] = exc.c;
@@ -483,6 +649,12 @@ void build_suffix_array(const u8* d_text, u64 n, IdxT* d_sa, IdxT* d_rank, cudaS
         U = U2; NG = NG2;
         H <<= 1;
     }
+    if (grp) grp->share_pieces(d_sa, piece_off.data(), int(sizeof(IdxT)), stream);
+}
+
+template <typename IdxT>
+void build_suffix_array(const u8* d_text, u64 n, IdxT* d_sa, IdxT* d_rank, cudaStream_t stream, SaStats* st, SaKeyHook* hook = nullptr) {
+    build_suffix_array<IdxT>(d_text, n, d_sa, RankView<IdxT>::single(d_rank), stream, st, hook, nullptr);
 }
 
 }  // namespace ab200

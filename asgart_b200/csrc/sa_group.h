@@ -1,0 +1,72 @@
+// sa_group.h — the group of devices that build one suffix array together (sharded SA build, sa_build.cuh).
+//
+// The reference builds its suffix array on one CPU thread (r_divsufsort, src/bin/asgart.rs:473-479) and has no
+// distributed mode; this is the multi-GPU side of the replacement. Member r of a group of `world` devices owns
+//   * the suffixes whose initial key falls into its key range = one contiguous range of the final suffix array, and
+//   * every world-th block of the rank array (RankView): ranks are written to and gathered from the owners'
+//     memory directly (peer stores / loads over NVLink), there is no staging copy.
+// Collectives are only needed at phase boundaries (a few per doubling round) and for the final exchange of SA pieces.
+// Two back ends: ThreadGroup (members = host threads of one process, any devices with peer access; also how the sharded
+// build is tested on a single GPU) and NcclGroup (one process per GPU: NCCL for the collectives, CUDA IPC for the peer
+// pointers) — both in dist_group.cuh.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstddef>
+#include <cstdint>
+
+namespace ab200 {
+
+constexpr int kMaxWorld = 16;
+
+struct SaGroup {
+    int rank = 0, world = 1;
+    // Sum of host values over the members. Every member calls it after synchronising its stream, so when it returns all
+    // device work issued before it — on every member, including stores into peer memory — is complete and visible.
+    virtual void allreduce_sum_host(uint64_t* vals, int n) = 0;
+    void barrier() { uint64_t z = 0; allreduce_sum_host(&z, 1); }
+    // element-wise maximum of a device array over the members (elem_bytes 4 or 8, unsigned); stream-ordered on return
+    virtual void allreduce_max_dev(void* buf, size_t count, int elem_bytes, cudaStream_t stream) = 0;
+    // member s holds elements [offs[s], offs[s+1]) of the array at `base`; afterwards every member holds all of it
+    virtual void share_pieces(void* base, const uint64_t* offs, int elem_bytes, cudaStream_t stream) = 0;
+    // pointers through which this member's kernels can reach every member's buffer (`mine` = start of a cudaMalloc block)
+    virtual void exchange_ptr(void* mine, size_t bytes, void** all) = 0;
+    virtual ~SaGroup() = default;
+};
+
+// Rank array of the suffix-array build, block-cyclic over the members: block j of 2^blk_shift positions lives on member
+// j % world. world == 1 is the plain array.
+template <typename IdxT>
+struct RankView {
+    IdxT* base[kMaxWorld];
+    uint32_t world;
+    uint32_t blk_shift;
+    __host__ __device__ __forceinline__ IdxT* ptr(uint64_t p) const {
+        if (world == 1) return base[0] + p;
+        const uint64_t blk = p >> blk_shift;
+        uint64_t q, o;
+        if (blk <= 0xFFFFFFFFull) { q = uint32_t(blk) / world; o = uint32_t(blk) % world; }
+        else { q = blk / world; o = blk % world; }
+        return base[o] + ((q << blk_shift) | (p & ((uint64_t(1) << blk_shift) - 1)));
+    }
+    static RankView single(IdxT* p) {
+        RankView v;
+        for (int i = 0; i < kMaxWorld; ++i) v.base[i] = p;
+        v.world = 1;
+        v.blk_shift = 20;
+        return v;
+    }
+    // block size: 1 Mi positions, smaller for short texts so that every member owns several blocks
+    static uint32_t pick_shift(uint64_t n, uint32_t world) {
+        uint32_t s = 20;
+        while (s > 4 && (n >> s) < uint64_t(world) * 4) --s;
+        return s;
+    }
+    // positions a member must hold
+    static uint64_t slice_len(uint64_t n, uint32_t world, uint32_t blk_shift) {
+        const uint64_t nblk = (n + (uint64_t(1) << blk_shift) - 1) >> blk_shift;
+        return ((nblk + world - 1) / world) << blk_shift;
+    }
+};
+
+}  // namespace ab200

@@ -111,30 +111,33 @@ __device__ __forceinline__ bool key_slot4(u64 key, int b, int p0, int depth, con
 // 8-mer LUT (Searcher::new, src/searcher.rs:99-143) and, when depth > 0, the first suffix of every ACGT-only
 // `depth`-mer (0 = not seen; position 0 is always the '$' suffix) from the sorted initial keys. Needs p0 >= 8, depth.
 template <typename IdxT>
-__global__ void __launch_bounds__(256) lut_from_keys_kernel(const u64* __restrict__ keys, u64 n1, int b, int p0, const LutCodeMap* __restrict__ map, int depth,
-                                                            IdxT* __restrict__ lut_lo, IdxT* __restrict__ lut_hi, IdxT* __restrict__ deep) {
+__global__ void __launch_bounds__(256) lut_from_keys_kernel(const u64* __restrict__ keys, u64 n_local, u64 base, int b, int p0,
+                                                            const LutCodeMap* __restrict__ map, int depth, IdxT* __restrict__ lut_lo,
+                                                            IdxT* __restrict__ lut_hi, IdxT* __restrict__ deep) {
     __shared__ LutCodeMap smap;   // dynamically indexed: a by-value kernel parameter would be copied to every thread's stack, so it comes by pointer
     if (threadIdx.x < 16) { smap.d5[threadIdx.x] = map->d5[threadIdx.x]; smap.d4[threadIdx.x] = map->d4[threadIdx.x]; }
     __syncthreads();
     const u64 i = u64(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (i >= n1) return;
+    if (i >= n_local) return;
+    // keys[0 .. n_local) are positions [base, base + n_local) of the sorted keys (sharded build: one member's key range,
+    // cut where the first four symbols change, so the first and the last key of the piece are bucket boundaries)
     const u64 cur = keys[i];
     const u64 prev = i > 0 ? keys[i - 1] : ~cur;
     // slots only change where the leading symbols do: decode the (rare) boundaries only
     const int s8 = b * (p0 - 8);
-    if ((cur >> s8) != (prev >> s8) || i + 1 == n1) {
+    if ((cur >> s8) != (prev >> s8) || i + 1 == n_local) {
         u32 cs = 0, ps = 0;
         const bool cur_ok = key_slot5(cur, b, p0, smap, cs);
         const bool prev_ok = i > 0 && key_slot5(prev, b, p0, smap, ps);
-        if (cur_ok && (!prev_ok || ps != cs)) lut_lo[cs] = IdxT(i);
-        if (prev_ok && (!cur_ok || ps != cs)) lut_hi[ps] = IdxT(i);
-        if (i + 1 == n1 && cur_ok) lut_hi[cs] = IdxT(n1);
+        if (cur_ok && (!prev_ok || ps != cs)) lut_lo[cs] = IdxT(base + i);
+        if (prev_ok && (!cur_ok || ps != cs)) lut_hi[ps] = IdxT(base + i);
+        if (i + 1 == n_local && cur_ok) lut_hi[cs] = IdxT(base + n_local);
     }
     if (depth > 0) {
         const int sd = b * (p0 - depth);
         if ((cur >> sd) != (prev >> sd)) {
             u32 cs = 0;
-            if (key_slot4(cur, b, p0, depth, smap, cs)) deep[cs] = IdxT(i);
+            if (key_slot4(cur, b, p0, depth, smap, cs)) deep[cs] = IdxT(base + i);
         }
     }
 }

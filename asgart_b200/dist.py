@@ -31,6 +31,21 @@ def all_gather_bytes(buf: np.ndarray, device: torch.device | None = None) -> Lis
     return [o[:s].cpu().numpy() for o, s in zip(outs, sizes)]
 
 
+def join_index_group(ctx, device: torch.device | None = None):
+    """Make `ctx.build_index()` a sharded, collective build over the ranks of the default process group (one process per
+    GPU): rank 0 creates the library's NCCL unique id, torch.distributed carries it to the others."""
+    from .api import dist_unique_id
+    rank, world = dist.get_rank(), dist.get_world_size()
+    if world == 1:
+        return
+    dev = device if device is not None else torch.device("cpu")
+    t = torch.zeros(128, dtype=torch.uint8, device=dev)
+    if rank == 0:
+        t.copy_(torch.frombuffer(bytearray(dist_unique_id()), dtype=torch.uint8))
+    dist.broadcast(t, src=0)
+    ctx.dist_init(rank, world, bytes(t.cpu().numpy().tobytes()))
+
+
 class _DevMem:
     """Zero-copy view of library-owned device memory for torch (CUDA array interface v3)."""
 

@@ -103,6 +103,21 @@ ASGART_B200_API const char *asgart_b200_ctx_last_error(const asgart_b200_ctx *ct
 ASGART_B200_API int32_t asgart_b200_ctx_load_strand(asgart_b200_ctx *ctx, const uint8_t *T, int64_t n_plus_1);
 /* Suffix array (replaces r_divsufsort, :149) + 8-mer LUT (replaces Searcher::new, :151; src/searcher.rs:99-143) */
 ASGART_B200_API int32_t asgart_b200_ctx_build_index(asgart_b200_ctx *ctx);
+/* Sharded index build (the reference builds its suffix array on one thread, src/bin/asgart.rs:473-479, and has no
+ * multi-device mode): the members of a group split the suffixes by initial-key range, keep the rank array block-cyclic
+ * in each other's memory (peer stores / loads over NVLink) and end with the whole index on every member, bit-identical
+ * to a single-device build. Every member must have the same strand loaded.
+ *   one process, several contexts (any devices with peer access, or all on one device): build_index_group runs the
+ *     members on host threads;
+ *   one process per GPU: rank 0 makes a unique id (dist_unique_id, 128 bytes) and sends it to the others by any means
+ *     (asgart_b200/dist.py: torch.distributed broadcast); every rank calls ctx_dist_init, after which ctx_build_index is
+ *     a collective call (NCCL for the phase boundaries and the final exchange of SA pieces, CUDA IPC for the peer
+ *     pointers) until ctx_dist_shutdown. */
+ASGART_B200_API int32_t asgart_b200_build_index_group(asgart_b200_ctx *const *ctxs, int32_t world);
+ASGART_B200_API int32_t asgart_b200_dist_unique_id(uint8_t *out, int64_t cap);   /* returns the id size (128) */
+ASGART_B200_API int32_t asgart_b200_ctx_dist_init(asgart_b200_ctx *ctx, int32_t rank, int32_t world,
+                                                  const uint8_t *unique_id, int64_t id_bytes);
+ASGART_B200_API int32_t asgart_b200_ctx_dist_shutdown(asgart_b200_ctx *ctx);
 /* force the suffix-index width of the next build_index / upload_sa: 0 = auto (32 bits when n+1 < 2^32-1), 32, 64 */
 ASGART_B200_API int32_t asgart_b200_ctx_set_index_bits(asgart_b200_ctx *ctx, int32_t bits);
 /* test hooks: use a suffix array built elsewhere (still builds the LUT on the device) / read the index back */

@@ -339,6 +339,97 @@ def test_run_files_json_identical_to_oracle(tmp_path):
     assert len(json.loads(ab.search_duplications([str(fa)], ab.RunSettings()))["families"]) > 0
 
 
+# ------------------------------------------------------------------------------------------------ sharded index build
+def _group_build(strand, world, bits=0):
+    ctxs = [ab.Context(0) for _ in range(world)]
+    for c in ctxs:
+        if bits:
+            c.set_index_bits(bits)
+        c.load_strand(strand)
+    ab.build_index_group(ctxs)
+    return ctxs
+
+
+@pytest.mark.parametrize("world", [2, 3, 4, 8])
+@pytest.mark.parametrize("bits", [32, 64])
+def test_sharded_index_equals_single(world, bits):
+    """The sharded build (members = host threads, all on this GPU: key ranges, block-cyclic rank array in the members'
+    slices, collectives at the phase boundaries) gives every member the suffix array, LUT and families of a lone build."""
+    text = cases.stress_text(7 + world, n=300_000, n_dups=40)
+    prep = ab.Prepared.from_memory(text, [("a", 0, len(text))], "g.fa")
+    strand = np.array(prep.strand)
+    sa_ref = oracle.best_suffix_array(strand)
+    st = ab.RunSettings(min_duplication_length=500, reverse=True, complement=True)
+    with ab.Context(0) as one:
+        one.set_index_bits(bits)
+        one.load_strand(strand)
+        one.build_index()
+        lut_ref = one.download_lut()
+        fam_ref = one.search(prep.chunks, st, ab.POST_ALL).as_lists()
+    ctxs = _group_build(strand, world, bits)
+    try:
+        for c in ctxs:
+            assert np.array_equal(c.download_sa(), sa_ref)
+            lo, hi = c.download_lut()
+            ne = lut_ref[1] > lut_ref[0]
+            assert np.array_equal((hi > lo), ne)
+            assert np.array_equal(lo[ne], lut_ref[0][ne]) and np.array_equal(hi[ne], lut_ref[1][ne])
+            assert c.check_sa() == 0
+        assert ctxs[-1].search(prep.chunks, st, ab.POST_ALL).as_lists() == fam_ref
+        assert len(fam_ref) > 0
+    finally:
+        for c in ctxs:
+            c.close()
+
+
+@pytest.mark.parametrize("name", ["runs", "tiny", "masked"])
+def test_sharded_index_edge_texts(name):
+    """Texts where the key ranges are lopsided: long single-symbol runs (one bin holds most suffixes, members with empty
+    pieces), a text shorter than the member count's blocks, a soft-masked genome (15 % N)."""
+    if name == "runs":
+        rng = np.random.default_rng(5)
+        parts = [b"A" * 40_000, bytes(rng.choice(list(b"ACGT"), 30_000).astype(np.uint8)), b"N" * 70_000, b"T" * 9_000,
+                 bytes(rng.choice(list(b"ACGT"), 20_000).astype(np.uint8)), b"A" * 25_000]
+        text = np.frombuffer(b"".join(parts), dtype=np.uint8)
+    elif name == "tiny":
+        text = np.frombuffer(b"ACGTACGTTTGACCANNNACGTACGTAC", dtype=np.uint8)
+    else:
+        g, fr = ab.synth_genome(2, scale_n=400_000)
+        text = ab.normalise(g, True)
+    strand = np.concatenate([text, np.frombuffer(b"$", dtype=np.uint8)])
+    sa_ref = oracle.best_suffix_array(strand)
+    for world in (2, 5):
+        ctxs = _group_build(strand, world)
+        try:
+            for c in ctxs:
+                assert np.array_equal(c.download_sa(), sa_ref)
+        finally:
+            for c in ctxs:
+                c.close()
+
+
+def test_sharded_index_full_size_c2():
+    """BASELINE configs[1] at full size through a 4-member group: on-device sufcheck and the single-build families."""
+    st, prep = _full_config(2)
+    strand = np.array(prep.strand)
+    with ab.Context(0) as one:
+        one.load_strand(strand)
+        one.build_index()
+        fam_ref = one.search(prep.chunks, st, ab.POST_ALL).as_lists()
+        lut_ref = one.download_lut()
+    ctxs = _group_build(strand, 4)
+    try:
+        for c in (ctxs[0], ctxs[3]):
+            assert c.check_sa() == 0
+            lo, hi = c.download_lut()
+            ne = lut_ref[1] > lut_ref[0]
+            assert np.array_equal(lo[ne], lut_ref[0][ne]) and np.array_equal(hi[ne], lut_ref[1][ne])
+        assert ctxs[2].search(prep.chunks, st, ab.POST_ALL).as_lists() == fam_ref
+    finally:
+        for c in ctxs:
+            c.close()
+
+
 # ------------------------------------------------------------------------------------------------ full-size configs
 def _full_config(config):
     flags = {1: dict(), 2: dict(reverse=True, complement=True, skip_masked=True),
