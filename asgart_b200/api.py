@@ -375,15 +375,25 @@ def prepare_data(files: Sequence[str], skip_masked: bool = False) -> Prepared:
 
 def normalise(seq: np.ndarray, skip_masked: bool) -> np.ndarray:
     """Per-base normalisation of read_fasta (src/bin/asgart.rs:291-301), vectorised for in-memory inputs."""
-    s = np.ascontiguousarray(seq, dtype=np.uint8).copy()
-    lower = (s >= ord("a")) & (s <= ord("z"))
-    if skip_masked:
-        masked = np.isin(s, np.frombuffer(b"atgcn", dtype=np.uint8))
-        s[masked] = ord("N")
+    # one 256-entry table: lower case -> 'N' (skip_masked) or upper case, then anything outside ATGCN -> 'N'
+    table = np.full(256, ord("N"), dtype=np.uint8)
+    for c in b"ATGCN":
+        table[c] = c
+    if not skip_masked:
+        for c in b"atgcn":
+            table[c] = c - 32
+    seq = np.ascontiguousarray(seq, dtype=np.uint8)
+    out = np.empty_like(seq)
+    step = 1 << 24
+    offs = range(0, len(seq), step)
+    if len(offs) > 1:   # numpy drops the GIL inside take
+        import os
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=min(len(offs), os.cpu_count() or 1)) as ex:
+            list(ex.map(lambda o: np.take(table, seq[o:o + step], out=out[o:o + step]), offs))
     else:
-        s[lower] -= 32
-    s[~np.isin(s, np.frombuffer(b"ATGCN", dtype=np.uint8))] = ord("N")
-    return s
+        np.take(table, seq, out=out)
+    return out
 
 
 def out_filename(files: Sequence[str], settings: RunSettings, prefix: str = "", out: Optional[str] = None) -> str:

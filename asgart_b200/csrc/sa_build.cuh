@@ -23,6 +23,7 @@
 // need 128 bits: U128). Both paths are exercised by the tests on small inputs.
 #pragma once
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 #include "common.cuh"
@@ -309,6 +310,17 @@ void build_suffix_array(const u8* d_text, u64 n, IdxT* d_sa, const RankView<IdxT
         g_host_stalls.syncs++;
     };
 
+    // developer aid: ASGART_B200_DEBUG_PHASES=1 prints the wall time of every phase (synchronises the stream at each mark)
+    static const bool dbg_phases = getenv("ASGART_B200_DEBUG_PHASES") != nullptr;
+    double dbg_t = host_now_ms();
+    auto phase = [&](const char* name, u64 count = 0) {
+        if (!dbg_phases) return;
+        cudaStreamSynchronize(stream);
+        const double t = host_now_ms();
+        fprintf(stderr, "[sa_build r%d/%d] %-22s %9.3f ms  (%llu)\n", grp ? grp->rank : 0, world, name, t - dbg_t, (unsigned long long)count);
+        dbg_t = t;
+    };
+
     // ---- 0. alphabet
     DevBuf<unsigned long long> d_hist(256, stream);
     d_hist.zero();
@@ -383,6 +395,7 @@ void build_suffix_array(const u8* d_text, u64 n, IdxT* d_sa, const RankView<IdxT
         n_loc = piece_off[grp->rank + 1] - base;
     }
     IdxT* const sa_loc = d_sa + base;
+    phase("alphabet+ranges", n_loc);
 
     {
         std::vector<int> shifts;
@@ -414,11 +427,14 @@ void build_suffix_array(const u8* d_text, u64 n, IdxT* d_sa, const RankView<IdxT
             KERNEL_CHECK();
             count_launch(2);
         }
+        phase("init keys", n_loc);
         radix_sort_pairs<u64, IdxT>(k, ka, v, va, n_loc, shifts.data(), int(shifts.size()), stream, st ? st->sort : nullptr,
                                     st ? st->scatter_main : nullptr);
+        phase("initial sort", shifts.size());
         if (grp && n_loc) CUDA_CHECK(cudaMemcpyAsync(sa_loc, v, n_loc * sizeof(IdxT), cudaMemcpyDeviceToDevice, stream));
 
         if (hook) hook->on_sorted_keys(k, n_loc, base, n, b, p0, h_code, stream, grp);
+        phase("lookup tables");
         DevBuf<Acc> d_total(1, stream);
         const u64* kk = k;
         const IdxT* vv = sa_loc;
@@ -466,6 +482,7 @@ void build_suffix_array(const u8* d_text, u64 n, IdxT* d_sa, const RankView<IdxT
             count_launch();
         }
         if (st && st->rank) st->rank->end(4, 0);
+        phase("heads+rank scatter", UA + US);
     }
 
     // ---- 3. run round: suffixes starting a run of >= p0 equal symbols are ordered by (symbol after the run, run length)
@@ -532,6 +549,7 @@ void build_suffix_array(const u8* d_text, u64 n, IdxT* d_sa, const RankView<IdxT
         if (st && st->rank) st->rank->end(3, 0);
     }
     GS.release(); IS.release();
+    phase("run round", US);
 
     // ---- 4. merged work list: ordinary groups at depth p0, then the run groups at depth = run length
     U = UA + US2; NG = NGA + NGS2;
@@ -649,7 +667,9 @@ void build_suffix_array(const u8* d_text, u64 n, IdxT* d_sa, const RankView<IdxT
         U = U2; NG = NG2;
         H <<= 1;
     }
+    phase("doubling rounds", st ? st->rounds : 0);
     if (grp) grp->share_pieces(d_sa, piece_off.data(), int(sizeof(IdxT)), stream);
+    phase("share SA pieces");
 }
 
 template <typename IdxT>
