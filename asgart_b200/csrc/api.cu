@@ -172,9 +172,11 @@ struct LutHook : SaKeyHook {
         const char* s4 = "ACGT";
         for (int d = 0; d < 5; ++d) if (h_code[u8(s5[d])] && h_code[u8(s5[d])] < 16) map.d5[h_code[u8(s5[d])]] = u8(d);
         for (int d = 0; d < 4; ++d) if (h_code[u8(s4[d])] && h_code[u8(s4[d])] < 16) map.d4[h_code[u8(s4[d])]] = u8(d);
-        // depth: buckets of a few suffixes (4^depth <= n), at most 14 symbols (1 GiB of u32 starts), inside the initial key
+        // depth: buckets of a few suffixes (4^depth <= n), at most 15 symbols (4 GiB of u32 starts: buckets of ~3 suffixes
+        // for a 3.1 Gbp strand, which one round of parallel loads compares, instead of a bisection), inside the initial key
+        static const int depth_cap = std::min(15, getenv("ASGART_B200_DEEP_MAX") ? atoi(getenv("ASGART_B200_DEEP_MAX")) : 15);
         int depth = 0;
-        while (depth < 14 && depth < p0 && (u64(1) << (2 * (depth + 1))) <= n) ++depth;
+        while (depth < depth_cap && depth < p0 && (u64(1) << (2 * (depth + 1))) <= n) ++depth;
         if (depth < 4) depth = 0;
         ix.lut_lo.alloc(kLutSize, stream);
         ix.lut_hi.alloc(kLutSize, stream);
@@ -184,11 +186,10 @@ struct LutHook : SaKeyHook {
         ix.deep.alloc(M, stream);
         ix.deep.zero();
         ix.deep_depth = depth;
-        DevBuf<LutCodeMap> d_map(1, stream);
-        CUDA_CHECK(cudaMemcpyAsync(d_map.p, &map, sizeof map, cudaMemcpyHostToDevice, stream));
         if (n_local) {
-            lut_from_keys_kernel<IdxT><<<unsigned(ceil_div(n_local, 256)), 256, 0, stream>>>(d_keys, n_local, base, b, p0, d_map.p, depth,
-                                                                                            ix.lut_lo.p, ix.lut_hi.p, ix.deep.p);
+            lut_from_keys_kernel<IdxT><<<unsigned(ceil_div(n_local, 256 * 4)), 256, 0, stream>>>(d_keys, n_local, base, b, p0, map.nibbles(map.d5),
+                                                                                                map.nibbles(map.d4), depth, ix.lut_lo.p,
+                                                                                                ix.lut_hi.p, ix.deep.p);
             KERNEL_CHECK();
             count_launch();
         }

@@ -195,20 +195,29 @@ __global__ void __launch_bounds__(kRsThreads, 2) rs_scatter_kernel(const KeyT* _
     }
 }
 
-// Sorts by the listed digit positions (each `shift` selects bits [shift, shift+8)), least significant first.
-// Ping-pongs between (keys, vals) and (keys_alt, vals_alt); on return `keys`/`vals` point at the sorted data.
+// Scratch of the radix passes over n elements: the digit-major tile histogram and its scanned offsets.
+template <typename KeyT>
+struct RadixScratch {
+    static constexpr int ITEMS = RsItems<KeyT>::value;
+    static constexpr int TILE = kRsThreads * ITEMS;
+    u64 n = 0, tiles = 0, table = 0;
+    bool wide = false;
+    DevBuf<u32> hist, offs32;
+    DevBuf<u64> offs64;
+    RadixScratch(u64 n_, cudaStream_t stream) : n(n_), tiles(ceil_div(n_, u64(TILE))), table(tiles * 256), wide(n_ >= (u64(1) << 32)) {
+        hist.alloc(table, stream);
+        offs32.alloc(wide ? 0 : table, stream);
+        offs64.alloc(wide ? table : 0, stream);
+    }
+};
+
+// One stable pass by the digit at bits [shift, shift + 8): (kin, vin) -> (kout, vout).
 template <typename KeyT, typename ValT>
-void radix_sort_pairs(KeyT*& keys, KeyT*& keys_alt, ValT*& vals, ValT*& vals_alt, u64 n, const int* shifts, int n_passes,
-                      cudaStream_t stream, FamilyTimer* timer = nullptr, FamilyTimer* scatter_timer = nullptr) {
-    if (n == 0 || n_passes == 0) return;
+void radix_pass(RadixScratch<KeyT>& ws, const KeyT* kin, const ValT* vin, KeyT* kout, ValT* vout, int shift, cudaStream_t stream,
+                FamilyTimer* timer = nullptr, FamilyTimer* scatter_timer = nullptr) {
     constexpr int ITEMS = RsItems<KeyT>::value;
-    constexpr int TILE = kRsThreads * ITEMS;
-    const u64 tiles = ceil_div(n, u64(TILE));
-    const u64 table = tiles * 256;
-    const bool wide = n >= (u64(1) << 32);
-    DevBuf<u32> hist(table, stream);
-    DevBuf<u32> offs32(wide ? 0 : table, stream);
-    DevBuf<u64> offs64(wide ? table : 0, stream);
+    const u64 n = ws.n, tiles = ws.tiles, table = ws.table;
+    if (n == 0) return;
     constexpr size_t smem32 = RsSmem<KeyT, ValT, u32, ITEMS>::bytes, smem64 = RsSmem<KeyT, ValT, u64, ITEMS>::bytes;
     static bool attr_set = false;  // per (KeyT, ValT) instantiation
     if (!attr_set) {
@@ -216,31 +225,40 @@ void radix_sort_pairs(KeyT*& keys, KeyT*& keys_alt, ValT*& vals, ValT*& vals_alt
         CUDA_CHECK(cudaFuncSetAttribute(rs_scatter_kernel<KeyT, ValT, u64, ITEMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem64)));
         attr_set = true;
     }
+    if (timer) timer->begin();
+    rs_hist_kernel<KeyT, ITEMS><<<unsigned(tiles), kRsThreads, 0, stream>>>(kin, n, shift, ws.hist.p, tiles);
+    KERNEL_CHECK();
+    const u32* hp = ws.hist.p;
+    if (!ws.wide) {
+        u32* op = ws.offs32.p;
+        device_scan<u32, SumOp>([hp] __device__(u64 i) { return hp[i]; },
+                                [op] __device__(u64 i, u32 exc, u32) { op[i] = exc; }, table, (u32*)nullptr, stream);
+        if (scatter_timer) scatter_timer->begin();
+        rs_scatter_kernel<KeyT, ValT, u32, ITEMS>
+            <<<unsigned(tiles), kRsThreads, smem32, stream>>>(kin, vin, kout, vout, n, shift, ws.offs32.p, tiles);
+    } else {
+        u64* op = ws.offs64.p;
+        device_scan<u64, SumOp>([hp] __device__(u64 i) { return u64(hp[i]); },
+                                [op] __device__(u64 i, u64 exc, u64) { op[i] = exc; }, table, (u64*)nullptr, stream);
+        if (scatter_timer) scatter_timer->begin();
+        rs_scatter_kernel<KeyT, ValT, u64, ITEMS>
+            <<<unsigned(tiles), kRsThreads, smem64, stream>>>(kin, vin, kout, vout, n, shift, ws.offs64.p, tiles);
+    }
+    if (scatter_timer) scatter_timer->end(1, n * (2 * sizeof(KeyT) + 2 * sizeof(ValT)));
+    KERNEL_CHECK();
+    count_launch(2);
+    if (timer) timer->end(5, n * (2 * sizeof(KeyT) + 2 * sizeof(ValT)));
+}
+
+// Sorts by the listed digit positions (each `shift` selects bits [shift, shift+8)), least significant first.
+// Ping-pongs between (keys, vals) and (keys_alt, vals_alt); on return `keys`/`vals` point at the sorted data.
+template <typename KeyT, typename ValT>
+void radix_sort_pairs(KeyT*& keys, KeyT*& keys_alt, ValT*& vals, ValT*& vals_alt, u64 n, const int* shifts, int n_passes,
+                      cudaStream_t stream, FamilyTimer* timer = nullptr, FamilyTimer* scatter_timer = nullptr) {
+    if (n == 0 || n_passes == 0) return;
+    RadixScratch<KeyT> ws(n, stream);
     for (int p = 0; p < n_passes; ++p) {
-        const int shift = shifts[p];
-        if (timer) timer->begin();
-        rs_hist_kernel<KeyT, ITEMS><<<unsigned(tiles), kRsThreads, 0, stream>>>(keys, n, shift, hist.p, tiles);
-        KERNEL_CHECK();
-        const u32* hp = hist.p;
-        if (!wide) {
-            u32* op = offs32.p;
-            device_scan<u32, SumOp>([hp] __device__(u64 i) { return hp[i]; },
-                                    [op] __device__(u64 i, u32 exc, u32) { op[i] = exc; }, table, (u32*)nullptr, stream);
-            if (scatter_timer) scatter_timer->begin();
-            rs_scatter_kernel<KeyT, ValT, u32, ITEMS>
-                <<<unsigned(tiles), kRsThreads, smem32, stream>>>(keys, vals, keys_alt, vals_alt, n, shift, offs32.p, tiles);
-        } else {
-            u64* op = offs64.p;
-            device_scan<u64, SumOp>([hp] __device__(u64 i) { return u64(hp[i]); },
-                                    [op] __device__(u64 i, u64 exc, u64) { op[i] = exc; }, table, (u64*)nullptr, stream);
-            if (scatter_timer) scatter_timer->begin();
-            rs_scatter_kernel<KeyT, ValT, u64, ITEMS>
-                <<<unsigned(tiles), kRsThreads, smem64, stream>>>(keys, vals, keys_alt, vals_alt, n, shift, offs64.p, tiles);
-        }
-        if (scatter_timer) scatter_timer->end(1, n * (2 * sizeof(KeyT) + 2 * sizeof(ValT)));
-        KERNEL_CHECK();
-        count_launch(2);
-        if (timer) timer->end(5, n * (2 * sizeof(KeyT) + 2 * sizeof(ValT)));
+        radix_pass<KeyT, ValT>(ws, keys, vals, keys_alt, vals_alt, shifts[p], stream, timer, scatter_timer);
         KeyT* tk = keys; keys = keys_alt; keys_alt = tk;
         ValT* tv = vals; vals = vals_alt; vals_alt = tv;
     }

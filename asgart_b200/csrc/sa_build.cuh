@@ -268,12 +268,12 @@ __global__ void large_copy_back_kernel(const IdxT* __restrict__ hs, const IdxT* 
 // secondary key of a suffix that starts a run of >= p0 equal symbols x: with r = run length left and c = the symbol after
 // the run, suffixes order by ascending r when c < x and by descending r, after all of those, when c > x.
 template <typename IdxT>
-__global__ void run_key_kernel(const u8* __restrict__ text, const uint16_t* __restrict__ code, const IdxT* __restrict__ E,
-                               const IdxT* __restrict__ GS, const IdxT* __restrict__ IS, u64 US, u64 n, int kb0, u64* __restrict__ K,
+__global__ void run_key_kernel(const u8* __restrict__ text, const uint16_t* __restrict__ code, const IdxT* __restrict__ RS,
+                               const IdxT* __restrict__ RE, u64 NR, const IdxT* __restrict__ GS, const IdxT* __restrict__ IS, u64 US, u64 n, int kb0, u64* __restrict__ K,
                                IdxT* __restrict__ Gx) {
     const u64 c = u64(blockIdx.x) * blockDim.x + threadIdx.x;
     if (c >= US) return;
-    const u64 i = IS[c], e = E[i], r = e - i;
+    const u64 i = IS[c], e = RE[last_le(RS, NR, i)], r = e - i;   // the long run that holds i
     const u32 x = code[text[i]];
     const u32 cs = e < n ? code[text[e]] : 0u;
     const u64 flag = cs > x ? 1 : 0;
@@ -402,7 +402,7 @@ void build_suffix_array(const u8* d_text, u64 n, IdxT* d_sa, const RankView<IdxT
         for (int s = 0; s < b * p0; s += 8) shifts.push_back(s);
         // the sorted suffix indices must end up in d_sa itself: with an even number of passes they start there
         // (sharded: the piece d_sa + base is not 16-byte aligned, the sort runs in its own buffers and is copied over)
-        DevBuf<u64> keysA(n_loc, stream), keysB(n_loc, stream);
+        DevBuf<u64> keysA(n_loc + 2, stream), keysB(n_loc + 2, stream);   // + 2: reused as pair buffers by the inverse scatter
         DevBuf<IdxT> valsT(n_loc, stream), valsU(grp ? n_loc : 0, stream);
         u64 *k = keysA.p, *ka = keysB.p;
         IdxT *v, *va;
@@ -474,7 +474,8 @@ void build_suffix_array(const u8* d_text, u64 n, IdxT* d_sa, const RankView<IdxT
                 if (head) hsa[exc.e] = exc.c;
             }
         });
-        if (!grp) inverse_scatter<IdxT>(d_sa, rpos, n, d_rank.base[0], n, stream);
+        // the sorted keys are dead from here on: both key buffers serve as scratch of the sort-back scatter
+        if (!grp) inverse_scatter<IdxT>(d_sa, rpos, n, d_rank.base[0], n, stream, k, ka);
         else if (n_loc) {
             const unsigned grid = unsigned(std::min<u64>(ceil_div(n_loc, 256), u64(kNumSMs) * 16));
             scatter_view_kernel<IdxT><<<grid, 256, 0, stream>>>(sa_loc, rpos, n_loc, d_rank);
@@ -491,18 +492,47 @@ void build_suffix_array(const u8* d_text, u64 n, IdxT* d_sa, const RankView<IdxT
     u64 US2 = 0, NGS2 = 0;
     if (US > 0) {
         if (st) st->rounds++;
-        DevBuf<IdxT> E(n, stream);
+        // the runs of >= p0 equal symbols, as sorted (start, end) lists: every suffix of the round lies inside one of them.
+        // Two counting flags in one flag scan over the text (start of a long run / last symbol of one); the lists pair up by
+        // index because runs are disjoint. (A run-end array over all n positions cost 16 ms and 4n bytes at 3.1 Gbp.)
+        DevBuf<IdxT> RS, RE;
+        u64 NR = 0;
         {
-            IdxT* ep = E.p;
             const u8* tp = d_text;
-            device_scan<IdxT, MaxOp>(
-                [tp, n] __device__(u64 kx) { const u64 i = n - 1 - kx; return (i + 1 == n || tp[i] != tp[i + 1]) ? IdxT(kx + 1) : IdxT(0); },
-                [ep, n] __device__(u64 kx, IdxT, IdxT inc) { ep[n - 1 - kx] = IdxT(n - u64(inc) + 1); }, n, (IdxT*)nullptr, stream);
+            const u64 nn = n;
+            const u32 p0u = u32(p0);
+            auto rin = [tp, nn, p0u] __device__(u64 i) -> u32 {
+                const u8 c = tp[i];
+                u32 f = 0;
+                if ((i == 0 || tp[i - 1] != c) && i + p0u <= nn) {
+                    bool all = true;
+                    for (u32 j = 1; j < p0u && all; ++j) all = tp[i + j] == c;
+                    if (all) f |= FS_CNT_C;
+                }
+                if ((i + 1 == nn || tp[i + 1] != c) && i + 1 >= p0u) {
+                    bool all = true;
+                    for (u32 j = 1; j < p0u && all; ++j) all = tp[i - j] == c;
+                    if (all) f |= FS_CNT_D;
+                }
+                return f;
+            };
+            DevBuf<Acc> d_rt(1, stream);
+            FlagScanPlan<IdxT> rplan;
+            rplan.prepare(rin, n, d_rt.p, stream);
+            Acc rt;
+            sync_read(&rt, d_rt.p, sizeof rt);
+            NR = u64(rt.c);
+            RS.alloc(NR, stream); RE.alloc(NR, stream);
+            IdxT *rs = RS.p, *re = RE.p;
+            rplan.finish(rin, [rs, re] __device__(u64 i, const Acc& exc, const Acc& inc) {
+                if (inc.c != exc.c) rs[exc.c] = IdxT(i);
+                if (inc.d != exc.d) re[exc.d] = IdxT(i + 1);
+            });
         }
         const int kb0 = std::max(1, bit_width_u64(n));
         DevBuf<u64> KA(US, stream), KB(US, stream);
         DevBuf<IdxT> IB(US, stream), Gx(sigma + 2, stream);
-        run_key_kernel<IdxT><<<unsigned(ceil_div(US, 256)), 256, 0, stream>>>(d_text, d_code.p, E.p, GS.p, IS.p, US, n, kb0, KA.p, Gx.p);
+        run_key_kernel<IdxT><<<unsigned(ceil_div(US, 256)), 256, 0, stream>>>(d_text, d_code.p, RS.p, RE.p, NR, GS.p, IS.p, US, n, kb0, KA.p, Gx.p);
         KERNEL_CHECK();
         count_launch();
         std::vector<int> shifts;

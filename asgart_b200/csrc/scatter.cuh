@@ -7,12 +7,18 @@
 // with four sweeps over 57 M elements. So:
 //   out fits one slice          -> plain scatter
 //   a few slices (<= kSweepMax) -> one sweep over (idx, val) per slice, each writing only its slice's targets
-//   more                        -> plain scatter. Tried and dropped: one radix partition pass of the pairs by slice number
-//                                  followed by an in-order scatter (profiles/r1_scatter_bench.log): the in-order scatter
-//                                  reaches 26-51 G elem/s only, and with the partition pass the whole is slower than the
-//                                  plain scatter at 249 M (15.0 vs 15.5 ms for the re-ranking) and at 3.1 G targets (229 vs 193 ms).
+//   more, idx a permutation     -> sort the pairs back by target: two radix partition passes by bits [16, 32) of idx leave
+//                                  the pairs of every 65 536-target bucket contiguous (bucket b = pairs [b << 16, (b+1) << 16),
+//                                  because idx is a permutation); one block per bucket then scatters inside shared memory
+//                                  and writes its slice of `out` as whole lines. No random access reaches L2 or DRAM:
+//                                  52 B of streamed traffic per element instead of a 64 B DRAM read-modify-write at
+//                                  random-access efficiency (C4, 3.1 G targets: 132 ms for the plain scatter).
+//   more, otherwise             -> plain scatter. Tried and dropped: one radix partition pass of the pairs by slice number
+//                                  followed by an in-order scatter into L2-sized slices (profiles/r1_scatter_bench.log):
+//                                  the L2 takes 26-51 G scattered elem/s only.
 #pragma once
 #include "common.cuh"
+#include "radix_sort.cuh"
 
 namespace ab200 {
 
@@ -38,11 +44,98 @@ __global__ void __launch_bounds__(256) scatter_slice_kernel(const IdxT* __restri
     }
 }
 
+// One block per bucket of 2^kBucketBits targets whose pairs are contiguous: the values are placed in shared memory, half a
+// bucket (128 KB) at a time, and leave as coalesced 16-byte stores. The second half re-reads the pairs (L2 hits).
+constexpr int kBucketBits = 16;
+constexpr int kBucketHalfBits = kBucketBits - 1;
+constexpr int kBucketThreads = 1024;
+
+__global__ void __launch_bounds__(kBucketThreads, 1) bucket_scatter_kernel(const u32* __restrict__ idx, const u32* __restrict__ val, u64 n,
+                                                                          u32* __restrict__ out) {
+    extern __shared__ __align__(16) u32 bs_slot[];   // 2^kBucketHalfBits values
+    const u64 b0 = u64(blockIdx.x) << kBucketBits;
+    const u32 cnt = u32(min(u64(1) << kBucketBits, n - b0));
+    const u32* __restrict__ pi = idx + b0;
+    const u32* __restrict__ pv = val + b0;
+    const u32 tid = threadIdx.x;
+    for (u32 half = 0; half < 2; ++half) {
+        const u32 lo = half << kBucketHalfBits;
+        if (lo >= cnt) break;
+#pragma unroll 4
+        for (u32 i = tid * 4; i < cnt; i += kBucketThreads * 4) {
+            if (i + 4 <= cnt) {
+                const uint4 p = *reinterpret_cast<const uint4*>(pi + i);
+                const uint4 v = *reinterpret_cast<const uint4*>(pv + i);
+                const u32 m = (1u << kBucketHalfBits) - 1u;
+                if (((p.x >> kBucketHalfBits) & 1u) == half) bs_slot[p.x & m] = v.x;
+                if (((p.y >> kBucketHalfBits) & 1u) == half) bs_slot[p.y & m] = v.y;
+                if (((p.z >> kBucketHalfBits) & 1u) == half) bs_slot[p.z & m] = v.z;
+                if (((p.w >> kBucketHalfBits) & 1u) == half) bs_slot[p.w & m] = v.w;
+            } else {
+                for (u32 j = i; j < cnt; ++j) {
+                    const u32 p = pi[j];
+                    if (((p >> kBucketHalfBits) & 1u) == half) bs_slot[p & ((1u << kBucketHalfBits) - 1u)] = pv[j];
+                }
+            }
+        }
+        __syncthreads();
+        const u32 m = min(1u << kBucketHalfBits, cnt - lo);
+        u32* __restrict__ po = out + b0 + lo;
+        for (u32 i = tid * 4; i < m; i += kBucketThreads * 4) {
+            if (i + 4 <= m) *reinterpret_cast<uint4*>(po + i) = *reinterpret_cast<const uint4*>(bs_slot + i);
+            else for (u32 j = i; j < m; ++j) po[j] = bs_slot[j];
+        }
+        __syncthreads();
+    }
+}
+
+// out[idx[i]] = val[i] for idx a permutation of [0, n), n < 2^32. ws_a and ws_b hold 2 * (n + 4) u32 each; `val` may be
+// overwritten (nothing here does), idx and val are left intact. All of idx/val/out/ws_* 16-byte aligned.
+inline void inverse_permutation_scatter(const u32* idx, const u32* val, u64 n, u32* out, u32* ws_a, u32* ws_b, cudaStream_t stream,
+                                        FamilyTimer* timer = nullptr) {
+    if (n == 0) return;
+    const u64 half = (n + 3) / 4 * 4;   // the value halves stay 16-byte aligned
+    RadixScratch<u32> ws(n, stream);
+    const int bits = bit_width_u64(n - 1);
+    const u32 *ki = idx, *vi = val;
+    u32* bufs[2] = {ws_a, ws_b};
+    int w = 0;
+    for (int shift = kBucketBits; shift < bits; shift += 8) {
+        radix_pass<u32, u32>(ws, ki, vi, bufs[w], bufs[w] + half, shift, stream, timer, nullptr);
+        ki = bufs[w]; vi = bufs[w] + half;
+        w ^= 1;
+    }
+    static bool attr_set = false;
+    constexpr int smem = int(sizeof(u32)) << kBucketHalfBits;
+    if (!attr_set) {
+        CUDA_CHECK(cudaFuncSetAttribute(bucket_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_set = true;
+    }
+    if (timer) timer->begin();
+    bucket_scatter_kernel<<<unsigned(ceil_div(n, u64(1) << kBucketBits)), kBucketThreads, smem, stream>>>(ki, vi, n, out);
+    KERNEL_CHECK();
+    count_launch();
+    if (timer) timer->end(1, n * 3 * sizeof(u32));
+}
+
+// out[idx[i]] = val[i]. perm_ws_a/b (optional, see inverse_permutation_scatter) enable the sort-back path when idx is
+// a permutation of [0, n) = [0, out_len).
 template <typename IdxT>
-void inverse_scatter(const IdxT* idx, const IdxT* val, u64 n, IdxT* out, u64 out_len, cudaStream_t stream) {
+void inverse_scatter(const IdxT* idx, const IdxT* val, u64 n, IdxT* out, u64 out_len, cudaStream_t stream, void* perm_ws_a = nullptr,
+                     void* perm_ws_b = nullptr, FamilyTimer* timer = nullptr) {
     if (n == 0) return;
     const u64 slice = kScatterSliceBytes / sizeof(IdxT);
     u64 sweeps = ceil_div(out_len, slice);
+    if constexpr (sizeof(IdxT) == 4) {
+        // developer/test knob: ASGART_B200_PERM_SCATTER_MIN=<elements> moves the threshold of the sort-back path
+        static const char* knob = getenv("ASGART_B200_PERM_SCATTER_MIN");
+        const bool big = knob ? n >= u64(strtoull(knob, nullptr, 10)) : sweeps > u64(kSweepMax);
+        if (big && perm_ws_a && perm_ws_b && n == out_len) {
+            inverse_permutation_scatter(reinterpret_cast<const u32*>(idx), reinterpret_cast<const u32*>(val), n, reinterpret_cast<u32*>(out),
+                                        static_cast<u32*>(perm_ws_a), static_cast<u32*>(perm_ws_b), stream, timer);
+            return;
+        }
+    }
     if (sweeps > u64(kSweepMax)) sweeps = 1;
     const unsigned grid = unsigned(std::min<u64>(ceil_div(n, 256 * (16 / sizeof(IdxT))), u64(kNumSMs) * 16));
     for (u64 k = 0; k < sweeps; ++k) {

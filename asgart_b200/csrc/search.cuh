@@ -80,64 +80,75 @@ __device__ __forceinline__ u32 chunk_of_probe(const ChunkDev* __restrict__ ch, u
 struct LutCodeMap {
     u8 d5[16];  // dense symbol code -> base-5 digit A,C,G,N,T = 0..4 (255: '$' or padding)
     u8 d4[16];  // dense symbol code -> base-4 digit A,C,G,T = 0..3 (255 otherwise)
+    u64 nibbles(const u8* d) const { u64 m = 0; for (int c = 0; c < 16; ++c) m |= u64(d[c] == 255 ? 15u : d[c]) << (4 * c); return m; }
 };
 
-__device__ __forceinline__ bool key_slot5(u64 key, int b, int p0, const LutCodeMap& m, u32& slot) {
-    u32 s = 0;
-    bool ok = true;
+// the code maps as 16 nibbles each (0xF = no digit): register-resident, so decoding a key is pure ALU work
+__device__ __forceinline__ bool key_slot5(u64 key, int b, int p0, u64 m5, u32& slot) {
+    u32 s = 0, bad = 0;
     const u32 mask = (1u << b) - 1u;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-        const u32 d = m.d5[u32(key >> (b * (p0 - 1 - j))) & mask];
-        ok = ok && d != 255u;
+        const u32 d = u32(m5 >> (4u * (u32(key >> (b * (p0 - 1 - j))) & mask))) & 15u;
+        bad |= d;
         s = s * 5u + d;
     }
     slot = s;
-    return ok;
+    return (bad & 8u) == 0;   // digits are 0..4, 15 = invalid symbol
 }
-__device__ __forceinline__ bool key_slot4(u64 key, int b, int p0, int depth, const LutCodeMap& m, u32& slot) {
-    u32 s = 0;
-    bool ok = true;
+__device__ __forceinline__ bool key_slot4(u64 key, int b, int p0, int depth, u64 m4, u32& slot) {
+    u32 s = 0, bad = 0;
     const u32 mask = (1u << b) - 1u;
-    for (int j = 0; j < depth; ++j) {
-        const u32 d = m.d4[u32(key >> (b * (p0 - 1 - j))) & mask];
-        ok = ok && d != 255u;
-        s = s * 4u + d;
+    int sh = b * (p0 - 1);
+    for (int j = 0; j < depth; ++j, sh -= b) {
+        const u32 d = u32(m4 >> (4u * (u32(key >> sh) & mask))) & 15u;
+        bad |= d;
+        s = s * 4u + (d & 3u);
     }
     slot = s;
-    return ok;
+    return (bad & 12u) == 0;   // digits are 0..3
 }
 
 // 8-mer LUT (Searcher::new, src/searcher.rs:99-143) and, when depth > 0, the first suffix of every ACGT-only
 // `depth`-mer (0 = not seen; position 0 is always the '$' suffix) from the sorted initial keys. Needs p0 >= 8, depth.
+// Four keys per thread (two 16-byte loads + the predecessor); keys must be 16-byte aligned.
 template <typename IdxT>
 __global__ void __launch_bounds__(256) lut_from_keys_kernel(const u64* __restrict__ keys, u64 n_local, u64 base, int b, int p0,
-                                                            const LutCodeMap* __restrict__ map, int depth, IdxT* __restrict__ lut_lo,
+                                                            u64 m5, u64 m4, int depth, IdxT* __restrict__ lut_lo,
                                                             IdxT* __restrict__ lut_hi, IdxT* __restrict__ deep) {
-    __shared__ LutCodeMap smap;   // dynamically indexed: a by-value kernel parameter would be copied to every thread's stack, so it comes by pointer
-    if (threadIdx.x < 16) { smap.d5[threadIdx.x] = map->d5[threadIdx.x]; smap.d4[threadIdx.x] = map->d4[threadIdx.x]; }
-    __syncthreads();
-    const u64 i = u64(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (i >= n_local) return;
     // keys[0 .. n_local) are positions [base, base + n_local) of the sorted keys (sharded build: one member's key range,
     // cut where the first four symbols change, so the first and the last key of the piece are bucket boundaries)
-    const u64 cur = keys[i];
-    const u64 prev = i > 0 ? keys[i - 1] : ~cur;
-    // slots only change where the leading symbols do: decode the (rare) boundaries only
-    const int s8 = b * (p0 - 8);
-    if ((cur >> s8) != (prev >> s8) || i + 1 == n_local) {
-        u32 cs = 0, ps = 0;
-        const bool cur_ok = key_slot5(cur, b, p0, smap, cs);
-        const bool prev_ok = i > 0 && key_slot5(prev, b, p0, smap, ps);
-        if (cur_ok && (!prev_ok || ps != cs)) lut_lo[cs] = IdxT(base + i);
-        if (prev_ok && (!cur_ok || ps != cs)) lut_hi[ps] = IdxT(base + i);
-        if (i + 1 == n_local && cur_ok) lut_hi[cs] = IdxT(base + n_local);
+    const u64 i0 = (u64(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
+    if (i0 >= n_local) return;
+    u64 kk[5];
+    kk[0] = i0 > 0 ? keys[i0 - 1] : 0;
+    if (i0 + 4 <= n_local) {
+        const ulonglong2 v0 = *reinterpret_cast<const ulonglong2*>(keys + i0), v1 = *reinterpret_cast<const ulonglong2*>(keys + i0 + 2);
+        kk[1] = v0.x; kk[2] = v0.y; kk[3] = v1.x; kk[4] = v1.y;
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) kk[j + 1] = i0 + j < n_local ? keys[i0 + j] : 0;
     }
-    if (depth > 0) {
-        const int sd = b * (p0 - depth);
-        if ((cur >> sd) != (prev >> sd)) {
+    if (i0 == 0) kk[0] = ~kk[1];
+    const int s8 = b * (p0 - 8);
+    const int sd = b * (p0 - depth);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const u64 i = i0 + j;
+        if (i >= n_local) break;
+        const u64 cur = kk[j + 1], prev = kk[j];
+        // slots only change where the leading symbols do: decode the boundaries only
+        if ((cur >> s8) != (prev >> s8) || i + 1 == n_local) {
+            u32 cs = 0, ps = 0;
+            const bool cur_ok = key_slot5(cur, b, p0, m5, cs);
+            const bool prev_ok = i > 0 && key_slot5(prev, b, p0, m5, ps);
+            if (cur_ok && (!prev_ok || ps != cs)) lut_lo[cs] = IdxT(base + i);
+            if (prev_ok && (!cur_ok || ps != cs)) lut_hi[ps] = IdxT(base + i);
+            if (i + 1 == n_local && cur_ok) lut_hi[cs] = IdxT(base + n_local);
+        }
+        if (depth > 0 && (cur >> sd) != (prev >> sd)) {
             u32 cs = 0;
-            if (key_slot4(cur, b, p0, depth, smap, cs)) deep[cs] = IdxT(base + i);
+            if (key_slot4(cur, b, p0, depth, m4, cs)) deep[cs] = IdxT(base + i);
         }
     }
 }

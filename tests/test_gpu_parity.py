@@ -492,3 +492,33 @@ def test_full_size_properties(config):
             for (l, r, ll, rl, rev, comp) in fam:
                 assert l < r and ll >= 1 and rl >= st.min_duplication_length
                 assert rev == st.reverse and comp == st.complement
+
+
+_SORT_BACK_SCRIPT = r"""
+import sys
+import numpy as np
+sys.path.insert(0, {root!r})
+import asgart_b200 as ab
+import oracle
+from tests import cases
+rng = np.random.default_rng(5)
+texts = [rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=n) for n in (10, 65535, 65536, 65537, 200003, 1 << 20)]
+texts.append(np.frombuffer(cases.stress_text(21, n=700_000, n_dups=40), dtype=np.uint8))
+g, fr = ab.synth_genome(2, scale_n=3_000_000)
+texts.append(np.array(ab.Prepared.from_memory(ab.normalise(g, True), fr, "x.fa").strand))
+for t in texts:
+    got = ab.r_divsufsort(t, device=0, index_bits=32)
+    assert np.array_equal(got, oracle.best_suffix_array(t)), len(t)
+print("sort-back ok", len(texts))
+"""
+
+
+def test_sa_sort_back_inverse_scatter(tmp_path):
+    """The sort-back inverse scatter (scatter.cuh: two radix partition passes + per-bucket shared-memory scatter) only
+    engages above 72 M suffixes; ASGART_B200_PERM_SCATTER_MIN=0 forces it for small texts, including bucket-edge sizes."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, ASGART_B200_PERM_SCATTER_MIN="0")
+    r = subprocess.run([sys.executable, "-c", _SORT_BACK_SCRIPT.format(root=root)], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "sort-back ok" in r.stdout, r.stdout + r.stderr
