@@ -11,8 +11,9 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libasgart_b200.so")
 
-OK, EINVAL, ENOMEM, ECUDA, ESTATE, ENODEVICE = 0, -1, -2, -3, -4, -5
+OK, EINVAL, ENOMEM, ECUDA, ESTATE, ENODEVICE, EPANIC = 0, -1, -2, -3, -4, -5, -6
 POST_FILTER_NS, POST_REORDER, POST_REDUCE_OVERLAP, POST_SORT, POST_ALL = 1, 2, 4, 8, 15
+POST_COMPUTE_SCORE = 16
 LUT_SIZE = 390625
 
 
@@ -27,6 +28,7 @@ class Settings(C.Structure):
         ("min_duplication_length", C.c_uint64),
         ("max_cardinality", C.c_uint64),
         ("has_trim", C.c_uint32),
+        ("compute_score", C.c_uint32),
         ("trim_a", C.c_uint64),
         ("trim_b", C.c_uint64),
     ]
@@ -59,6 +61,7 @@ class Stats(C.Structure):
                                      "n_skipped_n", "n_skipped_card", "n_matches", "n_events", "n_segments", "sa_rounds",
                                      "sa_index_bits", "h2d_bytes", "d2h_bytes")]
         + [("ms_sa_scatter_main", C.c_double), ("launches_sa_scatter_main", C.c_uint64), ("bytes_sa_scatter_main", C.c_uint64)]
+        + [("ms_score", C.c_double), ("score_cells", C.c_uint64), ("score_pairs", C.c_uint64)]
     )
 
     def as_dict(self):

@@ -13,7 +13,7 @@ from typing import List, Optional, Sequence, Tuple
 import numpy as np
 
 from . import _lib
-from ._lib import POST_ALL, POST_FILTER_NS, POST_REDUCE_OVERLAP, POST_REORDER, POST_SORT  # noqa: F401
+from ._lib import POST_ALL, POST_COMPUTE_SCORE, POST_FILTER_NS, POST_REDUCE_OVERLAP, POST_REORDER, POST_SORT  # noqa: F401
 
 
 class AsgartB200Error(RuntimeError):
@@ -33,6 +33,7 @@ class RunSettings:
     complement: bool = False
     skip_masked: bool = False
     trim: Optional[Tuple[int, int]] = None
+    compute_score: bool = False   # --compute-score: the ComputeScore step (src/bin/asgart.rs:744-746) runs on the GPU
 
     @property
     def max_gap_size(self) -> int:
@@ -42,7 +43,7 @@ class RunSettings:
         t = self.trim or (0, 0)
         return _lib.Settings(self.probe_size, self.max_gap_size, int(self.reverse), int(self.complement),
                              int(self.skip_masked), self.min_duplication_length, self.max_cardinality,
-                             int(self.trim is not None), t[0], t[1])
+                             int(self.trim is not None), int(self.compute_score), t[0], t[1])
 
 
 PROTOSD_DTYPE = np.dtype([("left", "<u8"), ("right", "<u8"), ("left_length", "<u8"), ("right_length", "<u8"),
@@ -70,6 +71,11 @@ class Families:
     @property
     def n_families(self) -> int:
         return len(self.fam_offsets) - 1
+
+
+def _with_score(settings: "RunSettings", post_mask: int) -> int:
+    """settings.compute_score pushes the ComputeScore step (src/bin/asgart.rs:744-746) onto a full pipeline."""
+    return post_mask | POST_COMPUTE_SCORE if (settings.compute_score and post_mask) else post_mask
 
 
 def _ptr(a: np.ndarray):
@@ -217,7 +223,7 @@ class Context:
         ch = _chunks_array(chunks)
         st = settings.to_c()
         rh = C.c_void_p()
-        self._check(self.L.asgart_b200_ctx_search(self.h, _ptr(ch), len(ch), C.byref(st), post_mask, C.byref(rh)))
+        self._check(self.L.asgart_b200_ctx_search(self.h, _ptr(ch), len(ch), C.byref(st), _with_score(settings, post_mask), C.byref(rh)))
         return self._take(rh)
 
     def probe_ranges(self, chunk: Tuple[int, int], settings: RunSettings, n_probes: int):
@@ -252,7 +258,7 @@ class Context:
         sizes = (C.c_int64 * len(parts))(*[len(p) for p in parts])
         rh = C.c_void_p()
         self._check(self.L.asgart_b200_ctx_finish(self.h, _ptr(ch), len(ch), C.byref(st), ptrs, sizes, len(parts),
-                                                  post_mask, C.byref(rh)))
+                                                  _with_score(settings, post_mask), C.byref(rh)))
         return self._take(rh)
 
     def search_shard_dev(self, chunks, settings: RunSettings, shard: int, n_shards: int):
@@ -272,7 +278,7 @@ class Context:
         ptrs = (C.c_void_p * len(blob_ptrs))(*blob_ptrs)
         rh = C.c_void_p()
         self._check(self.L.asgart_b200_ctx_finish_dev(self.h, _ptr(ch), len(ch), C.byref(st), ptrs, _ptr(metas), len(blob_ptrs),
-                                                      post_mask, C.byref(rh)))
+                                                      _with_score(settings, post_mask), C.byref(rh)))
         return self._take(rh)
 
     def post_steps(self, fam: Families, post_mask: int) -> Families:

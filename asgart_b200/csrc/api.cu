@@ -11,6 +11,7 @@
 #include "common.cuh"
 #include "dist_group.cuh"
 #include "sa_build.cuh"
+#include "levenshtein.cuh"
 #include "search.cuh"
 
 namespace ab200 {
@@ -516,6 +517,24 @@ void run_post(asgart_b200_ctx* ctx, DevBuf<asgart_b200_protosd>& d_sds, DevBuf<u
     n_fam = tot.b;
 }
 
+// ComputeScore (src/bin/asgart.rs:98-111): the reference runs it between ReduceOverlap and Sort; the identity of a duplicon
+// depends on its own fields only and Sort only permutes, so it is computed on the final list.
+void run_score(asgart_b200_ctx* ctx, DevBuf<asgart_b200_protosd>& d_sds, u64 n_sds) {
+    if (n_sds == 0) return;
+    if (!ctx->have_strand) throw CudaError(ASGART_B200_ESTATE, "ComputeScore needs a loaded strand");
+    LevStats ls;
+    const int rc = compute_score(ctx->d_text.p, ctx->n1, d_sds.p, n_sds, ctx->stream, &ls);
+    ctx->st.ms_score += ls.ms;
+    ctx->st.score_cells += ls.cells;
+    ctx->st.score_pairs += ls.pairs;
+    if (rc == 1)
+        throw CudaError(ASGART_B200_EPANIC, "ComputeScore: a complemented right arm ends on the '$' terminator; the reference panics here "
+                                            "(\"Unknown nucleotide\", src/structs.rs:28-34)");
+    if (rc == 2)
+        throw CudaError(ASGART_B200_EPANIC, "ComputeScore: an arm's inclusive range reaches past the strand; the reference panics here "
+                                            "(slice index out of range, src/structs.rs:441-442)");
+}
+
 void download_result(asgart_b200_ctx* ctx, const DevBuf<asgart_b200_protosd>& d_sds, const DevBuf<u64>& d_off, u64 n_fam, u64 n_sds,
                      asgart_b200_result* r) {
     r->fam_off.assign(n_fam + 1, 0);
@@ -641,6 +660,7 @@ void run_stage_b(asgart_b200_ctx* ctx, const ChunkPlan& plan, const asgart_b200_
     tpost.stop();
     ctx->st.ms_automaton += tauto.ms();
     ctx->st.ms_post += tpost.ms();
+    if (post_mask & ASGART_B200_POST_COMPUTE_SCORE) run_score(ctx, d_sds, n_sds);
     download_result(ctx, d_sds, d_off, n_fam, n_sds, result);
 }
 
@@ -1185,7 +1205,8 @@ int32_t asgart_b200_ctx_post_steps(asgart_b200_ctx* ctx, const uint64_t* family_
     return guarded(ctx, [&]() -> int32_t {
         if (!out || !family_offsets || n_families < 0) return fail(ctx, ASGART_B200_EINVAL, "bad post_steps arguments");
         *out = nullptr;
-        if ((post_mask & ASGART_B200_POST_FILTER_NS) && !ctx->have_strand) return fail(ctx, ASGART_B200_ESTATE, "FilterNs needs a loaded strand");
+        if ((post_mask & (ASGART_B200_POST_FILTER_NS | ASGART_B200_POST_COMPUTE_SCORE)) && !ctx->have_strand)
+            return fail(ctx, ASGART_B200_ESTATE, "FilterNs / ComputeScore need a loaded strand");
         u64 n_fam = u64(n_families), n_sds = family_offsets[n_families];
         if (n_sds && !sds) return fail(ctx, ASGART_B200_EINVAL, "null sds");
         cudaStream_t s = ctx->stream;
@@ -1195,6 +1216,7 @@ int32_t asgart_b200_ctx_post_steps(asgart_b200_ctx* ctx, const uint64_t* family_
         if (n_sds) CUDA_CHECK(cudaMemcpyAsync(d_sds.p, sds, n_sds * sizeof(asgart_b200_protosd), cudaMemcpyHostToDevice, s));
         CUDA_CHECK(cudaStreamSynchronize(s));
         run_post(ctx, d_sds, d_off, n_fam, n_sds, post_mask);
+        if (post_mask & ASGART_B200_POST_COMPUTE_SCORE) run_score(ctx, d_sds, n_sds);
         asgart_b200_result* r = new asgart_b200_result();
         try { download_result(ctx, d_sds, d_off, n_fam, n_sds, r); } catch (...) { delete r; throw; }
         CUDA_CHECK(cudaStreamSynchronize(s));

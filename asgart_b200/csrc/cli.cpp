@@ -44,7 +44,8 @@ int main(int argc, char** argv) {
         else if (a == "--out") out = need(i);
         else if (a == "--device") device = atoi(need(i));
         else if (a == "--threads" || a == "--chunk-size") need(i);
-        else if (a == "--trim" || a == "--compute-score") { fprintf(stderr, "asgart-b200: %s is outside the accelerated path\n", a.c_str()); return 2; }
+        else if (a == "--compute-score") st.compute_score = 1;
+        else if (a == "--trim") { fprintf(stderr, "asgart-b200: %s is outside the accelerated path\n", a.c_str()); return 2; }
         else if (a == "-h" || a == "--help") { usage(); return 0; }
         else if (a == "--reverse") st.reverse = 1;
         else if (a == "--complement") st.complement = 1;

@@ -590,7 +590,8 @@ char* asgart_b200_run_files(const char* files, const asgart_b200_settings* st, i
     char* js = nullptr;
     rc = asgart_b200_ctx_load_strand(ctx, p->data.data(), int64_t(p->data.size()));
     if (!rc) rc = asgart_b200_ctx_build_index(ctx);
-    if (!rc) rc = asgart_b200_ctx_search(ctx, p->chunks.data(), int64_t(p->chunks.size()), st, ASGART_B200_POST_ALL, &res);
+    if (!rc) rc = asgart_b200_ctx_search(ctx, p->chunks.data(), int64_t(p->chunks.size()), st,
+                                        ASGART_B200_POST_ALL | (st->compute_score ? ASGART_B200_POST_COMPUTE_SCORE : 0u), &res);
     if (rc) failf(std::string("device pipeline failed: ") + asgart_b200_ctx_last_error(ctx));
     else js = asgart_b200_to_json(p, st, asgart_b200_result_family_offsets(res), asgart_b200_result_n_families(res), asgart_b200_result_sds(res));
     asgart_b200_result_free(res);

@@ -35,6 +35,7 @@ extern "C" {
 #define ASGART_B200_ECUDA      (-3)  /* CUDA runtime error; see asgart_b200_ctx_last_error */
 #define ASGART_B200_ESTATE     (-4)  /* call order violated (e.g. search before build_index) */
 #define ASGART_B200_ENODEVICE  (-5)  /* no usable CUDA device: the product has no CPU path */
+#define ASGART_B200_EPANIC     (-6)  /* the reference itself panics on this input (last_error says where) */
 
 /* ---- (1) drop-in for divsufsort64 (src/divsufsort.rs:10) ------------------------------------------------
  * T[0..n) any bytes, SA[0..n) output, both host memory. Suffix array built on the current CUDA device by
@@ -53,7 +54,8 @@ typedef struct asgart_b200_result asgart_b200_result;
 typedef struct asgart_b200_partial asgart_b200_partial;
 
 /* mirror of RunSettings (src/structs.rs:36-58). max_gap_size is ALREADY gap_size + probe_size
- * (src/bin/asgart.rs:681). threads_count / compute_score have no meaning here. trim is carried for the JSON
+ * (src/bin/asgart.rs:681). threads_count has no meaning here; compute_score is the
+ * post-step bit ASGART_B200_POST_COMPUTE_SCORE. trim is carried for the JSON
  * settings block only (--trim is out of scope). */
 typedef struct asgart_b200_settings {
     uint64_t probe_size;
@@ -64,6 +66,8 @@ typedef struct asgart_b200_settings {
     uint64_t min_duplication_length;
     uint64_t max_cardinality;
     uint32_t has_trim;
+    uint32_t compute_score;   /* --compute-score (src/structs.rs:57): asgart_b200_run_files adds the ComputeScore step.
+                                 Sits in what used to be alignment padding: the struct keeps its 64 bytes. */
     uint64_t trim_a, trim_b;
 } asgart_b200_settings;
 
@@ -90,7 +94,12 @@ typedef struct asgart_b200_protosd {
 #define ASGART_B200_POST_REORDER         2u  /* ReOrder       src/bin/asgart.rs:33-51 */
 #define ASGART_B200_POST_REDUCE_OVERLAP  4u  /* ReduceOverlap src/bin/asgart.rs:67-79, :481-562 */
 #define ASGART_B200_POST_SORT            8u  /* Sort          src/bin/asgart.rs:53-65 */
-#define ASGART_B200_POST_ALL            15u
+#define ASGART_B200_POST_ALL            15u  /* the reference's default pipeline */
+/* ComputeScore (--compute-score): src/bin/asgart.rs:98-111, ProtoSD::levenshtein src/structs.rs:439-452. identity =
+ * 100 * (1 - levenshtein(left arm, right arm reversed then complemented per the flags) / max(left_length, right_length)),
+ * arms taken as the reference takes them (inclusive ranges, length + 1 bytes), f64 arithmetic cast to f32 once.
+ * Bit-parallel (Myers/Hyyro) global edit distance on the GPU, one thread block per duplicon. */
+#define ASGART_B200_POST_COMPUTE_SCORE  16u
 
 /* lifetime */
 ASGART_B200_API int32_t asgart_b200_device_count(void);
@@ -201,6 +210,9 @@ typedef struct asgart_b200_stats {
     /* rs_scatter_kernel launches of the initial sort only (every launch moves all n+1 suffixes: the roofline kernel) */
     double ms_sa_scatter_main;
     uint64_t launches_sa_scatter_main, bytes_sa_scatter_main;
+    /* ComputeScore: device ms, DP cells (sum of arm-length products) and duplicons scored */
+    double ms_score;
+    uint64_t score_cells, score_pairs;
 } asgart_b200_stats;
 ASGART_B200_API int32_t asgart_b200_ctx_stats(const asgart_b200_ctx *ctx, asgart_b200_stats *out);
 ASGART_B200_API void asgart_b200_ctx_reset_stats(asgart_b200_ctx *ctx);

@@ -42,16 +42,17 @@ class Settings(C.Structure):
         ("min_duplication_length", C.c_uint64),
         ("max_cardinality", C.c_uint64),
         ("has_trim", C.c_uint32),
+        ("compute_score", C.c_uint32),
         ("trim_a", C.c_uint64),
         ("trim_b", C.c_uint64),
     ]
 
 
 def make_settings(probe_size=20, gap_size=100, min_length=1000, max_cardinality=500, reverse=False,
-                  complement=False, skip_masked=False) -> Settings:
+                  complement=False, skip_masked=False, compute_score=False) -> Settings:
     """RunSettings as bin/asgart.rs:679-692 builds it: max_gap_size = gap_size + probe_size."""
     return Settings(probe_size, gap_size + probe_size, int(reverse), int(complement), int(skip_masked), min_length,
-                    max_cardinality, 0, 0, 0)
+                    max_cardinality, 0, int(compute_score), 0, 0)
 
 
 _lib = None
@@ -81,7 +82,10 @@ def lib() -> C.CDLL:
         L.oracle_search.restype = C.c_void_p
         L.oracle_result_from_arrays.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
         L.oracle_result_from_arrays.restype = C.c_void_p
-        L.oracle_result_post.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.oracle_result_post.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int]
+        L.oracle_result_post.restype = C.c_int
+        L.oracle_levenshtein.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64]
+        L.oracle_levenshtein.restype = C.c_uint32
         L.oracle_result_n_families.argtypes = [C.c_void_p]
         L.oracle_result_n_families.restype = C.c_int64
         L.oracle_result_n_sds.argtypes = [C.c_void_p]
@@ -261,6 +265,18 @@ def _copy_result(h) -> Families:
 
 POST_FILTER_NS, POST_REORDER, POST_REDUCE_OVERLAP, POST_SORT = 1, 2, 4, 8
 POST_ALL = 15
+POST_COMPUTE_SCORE = 16   # --compute-score (bin/asgart.rs:98-111, 744-746); not part of the default pipeline
+
+
+class RefPanic(RuntimeError):
+    pass
+
+
+def levenshtein(a: bytes, b: bytes) -> int:
+    """bio::alignment::distance::levenshtein restated (plain DP)."""
+    aa = np.frombuffer(bytes(a), dtype=np.uint8) if len(a) else np.zeros(1, dtype=np.uint8)
+    bb = np.frombuffer(bytes(b), dtype=np.uint8) if len(b) else np.zeros(1, dtype=np.uint8)
+    return int(lib().oracle_levenshtein(_ptr(aa), len(a), _ptr(bb), len(b)))
 
 
 @dataclass
@@ -280,6 +296,8 @@ def search(text_with_dollar, sa, chunks: Sequence[Tuple[int, int]], settings: Se
     ctr = np.zeros(6, dtype=np.uint64)
     h = lib().oracle_search(_ptr(t), len(t), _ptr(sa), _ptr(ch), len(ch), C.byref(settings), post_mask, threads,
                             _ptr(secs), _ptr(ctr))
+    if not h:
+        raise RefPanic("the reference panics on this input (ComputeScore)")
     try:
         fam = _copy_result(h)
     finally:
@@ -299,7 +317,8 @@ def post_steps(fam: Families, text_with_dollar, post_mask: int) -> Families:
     flags = np.ascontiguousarray(fam.flags, dtype=np.uint8)
     h = lib().oracle_result_from_arrays(_ptr(off), len(off) - 1, _ptr(fields), _ptr(ident), _ptr(flags))
     try:
-        lib().oracle_result_post(h, _ptr(t), post_mask)
+        if lib().oracle_result_post(h, _ptr(t), len(t), post_mask) != 0:
+            raise RefPanic("the reference panics on this input (ComputeScore: '$' under complement, or arm past the strand)")
         return _copy_result(h)
     finally:
         lib().oracle_result_free(h)
@@ -369,5 +388,6 @@ def run_files(files: Sequence[str], settings: Settings, threads: int = 1) -> str
     """The whole reference pipeline on FASTA files -> JSON text (bin/asgart.rs:731-822 + exporters.rs:12-25)."""
     prep = Prepared.from_files(files, bool(settings.skip_masked))
     sa = best_suffix_array(prep.strand)
-    out = search(prep.strand, sa, prep.chunks, settings, POST_ALL, threads)
+    mask = POST_ALL | (POST_COMPUTE_SCORE if settings.compute_score else 0)   # bin/asgart.rs:744-746
+    out = search(prep.strand, sa, prep.chunks, settings, mask, threads)
     return prep.to_json(settings, out.families)

@@ -36,6 +36,7 @@
 #include <mutex>
 #include <numeric>
 #include <sstream>
+#include <stdexcept>
 #include <string>
 #include <thread>
 #include <unordered_map>
@@ -489,6 +490,46 @@ Family reduce_overlap(const Family& result) {  // :515-562
 void step_reduce_overlap(std::vector<Family>& fams) {  // :67-79
     for (Family& f : fams) f = reduce_overlap(f);
 }
+// structs.rs:28-34 — complement() of structs.rs: panics on anything outside the TR table (so on '$')
+struct RefPanic : std::runtime_error { using std::runtime_error::runtime_error; };
+uint8_t complement_strict(uint8_t n) {
+    switch (n) {
+        case 'A': return 'T'; case 'T': return 'A'; case 'G': return 'C'; case 'C': return 'G'; case 'N': return 'N';
+        case 'a': return 't'; case 't': return 'a'; case 'g': return 'c'; case 'c': return 'g'; case 'n': return 'n';
+        default: throw RefPanic("Unknown nucleotide");
+    }
+}
+// bio::alignment::distance::levenshtein (crate bio "*", Cargo.toml:13; source not on disk): the unit-cost global edit
+// distance. Restated as the textbook two-row dynamic programme.
+uint32_t levenshtein_dp(const std::vector<uint8_t>& a, const std::vector<uint8_t>& b) {
+    std::vector<uint32_t> prev(b.size() + 1), cur(b.size() + 1);
+    for (size_t j = 0; j <= b.size(); ++j) prev[j] = uint32_t(j);
+    for (size_t i = 1; i <= a.size(); ++i) {
+        cur[0] = uint32_t(i);
+        for (size_t j = 1; j <= b.size(); ++j) {
+            uint32_t sub = prev[j - 1] + (a[i - 1] != b[j - 1] ? 1u : 0u);
+            cur[j] = std::min(sub, std::min(prev[j], cur[j - 1]) + 1u);
+        }
+        prev.swap(cur);
+    }
+    return prev[b.size()];
+}
+// structs.rs:439-452 ProtoSD::levenshtein: inclusive ranges, reverse THEN complement of the right arm, f64 arithmetic
+double sd_levenshtein(const ProtoSD& sd, const uint8_t* strand, usize strand_len) {
+    if (sd.left + sd.left_length >= strand_len || sd.right + sd.right_length >= strand_len)
+        throw RefPanic("range end index out of range for slice");
+    std::vector<uint8_t> left_arm(strand + sd.left, strand + sd.left + sd.left_length + 1);
+    std::vector<uint8_t> right_arm(strand + sd.right, strand + sd.right + sd.right_length + 1);
+    if (sd.reversed) std::reverse(right_arm.begin(), right_arm.end());
+    if (sd.complemented)
+        for (auto& c : right_arm) c = complement_strict(c);
+    double dist = double(levenshtein_dp(left_arm, right_arm));
+    return 100.0 * (1.0 - dist / double(std::max(sd.left_length, sd.right_length)));
+}
+void step_compute_score(std::vector<Family>& fams, const uint8_t* strand, usize strand_len) {  // bin/asgart.rs:98-111
+    for (Family& f : fams)
+        for (ProtoSD& sd : f) sd.identity = float(sd_levenshtein(sd, strand, strand_len));
+}
 void step_sort(std::vector<Family>& fams) {  // :53-65 (sort_by is stable)
     for (Family& f : fams)
         std::stable_sort(f.begin(), f.end(), [](const ProtoSD& a, const ProtoSD& b) { return a.left < b.left; });
@@ -761,6 +802,7 @@ struct oracle_settings {
     uint64_t min_duplication_length;
     uint64_t max_cardinality;
     uint32_t has_trim;
+    uint32_t compute_score;   // --compute-score (structs.rs:57); occupies former padding
     uint64_t trim_a, trim_b;
 };
 
@@ -831,6 +873,9 @@ void* oracle_search(const uint8_t* T, int64_t n1, const int64_t* SA, const uint6
     if (post_mask & 1) step_filter_ns(r->fams, T);
     if (post_mask & 2) step_reorder(r->fams);
     if (post_mask & 4) step_reduce_overlap(r->fams);
+    if (post_mask & 16) {   // ComputeScore sits between ReduceOverlap and Sort (bin/asgart.rs:744-747)
+        try { step_compute_score(r->fams, T, usize(n1)); } catch (const RefPanic&) { delete r; return nullptr; }
+    }
     if (post_mask & 8) step_sort(r->fams);
     auto t1 = std::chrono::steady_clock::now();
     if (phase_seconds) {
@@ -850,12 +895,21 @@ void* oracle_result_from_arrays(const int64_t* fam_offsets, int64_t n_fam, const
     r->fams = from_arrays(fam_offsets, n_fam, fields, identity, flags);
     return r;
 }
-void oracle_result_post(void* h, const uint8_t* T, int post_mask) {
+// returns -1 where the reference panics (ComputeScore on an arm that ends on '$' under -C, or past the strand)
+int oracle_result_post(void* h, const uint8_t* T, int64_t n1, int post_mask) {
     Result* r = static_cast<Result*>(h);
     if (post_mask & 1) step_filter_ns(r->fams, T);
     if (post_mask & 2) step_reorder(r->fams);
     if (post_mask & 4) step_reduce_overlap(r->fams);
+    if (post_mask & 16) {
+        try { step_compute_score(r->fams, T, usize(n1)); } catch (const RefPanic&) { return -1; }
+    }
     if (post_mask & 8) step_sort(r->fams);
+    return 0;
+}
+// plain edit distance of two byte strings (for pinning the GPU kernel on arbitrary pairs)
+uint32_t oracle_levenshtein(const uint8_t* a, int64_t na, const uint8_t* b, int64_t nb) {
+    return levenshtein_dp(std::vector<uint8_t>(a, a + na), std::vector<uint8_t>(b, b + nb));
 }
 int64_t oracle_result_n_families(void* h) { return int64_t(static_cast<Result*>(h)->fams.size()); }
 int64_t oracle_result_n_sds(void* h) {

@@ -18,7 +18,7 @@ def main():
     device = int(sys.argv[4]) if len(sys.argv) > 4 else 0
     flags = {1: dict(), 2: dict(reverse=True, complement=True, skip_masked=True), 3: dict(reverse=True, complement=True),
              4: dict(reverse=True, complement=True), 0: dict()}[config]
-    st = ab.RunSettings(**flags)
+    st = ab.RunSettings(compute_score=bool(os.environ.get("QB_SCORE")), **flags)   # QB_SCORE=1: with --compute-score
     t0 = time.time()
     g, fr = ab.synth_genome(config, scale_n=scale_n)
     prep = ab.Prepared.from_memory(ab.normalise(g, st.skip_masked), fr)
