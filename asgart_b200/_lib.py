@@ -62,6 +62,7 @@ class Stats(C.Structure):
                                      "sa_index_bits", "h2d_bytes", "d2h_bytes")]
         + [("ms_sa_scatter_main", C.c_double), ("launches_sa_scatter_main", C.c_uint64), ("bytes_sa_scatter_main", C.c_uint64)]
         + [("ms_score", C.c_double), ("score_cells", C.c_uint64), ("score_pairs", C.c_uint64)]
+        + [("ms_ingest", C.c_double), ("ingest_bytes", C.c_uint64), ("ingest_records", C.c_uint64)]
     )
 
     def as_dict(self):
@@ -85,6 +86,8 @@ SYMBOLS = [
     "asgart_b200_out_filename", "asgart_b200_run_files", "asgart_b200_synth_length", "asgart_b200_synth_fill",
     "asgart_b200_synth_fragments",
     "asgart_b200_build_index_group", "asgart_b200_dist_unique_id", "asgart_b200_ctx_dist_init", "asgart_b200_ctx_dist_shutdown",
+    "asgart_b200_ctx_ingest_begin", "asgart_b200_ctx_ingest_fasta", "asgart_b200_ctx_ingest_file",
+    "asgart_b200_ctx_ingest_finish", "asgart_b200_ctx_download_strand",
 ]
 
 _lib = None
@@ -116,6 +119,11 @@ def load() -> C.CDLL:
         "asgart_b200_dist_unique_id": (i32, [vp, i64]),
         "asgart_b200_ctx_dist_init": (i32, [vp, i32, i32, vp, i64]),
         "asgart_b200_ctx_dist_shutdown": (i32, [vp]),
+        "asgart_b200_ctx_ingest_begin": (i32, [vp]),
+        "asgart_b200_ctx_ingest_fasta": (i32, [vp, vp, i64, i32]),
+        "asgart_b200_ctx_ingest_file": (i32, [vp, C.c_char_p, i32]),
+        "asgart_b200_ctx_ingest_finish": (i32, [vp, C.c_char_p, C.POINTER(vp)]),
+        "asgart_b200_ctx_download_strand": (i32, [vp, vp, i64]),
         "asgart_b200_ctx_upload_sa": (i32, [vp, vp]),
         "asgart_b200_ctx_download_sa": (i32, [vp, vp]),
         "asgart_b200_ctx_check_sa": (i32, [vp, vp]),

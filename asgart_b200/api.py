@@ -167,6 +167,32 @@ class Context:
         self.n1 = n1
         self._check(self.L.asgart_b200_ctx_load_strand(self.h, C.c_void_p(ptr), n1))
 
+    # -- GPU-side FASTA ingest (prepare_data on the device, src/bin/asgart.rs:273-471)
+    def ingest(self, files: Sequence, skip_masked: bool = False, names: Optional[Sequence[str]] = None) -> "Prepared":
+        """read_fasta + find_chunks_to_process + '$' for FASTA files on the device. `files`: paths (str) or the files'
+        raw bytes (bytes / uint8 arrays; `names` then gives the file names for the JSON). The context ends up as after
+        load_strand; the returned Prepared has the fragment map and the chunks but no host copy of the strand."""
+        self._check(self.L.asgart_b200_ctx_ingest_begin(self.h))
+        shown = []
+        for i, f in enumerate(files):
+            if isinstance(f, str):
+                self._check(self.L.asgart_b200_ctx_ingest_file(self.h, f.encode(), int(skip_masked)))
+                shown.append(f)
+            else:
+                b = np.frombuffer(f, dtype=np.uint8) if isinstance(f, (bytes, bytearray)) else np.ascontiguousarray(f, dtype=np.uint8)
+                self._check(self.L.asgart_b200_ctx_ingest_fasta(self.h, _ptr(b) if len(b) else None, len(b), int(skip_masked)))
+                shown.append(names[i] if names else f"mem{i}.fa")
+        h = C.c_void_p()
+        self._check(self.L.asgart_b200_ctx_ingest_finish(self.h, "\n".join(shown).encode(), C.byref(h)))
+        prep = Prepared(h.value)
+        self.n1 = prep.n1
+        return prep
+
+    def download_strand(self) -> np.ndarray:
+        out = np.empty(self.n1, dtype=np.uint8)
+        self._check(self.L.asgart_b200_ctx_download_strand(self.h, _ptr(out), len(out)))
+        return out
+
     def set_index_bits(self, bits: int):
         self._check(self.L.asgart_b200_ctx_set_index_bits(self.h, bits))
 
@@ -324,7 +350,9 @@ class Prepared:
         self.h = C.c_void_p(handle)
         n1 = C.c_int64()
         p = self.L.asgart_b200_prepared_strand(self.h, C.byref(n1))
-        self.strand = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(n1.value,))  # view, owned by handle
+        self.n1 = n1.value
+        # view owned by the handle; None when the strand lives only on the device (Context.ingest)
+        self.strand = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(n1.value,)) if p else None
         nc = C.c_int64()
         cp = self.L.asgart_b200_prepared_chunks(self.h, C.byref(nc))
         ch = np.ctypeslib.as_array(C.cast(cp, C.POINTER(C.c_uint64)), shape=(nc.value, 2)) if nc.value else np.zeros((0, 2), np.uint64)

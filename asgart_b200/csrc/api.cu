@@ -7,9 +7,15 @@
 #include <thread>
 #include <vector>
 
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
 #include "automaton.cuh"
 #include "common.cuh"
 #include "dist_group.cuh"
+#include "fasta_ingest.cuh"
+#include "host_internal.h"
 #include "sa_build.cuh"
 #include "levenshtein.cuh"
 #include "search.cuh"
@@ -79,6 +85,11 @@ struct asgart_b200_ctx {
     void* rank_slice = nullptr;
     size_t rank_slice_bytes = 0;
     std::vector<void*> retired_slices;
+    // GPU-side FASTA ingest: one piece per file between ingest_begin and ingest_finish; pinned staging for ingest_file
+    bool ingesting = false;
+    std::vector<IngestPiece> pieces;
+    u8* stage[2] = {nullptr, nullptr};
+    cudaEvent_t stage_ev[2] = {nullptr, nullptr};
 };
 
 namespace ab200 { namespace detail {
@@ -127,6 +138,33 @@ void pack_image(asgart_b200_ctx* ctx, int mode, DevBuf<u64>& out, u32* d_err) {
     pack_text_kernel<<<unsigned(ceil_div(words, 256)), 256, 0, ctx->stream>>>(ctx->d_text.p, ctx->n1, mode, out.p, words, d_err);
     KERNEL_CHECK();
     count_launch();
+}
+
+// validation + 4-bit packing of the strand in ctx->d_text (n1 bytes): the tail of load_strand and of ingest_finish
+int32_t pack_loaded_strand(asgart_b200_ctx* ctx) {
+    EventTimer tp(ctx->stream);
+    tp.start();
+    DevBuf<u32> d_err(1, ctx->stream);
+    d_err.zero();
+    pack_image(ctx, PACK_DIRECT, ctx->d_pt, d_err.p);
+    tp.stop();
+    u32 h_err = 0;
+    CUDA_CHECK(cudaMemcpyAsync(&h_err, d_err.p, sizeof h_err, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    ctx->st.ms_pack += tp.ms();
+    if (h_err) return fail(ctx, ASGART_B200_EINVAL, "strand is not normalised: expected bytes in {A,C,G,N,T} followed by one '$'");
+    ctx->have_strand = true;
+    return ASGART_B200_OK;
+}
+
+void ingest_piece(asgart_b200_ctx* ctx, const u8* d_file, u64 n, bool skip_masked, IngestPiece& piece) {
+    EventTimer t(ctx->stream);
+    t.start();
+    ingest_fasta_device(d_file, n, skip_masked, piece, ctx->stream);
+    t.stop();
+    ctx->st.ms_ingest += t.ms();
+    ctx->st.ingest_bytes += n;
+    ctx->st.ingest_records += piece.rec_off.size();
 }
 
 template <typename IdxT> struct IxOf;
@@ -744,6 +782,11 @@ void asgart_b200_ctx_destroy(asgart_b200_ctx* ctx) {
     ctx->group = nullptr;
     if (ctx->rank_slice) cudaFree(ctx->rank_slice);
     for (void* p : ctx->retired_slices) cudaFree(p);
+    ctx->pieces.clear();
+    for (int i = 0; i < 2; ++i) {
+        if (ctx->stage[i]) cudaFreeHost(ctx->stage[i]);
+        if (ctx->stage_ev[i]) cudaEventDestroy(ctx->stage_ev[i]);
+    }
     ctx->d_text.release(); ctx->d_pt.release(); ctx->d_pn.release(); ctx->shard_blob.release();
     ctx->ix32 = Index32();
     ctx->ix64 = Index64();
@@ -766,24 +809,166 @@ int32_t asgart_b200_ctx_load_strand(asgart_b200_ctx* ctx, const uint8_t* T, int6
         ctx->have_strand = ctx->have_index = false;
         ctx->pn_mode = -1;
         ctx->n1 = u64(n_plus_1);
-        EventTimer th(ctx->stream), tp(ctx->stream);
+        EventTimer th(ctx->stream);
         th.start();
         ctx->d_text.alloc(ctx->n1, ctx->stream);
         CUDA_CHECK(cudaMemcpyAsync(ctx->d_text.p, T, ctx->n1, cudaMemcpyHostToDevice, ctx->stream));
         th.stop();
-        tp.start();
-        DevBuf<u32> d_err(1, ctx->stream);
-        d_err.zero();
-        pack_image(ctx, PACK_DIRECT, ctx->d_pt, d_err.p);
-        tp.stop();
-        u32 h_err = 0;
-        CUDA_CHECK(cudaMemcpyAsync(&h_err, d_err.p, sizeof h_err, cudaMemcpyDeviceToHost, ctx->stream));
-        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        const int32_t rc = pack_loaded_strand(ctx);
         ctx->st.ms_h2d += th.ms();
-        ctx->st.ms_pack += tp.ms();
         ctx->st.h2d_bytes += ctx->n1;
-        if (h_err) return fail(ctx, ASGART_B200_EINVAL, "strand is not normalised: expected bytes in {A,C,G,N,T} followed by one '$'");
-        ctx->have_strand = true;
+        return rc;
+    });
+}
+
+// ---- GPU-side FASTA ingest (fasta_ingest.cuh) -----------------------------------------------------------------
+int32_t asgart_b200_ctx_ingest_begin(asgart_b200_ctx* ctx) {
+    return guarded(ctx, [&]() -> int32_t {
+        ctx->have_strand = ctx->have_index = false;
+        ctx->pn_mode = -1;
+        ctx->pieces.clear();
+        ctx->ingesting = true;
+        return ASGART_B200_OK;
+    });
+}
+
+int32_t asgart_b200_ctx_ingest_fasta(asgart_b200_ctx* ctx, const uint8_t* bytes, int64_t n_bytes, int32_t skip_masked) {
+    return guarded(ctx, [&]() -> int32_t {
+        if (!ctx->ingesting) return fail(ctx, ASGART_B200_ESTATE, "ingest_fasta before ingest_begin");
+        if ((!bytes && n_bytes > 0) || n_bytes < 0) return fail(ctx, ASGART_B200_EINVAL, "null bytes or negative size");
+        const u64 n = u64(n_bytes);
+        u64 h = 0;
+        while (h < n && bytes[h] == '\n') ++h;
+        if (h < n && bytes[h] != '>') return fail(ctx, ASGART_B200_EINVAL, "Unable to parse FASTA: the first non-empty line is not a header");
+        DevBuf<u8> d_file(n, ctx->stream);
+        EventTimer th(ctx->stream);
+        th.start();
+        if (n) CUDA_CHECK(cudaMemcpyAsync(d_file.p, bytes, n, cudaMemcpyHostToDevice, ctx->stream));
+        th.stop();
+        ctx->pieces.emplace_back();
+        IngestPiece& piece = ctx->pieces.back();
+        ingest_piece(ctx, d_file.p, n, skip_masked != 0, piece);
+        for (u64 off : piece.rec_off) {
+            u64 e = off + 1;
+            while (e < n && !fa_space(bytes[e])) ++e;
+            piece.names.emplace_back(reinterpret_cast<const char*>(bytes) + off + 1, size_t(e - off - 1));
+        }
+        ctx->st.ms_h2d += th.ms();
+        ctx->st.h2d_bytes += n;
+        return ASGART_B200_OK;
+    });
+}
+
+int32_t asgart_b200_ctx_ingest_file(asgart_b200_ctx* ctx, const char* path, int32_t skip_masked) {
+    return guarded(ctx, [&]() -> int32_t {
+        if (!ctx->ingesting) return fail(ctx, ASGART_B200_ESTATE, "ingest_file before ingest_begin");
+        if (!path) return fail(ctx, ASGART_B200_EINVAL, "null path");
+        struct FdGuard { int fd; ~FdGuard() { if (fd >= 0) close(fd); } } f{open(path, O_RDONLY)};
+        struct stat sb;
+        if (f.fd < 0 || fstat(f.fd, &sb) != 0 || !S_ISREG(sb.st_mode)) {
+            ctx->err = std::string("Unable to read FASTA file `") + path + "`";
+            return ASGART_B200_EINVAL;
+        }
+        const u64 n = u64(sb.st_size);
+        constexpr size_t kStage = size_t(32) << 20;
+        for (int i = 0; i < 2; ++i) {
+            if (!ctx->stage[i]) CUDA_CHECK(cudaHostAlloc(reinterpret_cast<void**>(&ctx->stage[i]), kStage, cudaHostAllocDefault));
+            if (!ctx->stage_ev[i]) CUDA_CHECK(cudaEventCreateWithFlags(&ctx->stage_ev[i], cudaEventDisableTiming));
+        }
+        DevBuf<u8> d_file(n, ctx->stream);
+        EventTimer th(ctx->stream);
+        th.start();
+        bool seen_first = false, bad_first = false;
+        u64 done = 0;
+        for (int slot = 0; done < n; slot ^= 1) {
+            CUDA_CHECK(cudaEventSynchronize(ctx->stage_ev[slot]));   // the copy that last used this buffer has finished
+            const size_t want = size_t(std::min<u64>(kStage, n - done));
+            size_t got = 0;
+            while (got < want) {
+                const ssize_t r = pread(f.fd, ctx->stage[slot] + got, want - got, off_t(done + got));
+                if (r <= 0) { ctx->err = std::string("Unable to read FASTA file `") + path + "`"; return ASGART_B200_EINVAL; }
+                got += size_t(r);
+            }
+            for (size_t i = 0; i < got && !seen_first; ++i)
+                if (ctx->stage[slot][i] != '\n') { seen_first = true; bad_first = ctx->stage[slot][i] != '>'; }
+            if (bad_first) break;
+            CUDA_CHECK(cudaMemcpyAsync(d_file.p + done, ctx->stage[slot], got, cudaMemcpyHostToDevice, ctx->stream));
+            CUDA_CHECK(cudaEventRecord(ctx->stage_ev[slot], ctx->stream));
+            done += got;
+        }
+        th.stop();
+        if (bad_first) {
+            CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+            ctx->err = std::string("Unable to parse `") + path + "`";
+            return ASGART_B200_EINVAL;
+        }
+        ctx->pieces.emplace_back();
+        IngestPiece& piece = ctx->pieces.back();
+        ingest_piece(ctx, d_file.p, n, skip_masked != 0, piece);
+        for (u64 off : piece.rec_off) {     // record ids: the few bytes after each '>' straight from the file
+            std::string name;
+            char buf[256];
+            bool end = false;
+            for (u64 at = off + 1; !end && at < n;) {
+                const ssize_t r = pread(f.fd, buf, sizeof buf, off_t(at));
+                if (r <= 0) break;
+                for (ssize_t i = 0; i < r; ++i) {
+                    if (fa_space(u8(buf[i]))) { end = true; break; }
+                    name.push_back(buf[i]);
+                }
+                at += u64(r);
+            }
+            piece.names.push_back(std::move(name));
+        }
+        ctx->st.ms_h2d += th.ms();
+        ctx->st.h2d_bytes += n;
+        return ASGART_B200_OK;
+    });
+}
+
+int32_t asgart_b200_ctx_ingest_finish(asgart_b200_ctx* ctx, const char* file_names, asgart_b200_prepared** out) {
+    return guarded(ctx, [&]() -> int32_t {
+        if (!ctx->ingesting) return fail(ctx, ASGART_B200_ESTATE, "ingest_finish before ingest_begin");
+        if (!out) return fail(ctx, ASGART_B200_EINVAL, "null out");
+        *out = nullptr;
+        u64 total = 0;
+        for (const IngestPiece& p : ctx->pieces) total += p.kept;
+        ctx->n1 = total + 1;
+        ctx->d_text.alloc(ctx->n1, ctx->stream);
+        std::vector<std::string> names;
+        std::vector<u64> pos, len;
+        std::vector<asgart_b200_chunk> chunks;
+        u64 off = 0;
+        for (IngestPiece& p : ctx->pieces) {    // src/bin/asgart.rs:375-395: files concatenated with a running offset
+            if (p.kept) CUDA_CHECK(cudaMemcpyAsync(ctx->d_text.p + off, p.strand.p, p.kept, cudaMemcpyDeviceToDevice, ctx->stream));
+            ingest_chunks(p, off, chunks, pos, len);
+            for (std::string& s : p.names) names.push_back(std::move(s));
+            off += p.kept;
+        }
+        CUDA_CHECK(cudaMemsetAsync(ctx->d_text.p + total, '$', 1, ctx->stream));   // src/bin/asgart.rs:430
+        const int32_t rc = pack_loaded_strand(ctx);
+        ctx->pieces.clear();
+        ctx->ingesting = false;
+        if (rc) return rc;
+        std::string joined;                     // src/bin/asgart.rs:466
+        for (const char* c = file_names ? file_names : ""; *c;) {
+            const char* e = strchr(c, '\n');
+            const size_t l = e ? size_t(e - c) : strlen(c);
+            if (l) { if (!joined.empty()) joined += ", "; joined.append(c, l); }
+            c += l + (e ? 1 : 0);
+        }
+        *out = ab200_prepared_device_only(joined, total, names, pos, len, chunks);
+        return ASGART_B200_OK;
+    });
+}
+
+int32_t asgart_b200_ctx_download_strand(asgart_b200_ctx* ctx, uint8_t* out, int64_t cap) {
+    return guarded(ctx, [&]() -> int32_t {
+        if (!ctx->have_strand) return fail(ctx, ASGART_B200_ESTATE, "download_strand without a strand");
+        if (!out || cap < int64_t(ctx->n1)) return fail(ctx, ASGART_B200_EINVAL, "null out or cap < n + 1");
+        CUDA_CHECK(cudaMemcpyAsync(out, ctx->d_text.p, ctx->n1, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        ctx->st.d2h_bytes += ctx->n1;
         return ASGART_B200_OK;
     });
 }

@@ -18,6 +18,7 @@
 #include <vector>
 
 #include "../../include/asgart_b200.h"
+#include "host_internal.h"
 
 namespace {
 
@@ -30,7 +31,8 @@ struct Fragment {
 
 struct asgart_b200_prepared {
     std::string file_names;
-    std::vector<uint8_t> data;  // incl. '$'
+    std::vector<uint8_t> data;  // incl. '$'; empty when the strand lives only on the device (GPU-side ingest)
+    uint64_t n_plus_1 = 0;
     std::vector<Fragment> map;
     std::vector<asgart_b200_chunk> chunks;
 };
@@ -419,6 +421,17 @@ void generate(const SynthSpec& sp, std::vector<uint8_t>& g, int threads, const s
 }  // namespace
 
 // ================================================================================================ C ABI
+asgart_b200_prepared* ab200_prepared_device_only(const std::string& file_names, uint64_t n, const std::vector<std::string>& names,
+                                                 const std::vector<uint64_t>& pos, const std::vector<uint64_t>& len,
+                                                 const std::vector<asgart_b200_chunk>& chunks) {
+    auto* p = new asgart_b200_prepared();
+    p->file_names = file_names;
+    p->n_plus_1 = n + 1;
+    for (size_t i = 0; i < names.size(); ++i) p->map.push_back(Fragment{names[i], pos[i], len[i]});
+    p->chunks = chunks;
+    return p;
+}
+
 extern "C" {
 
 asgart_b200_prepared* asgart_b200_prepare_files(const char* files, int32_t skip_masked, const char** err) {
@@ -454,8 +467,8 @@ asgart_b200_prepared* asgart_b200_prepare_memory(const char* file_names, const u
 }
 
 const uint8_t* asgart_b200_prepared_strand(const asgart_b200_prepared* p, int64_t* n_plus_1) {
-    if (n_plus_1) *n_plus_1 = int64_t(p->data.size());
-    return p->data.data();
+    if (n_plus_1) *n_plus_1 = int64_t(p->data.empty() ? p->n_plus_1 : p->data.size());
+    return p->data.empty() ? nullptr : p->data.data();
 }
 const asgart_b200_chunk* asgart_b200_prepared_chunks(const asgart_b200_prepared* p, int64_t* n_chunks) {
     if (n_chunks) *n_chunks = int64_t(p->chunks.size());
@@ -575,28 +588,35 @@ char* asgart_b200_out_filename(const char* files, const char* prefix, const char
     return r;
 }
 
-// bin/asgart.rs:731-822: prepare_data -> SearchDuplications -> FilterNs -> ReOrder -> ReduceOverlap -> Sort -> JSON
+// bin/asgart.rs:731-822: prepare_data -> SearchDuplications -> FilterNs -> ReOrder -> ReduceOverlap -> Sort -> JSON.
+// prepare_data runs on the device too (GPU-side FASTA ingest): the files' bytes go to HBM as they are read.
 char* asgart_b200_run_files(const char* files, const asgart_b200_settings* st, int32_t device, const char** err) {
     static thread_local std::string msg;
     if (err) *err = nullptr;
     auto failf = [&](const std::string& m) -> char* { msg = m; if (err) *err = msg.c_str(); return nullptr; };
-    const char* perr = nullptr;
-    asgart_b200_prepared* p = asgart_b200_prepare_files(files, int32_t(st->skip_masked), &perr);
-    if (!p) return failf(perr ? perr : "prepare_data failed");
+    const std::vector<std::string> fl = split_lines(files);
+    if (fl.empty()) return failf("no input files");
     asgart_b200_ctx* ctx = nullptr;
     int rc = asgart_b200_ctx_create(device, &ctx);
-    if (rc) { asgart_b200_prepared_free(p); return failf("no usable CUDA device (code " + std::to_string(rc) + "); this build has no CPU path"); }
+    if (rc) return failf("no usable CUDA device (code " + std::to_string(rc) + "); this build has no CPU path");
+    asgart_b200_prepared* p = nullptr;
     asgart_b200_result* res = nullptr;
     char* js = nullptr;
-    rc = asgart_b200_ctx_load_strand(ctx, p->data.data(), int64_t(p->data.size()));
-    if (!rc) rc = asgart_b200_ctx_build_index(ctx);
-    if (!rc) rc = asgart_b200_ctx_search(ctx, p->chunks.data(), int64_t(p->chunks.size()), st,
-                                        ASGART_B200_POST_ALL | (st->compute_score ? ASGART_B200_POST_COMPUTE_SCORE : 0u), &res);
-    if (rc) failf(std::string("device pipeline failed: ") + asgart_b200_ctx_last_error(ctx));
-    else js = asgart_b200_to_json(p, st, asgart_b200_result_family_offsets(res), asgart_b200_result_n_families(res), asgart_b200_result_sds(res));
+    rc = asgart_b200_ctx_ingest_begin(ctx);
+    for (size_t i = 0; !rc && i < fl.size(); ++i) rc = asgart_b200_ctx_ingest_file(ctx, fl[i].c_str(), int32_t(st->skip_masked));
+    if (!rc) rc = asgart_b200_ctx_ingest_finish(ctx, files, &p);
+    if (rc) {
+        failf(asgart_b200_ctx_last_error(ctx));
+    } else {
+        rc = asgart_b200_ctx_build_index(ctx);
+        if (!rc) rc = asgart_b200_ctx_search(ctx, p->chunks.data(), int64_t(p->chunks.size()), st,
+                                            ASGART_B200_POST_ALL | (st->compute_score ? ASGART_B200_POST_COMPUTE_SCORE : 0u), &res);
+        if (rc) failf(std::string("device pipeline failed: ") + asgart_b200_ctx_last_error(ctx));
+        else js = asgart_b200_to_json(p, st, asgart_b200_result_family_offsets(res), asgart_b200_result_n_families(res), asgart_b200_result_sds(res));
+    }
     asgart_b200_result_free(res);
     asgart_b200_ctx_destroy(ctx);
-    asgart_b200_prepared_free(p);
+    if (p) asgart_b200_prepared_free(p);
     return js;
 }
 

@@ -213,6 +213,9 @@ typedef struct asgart_b200_stats {
     /* ComputeScore: device ms, DP cells (sum of arm-length products) and duplicons scored */
     double ms_score;
     uint64_t score_cells, score_pairs;
+    /* FASTA ingest: device ms of the scan passes (the file's H2D copy is in ms_h2d / h2d_bytes), file bytes, records */
+    double ms_ingest;
+    uint64_t ingest_bytes, ingest_records;
 } asgart_b200_stats;
 ASGART_B200_API int32_t asgart_b200_ctx_stats(const asgart_b200_ctx *ctx, asgart_b200_stats *out);
 ASGART_B200_API void asgart_b200_ctx_reset_stats(asgart_b200_ctx *ctx);
@@ -246,6 +249,28 @@ ASGART_B200_API char *asgart_b200_out_filename(const char *files, const char *pr
 /* whole `asgart FILES...` run on one device: prepare_data -> index -> search -> post-steps -> JSON text (malloc'd) */
 ASGART_B200_API char *asgart_b200_run_files(const char *files, const asgart_b200_settings *settings, int32_t device,
                                             const char **err);
+
+/* ---- GPU-side FASTA ingest ----------------------------------------------------------------
+ * read_fasta + find_chunks_to_process of prepare_data (src/bin/asgart.rs:278-366) on the device, for the raw bytes of
+ * FASTA / multiFASTA files: record splitting with the semantics of the bio reader the reference calls (:282-290; id =
+ * header up to the first white space, sequence lines joined after `trim_end`), per-base normalisation (:291-301),
+ * fragment map (:303-308), chunks split at N-runs > 5000 per fragment (:317-366, :381-387), files concatenated with a
+ * running offset (:375-395), '$' appended (:430). The strand never exists on the host: ingest_finish leaves the context
+ * exactly as ctx_load_strand would (packed, ready for ctx_build_index) and returns the prepare_data result without the
+ * strand bytes (asgart_b200_prepared_strand gives NULL and the length; ctx_download_strand reads it back for tests).
+ *   ingest_begin -> ingest_fasta (bytes in host memory) | ingest_file (path; read through two pinned staging buffers so
+ *   disk reads overlap the copies) once per file, in the order of the command line -> ingest_finish.
+ * A file whose first non-empty line is not a header is refused with ASGART_B200_EINVAL ("Unable to parse", as the
+ * reference's reader does); an unreadable path with ASGART_B200_EINVAL ("Unable to read FASTA file"). */
+ASGART_B200_API int32_t asgart_b200_ctx_ingest_begin(asgart_b200_ctx *ctx);
+ASGART_B200_API int32_t asgart_b200_ctx_ingest_fasta(asgart_b200_ctx *ctx, const uint8_t *bytes, int64_t n_bytes,
+                                                     int32_t skip_masked);
+ASGART_B200_API int32_t asgart_b200_ctx_ingest_file(asgart_b200_ctx *ctx, const char *path, int32_t skip_masked);
+/* file_names: '\n'-separated paths as given on the command line (for strand.name of the JSON, src/bin/asgart.rs:466) */
+ASGART_B200_API int32_t asgart_b200_ctx_ingest_finish(asgart_b200_ctx *ctx, const char *file_names,
+                                                      asgart_b200_prepared **out);
+/* the strand held by the context (n+1 bytes incl. '$') back to host memory; cap >= n+1 */
+ASGART_B200_API int32_t asgart_b200_ctx_download_strand(asgart_b200_ctx *ctx, uint8_t *out, int64_t cap);
 
 /* ---- deterministic synthetic genomes (bench/test input; DESIGN.md "Synthetic inputs") ---------------------- */
 /* Fills out[0..n) (no '$') with the config's sequence (upper/lower case ACGT and N). config: 1..5 = BASELINE.json

@@ -1,0 +1,150 @@
+"""GPU-side FASTA ingest (fasta_ingest.cuh) against the oracle's restatement of prepare_data
+(src/bin/asgart.rs:273-471): strand bytes, fragment map and chunks_to_process must be identical, for files and for
+in-memory buffers, and the context must be left exactly as load_strand leaves it."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import asgart_b200 as ab
+import oracle
+from tests.test_gpu_parity import _osettings
+
+pytestmark = pytest.mark.gpu
+
+
+def _fasta(records, width=60, eol="\n", final_eol=True) -> bytes:
+    out = []
+    for name, seq in records:
+        out.append(">" + name)
+        for i in range(0, len(seq), width):
+            out.append(seq[i:i + width])
+    s = eol.join(out)
+    return (s + (eol if final_eol else "")).encode()
+
+
+def _rand_seq(rng, n, alphabet="ACGT"):
+    return "".join(rng.choice(list(alphabet), size=n))
+
+
+def _check(tmp_path, blobs, skip_masked, tag="f"):
+    """ingest from paths and from memory; compare with the oracle's prepare_data on the same files"""
+    paths = []
+    for i, b in enumerate(blobs):
+        p = tmp_path / f"{tag}{i}.fa"
+        p.write_bytes(b)
+        paths.append(str(p))
+    want = oracle.Prepared.from_files(paths, skip_masked)
+    with ab.Context(0) as ctx:
+        for files, names in ((paths, None), (blobs, paths)):
+            got = ctx.ingest(files, skip_masked, names=names)
+            assert got.strand is None and got.n1 == len(want.strand)
+            assert np.array_equal(ctx.download_strand(), want.strand)
+            assert got.map == want.map
+            assert got.chunks == want.chunks
+            s = ctx.stats()
+            assert s["ingest_records"] >= len(want.map)
+    return want
+
+
+@pytest.mark.parametrize("skip_masked", [False, True])
+def test_ingest_line_and_record_shapes(tmp_path, skip_masked):
+    rng = np.random.default_rng(7)
+    a = _rand_seq(rng, 1000, "ACGTacgtNnRYKM-*xX")
+    b = _rand_seq(rng, 7321, "ACGTacgt")
+    blobs = [
+        _fasta([("chr1 some description", a), ("chr2", b)]),
+        _fasta([("chr1\tdesc", a), ("chr2", b)], eol="\r\n"),                       # CRLF
+        _fasta([("x", a), ("y", b)], final_eol=False),                              # no newline at the end of the file
+        _fasta([("x", a)], width=10 ** 9),                                          # one-line record
+        b"\n\n>lead empty lines\nACGT\nAC GT  \t\nGG\r\n\n\nTT \n>e1\n>e2 d\n\n>last\nNNNN>AC\n ACGT\nA",   # interior blanks, empty records, '>' inside a line
+        b">only header",
+        b">only header\n",
+        b">\nACGT\n",                                                                 # empty id
+        b"",                                                                          # empty file: no records
+        b"\n\n",
+        b">a\n   \n \t \n>b\n\x0b\x0cAC\x0b\x0c\n",                                  # lines of blanks only; VT / FF
+    ]
+    for i, blob in enumerate(blobs):
+        _check(tmp_path, [blob], skip_masked, tag=f"s{i}_")
+    _check(tmp_path, blobs[:4], skip_masked, tag="multi")                            # several files: running offset
+
+
+def test_ingest_n_runs_and_chunks(tmp_path):
+    rng = np.random.default_rng(8)
+    s = lambda n: _rand_seq(rng, n)   # noqa: E731
+    N = lambda n: "N" * n             # noqa: E731
+    recs = [
+        ("short_and_edge", s(300) + N(5000) + s(700) + N(5001) + s(900) + N(12) + s(10)),
+        ("leading_short", N(100) + s(2000) + N(6000) + N(1) + s(50) + N(40)),
+        ("leading_long", N(7000) + s(3000) + N(9000)),
+        ("ends_with_3000", s(500) + N(3000)),
+        ("starts_with_3000", N(3000) + s(500)),                                      # 6000 across the border: no split
+        ("ends_with_6000", s(500) + N(6000)),
+        ("starts_with_6000", N(6000) + s(500) + "n" * 5500 + s(100)),               # lower-case n: N either way
+        ("all_n_long", N(20000)),
+        ("all_n_short", N(30)),
+        ("empty", ""),
+        ("tail", s(12345)),
+    ]
+    for width in (60, 4096, 10 ** 9):
+        want = _check(tmp_path, [_fasta(recs, width=width)], False, tag=f"n{width}_")
+        assert len(want.chunks) > len(recs)
+    _check(tmp_path, [_fasta(recs[:5]), _fasta(recs[5:])], True, tag="two")
+    # masked stretches become N-runs under -S and split chunks there
+    masked = [("m", s(4000) + s(5200).lower() + s(3000) + s(4999).lower() + s(100))]
+    w0 = _check(tmp_path, [_fasta(masked)], False, tag="m0")
+    w1 = _check(tmp_path, [_fasta(masked)], True, tag="m1")
+    assert len(w0.chunks) == 1 and len(w1.chunks) == 2
+
+
+def test_ingest_errors(tmp_path):
+    bad = tmp_path / "bad.fa"
+    bad.write_bytes(b"ACGT\n>late header\nACGT\n")
+    with ab.Context(0) as ctx:
+        with pytest.raises(ab.AsgartB200Error, match="Unable to parse"):
+            ctx.ingest([str(bad)])
+        with pytest.raises(ab.AsgartB200Error, match="Unable to parse"):
+            ctx.ingest([b"\r\n>x\nAC\n"])
+        with pytest.raises(ab.AsgartB200Error, match="Unable to read FASTA file"):
+            ctx.ingest([str(tmp_path / "missing.fa")])
+        with pytest.raises(ab.AsgartB200Error):
+            ctx.build_index()                                                         # no strand after a failed ingest
+        with pytest.raises(IOError):
+            oracle.Prepared.from_files([str(bad)])
+        ok = ctx.ingest([b">x\nACGTACGTAC\n"])
+        assert ok.map == [("x", 0, 10)] and ok.chunks == [(0, 10)]
+        assert ctx.download_strand().tobytes() == b"ACGTACGTAC$"
+
+
+def test_ingest_then_search_equals_host_prepared_path(tmp_path):
+    """Synthetic C2-shaped genome (soft-masked, N-runs) written as a 60-column FASTA plus a second small file: the
+    ingested context gives the same index, families and JSON as the host-prepared one and as the oracle."""
+    g, fr = ab.synth_genome(2, scale_n=3_000_000)
+    text = g.tobytes().decode()
+    fa = tmp_path / "synthY.fa"
+    fa.write_bytes(_fasta([("synthY desc", text)]))
+    rng = np.random.default_rng(3)
+    fb = tmp_path / "extra.fa"
+    fb.write_bytes(_fasta([("e1", _rand_seq(rng, 70000)), ("e2", text[100000:160000])], width=80))
+    files = [str(fa), str(fb)]
+    for kw in (dict(reverse=True, complement=True, skip_masked=True), dict()):
+        st = ab.RunSettings(**kw)
+        want_prep = oracle.Prepared.from_files(files, st.skip_masked)
+        sa = oracle.best_suffix_array(want_prep.strand)
+        want = oracle.search(want_prep.strand, sa, want_prep.chunks, _osettings(st), oracle.POST_ALL, threads=4)
+        with ab.Context(0) as ctx:
+            prep = ctx.ingest(files, st.skip_masked)
+            assert prep.map == want_prep.map and prep.chunks == want_prep.chunks
+            ctx.build_index()
+            assert np.array_equal(ctx.download_sa(), sa)
+            got = ctx.search(prep.chunks, st, ab.POST_ALL)
+            assert got.as_lists() == want.families.as_lists()
+            assert got.n_families > 0
+            assert prep.to_json(st, got) == want_prep.to_json(_osettings(st), want.families)
+            s = ctx.stats()
+            assert s["ingest_bytes"] == os.path.getsize(fa) + os.path.getsize(fb)
+        js = ab.search_duplications(files, st)                                        # run_files goes through the ingest
+        assert js == oracle.run_files(files, _osettings(st), threads=4)
+        assert json.loads(js)["strand"]["name"] == ", ".join(files)
