@@ -6,17 +6,20 @@
 // and contributes its bytes with the trailing white space cut off (`trim_end`); white space INSIDE a sequence line stays
 // (and becomes 'N' below, exactly as the reference's normalisation treats any byte outside ATGCN).
 //
-// Everything is a flag scan (scan.cuh) over the bytes, so the work does not depend on line lengths (a one-line 250 Mbp
-// record costs what 4 M lines of 60 columns cost):
-//   R   reverse scan, marks: '\n' / non-white byte. A white byte is trailing iff the nearest non-blank event after it is
-//       a newline (or the end of the file)                                                   -> class bit per byte
-//   H   forward scan, marks: header start ('>' as first byte of a line) / '\n'. A byte lies on a header line iff the
-//       latest header start is more recent than the latest newline                            -> keep bit, header bit
-//   K   forward scan, counts: kept bytes / header starts. Output pass: compaction + normalisation of the kept bytes
-//       (src/bin/asgart.rs:291-301) and one (file offset, strand position) pair per record
-//   N   forward scan over the strand, mark: non-N byte. At the last byte of an N-run the mark gives the run's first byte;
-//       runs longer than 5000 (src/bin/asgart.rs:326,336) are appended to a list (there are at most n/5001 of them)
-// Algorithmic bytes: 1 read per file byte and pass (R, H, K) + 1 write per kept byte + 1 read per strand byte (N).
+// Three streaming passes over the file bytes, 32 bytes (two 128-bit loads) per thread, 8 KB per block, so the work does
+// not depend on line lengths (a one-line 250 Mbp record costs what 4 M lines of 60 columns cost). Two one-bit state
+// machines run over the bytes:
+//   header  (forward)   '>' as first byte of a line sets it, '\n' clears it: a byte lies on a header line iff it is set
+//   rest    (backward)  '\n' (or the end of the file) sets it, a non-white byte clears it: a blank byte is trailing white
+//                       space iff it is set
+// For both, a stretch of bytes is summarised by its last (first) event, and "latest event wins" is associative:
+//   pass 1  per 8 KB tile: last header event, first rest event                     -> tiny tile-level scans (scan.cuh)
+//   pass 2  per tile, with the states entering it: kept bytes, header starts, and the state of the N-run counter
+//           (kept bytes since the last kept non-N byte)                             -> one tile-level scan of the triple
+//   pass 3  compaction + normalisation of the kept bytes (src/bin/asgart.rs:291-301) staged in shared memory and written
+//           with 128-bit stores; one (file offset, strand position) pair per record; an N-run longer than 5000
+//           (src/bin/asgart.rs:326,336) is reported by the first non-N base after it (there are at most n/5001 of them)
+// Algorithmic bytes: 3 reads per file byte + 1 write per kept byte.
 #pragma once
 #include <algorithm>
 #include <vector>
@@ -46,116 +49,297 @@ struct IngestPiece {
     std::vector<std::string> names;  // record ids (header up to the first white space), filled by the caller
 };
 
-enum : u8 { FA_KEEP = 1, FA_HEADER = 2 };
+constexpr int kFiThreads = 256;
+constexpr int kFiBytes = 32;
+constexpr int kFiWarps = kFiThreads / 32;
+constexpr u64 kFiTile = u64(kFiThreads) * kFiBytes;
+enum : u32 { FI_NONE = 0, FI_CLR = 1, FI_SET = 2 };
+
+// Tile-level prefixes, all with commutative operators (the generic scans of scan.cuh reduce in strided order):
+//   sums  kept bytes, header starts
+//   max   strand position just after the last kept non-N byte (0: none so far). The N-run counter at any point is
+//         (kept bytes so far) - (that position).
+struct FiSum {
+    u64 kept, headers;
+    FiSum() = default;
+    __host__ __device__ explicit FiSum(int) : kept(0), headers(0) {}
+};
+struct FiSumOp {
+    __device__ __forceinline__ FiSum operator()(const FiSum& x, const FiSum& y) const {
+        FiSum r(0);
+        r.kept = x.kept + y.kept;
+        r.headers = x.headers + y.headers;
+        return r;
+    }
+};
+
+#ifdef __CUDACC__
+__device__ __forceinline__ unsigned lanemask_gt() {
+    unsigned m;
+    asm("mov.u32 %0, %%lanemask_gt;" : "=r"(m));
+    return m;
+}
+
+struct FiThread {
+    u8 b[kFiBytes];
+    u8 prev;        // the byte before b[0] ('\n' before the file)
+    int valid;      // bytes of this thread inside the file
+    u64 base;
+    u32 h_last, r_first;   // this thread's last header event / first rest event
+};
+
+__device__ __forceinline__ void fi_load(const u8* __restrict__ d_file, u64 n, FiThread& t) {
+    t.base = u64(blockIdx.x) * kFiTile + u64(threadIdx.x) * kFiBytes;
+    t.valid = t.base >= n ? 0 : int(n - t.base < u64(kFiBytes) ? n - t.base : u64(kFiBytes));
+    if (t.valid == kFiBytes) {
+        const uint4* p = reinterpret_cast<const uint4*>(d_file + t.base);
+        const uint4 v0 = __ldg(p), v1 = __ldg(p + 1);
+        const u32 w[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+        for (int j = 0; j < kFiBytes; ++j) t.b[j] = u8(w[j >> 2] >> ((j & 3) * 8));
+    } else {
+#pragma unroll
+        for (int j = 0; j < kFiBytes; ++j) t.b[j] = j < t.valid ? d_file[t.base + j] : u8('\n');
+    }
+    t.prev = (t.base == 0 || t.valid == 0) ? u8('\n') : d_file[t.base - 1];
+    u32 hl = FI_NONE, rf = FI_NONE;
+    u8 p = t.prev;
+#pragma unroll
+    for (int j = 0; j < kFiBytes; ++j) {
+        const u8 c = t.b[j];
+        if (j < t.valid) {
+            if (c == '\n') hl = FI_CLR;
+            else if (c == '>' && p == '\n') hl = FI_SET;
+            if (rf == FI_NONE) rf = c == '\n' ? u32(FI_SET) : (fa_space(c) ? u32(FI_NONE) : u32(FI_CLR));
+        }
+        p = c;
+    }
+    t.h_last = hl;
+    t.r_first = rf;
+}
+
+// states entering this thread from the left (header) and from the right (rest), given those entering the tile;
+// also the tile's own summary (last header event, first rest event) in tile_h / tile_r
+__device__ __forceinline__ void fi_block_states(const FiThread& t, u32 tile_h_in, u32 tile_r_in, u32& h_in, u32& r_in,
+                                                u32& tile_h, u32& tile_r, u32* sm /* 2 * kFiWarps */) {
+    const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
+    const unsigned hb = __ballot_sync(0xffffffffu, t.h_last != FI_NONE), hs = __ballot_sync(0xffffffffu, t.h_last == FI_SET);
+    const unsigned rb = __ballot_sync(0xffffffffu, t.r_first != FI_NONE), rs = __ballot_sync(0xffffffffu, t.r_first == FI_SET);
+    if (lane == 0) {
+        sm[warp] = hb ? (((hs >> (31 - __clz(hb))) & 1u) ? FI_SET : FI_CLR) : FI_NONE;
+        sm[kFiWarps + warp] = rb ? (((rs >> (__ffs(rb) - 1)) & 1u) ? FI_SET : FI_CLR) : FI_NONE;
+    }
+    __syncthreads();
+    u32 wh = tile_h_in, wr = tile_r_in;
+    for (unsigned w = 0; w < warp; ++w) if (sm[w] != FI_NONE) wh = sm[w] == FI_SET;
+    for (unsigned w = kFiWarps - 1; w > warp; --w) if (sm[kFiWarps + w] != FI_NONE) wr = sm[kFiWarps + w] == FI_SET;
+    const unsigned ml = hb & lanemask_lt(), mg = rb & lanemask_gt();
+    h_in = ml ? ((hs >> (31 - __clz(ml))) & 1u) : wh;
+    r_in = mg ? ((rs >> (__ffs(mg) - 1)) & 1u) : wr;
+    tile_h = FI_NONE; tile_r = FI_NONE;
+    for (int w = 0; w < kFiWarps; ++w) if (sm[w] != FI_NONE) tile_h = sm[w];
+    for (int w = kFiWarps - 1; w >= 0; --w) if (sm[kFiWarps + w] != FI_NONE) tile_r = sm[kFiWarps + w];
+    __syncthreads();
+}
+
+// keep mask and header-start mask of this thread's bytes
+__device__ __forceinline__ void fi_masks(const FiThread& t, u32 h_in, u32 r_in, u32& keep, u32& heads) {
+    u32 on_header = 0, newline = 0, trailing = 0;
+    heads = 0;
+    u32 h = h_in;
+    u8 p = t.prev;
+#pragma unroll
+    for (int j = 0; j < kFiBytes; ++j) {
+        const u8 c = t.b[j];
+        if (c == '\n') { h = 0; newline |= 1u << j; }
+        else if (c == '>' && p == '\n') { h = 1; heads |= 1u << j; }
+        on_header |= h << j;
+        p = c;
+    }
+    u32 r = r_in;
+#pragma unroll
+    for (int j = kFiBytes - 1; j >= 0; --j) {
+        const u8 c = t.b[j];
+        if (j < t.valid) {
+            if (c == '\n') r = 1;
+            else if (!fa_space(c)) r = 0;
+            else trailing |= r << j;
+        }
+    }
+    const u32 vmask = t.valid == kFiBytes ? 0xffffffffu : ((1u << t.valid) - 1u);
+    keep = ~on_header & ~newline & ~trailing & vmask;
+    heads &= vmask;
+}
+
+// kept | header starts << 32 of this thread, and the number of its kept bytes up to and including the last non-N one
+__device__ __forceinline__ void fi_thread_counts(const FiThread& t, u32 keep, u32 heads, bool skip_masked, u64& packed, u32& upto_base) {
+    packed = u64(__popc(keep)) | (u64(__popc(heads)) << 32);
+    u32 seen = 0;
+    upto_base = 0;
+#pragma unroll
+    for (int j = 0; j < kFiBytes; ++j) {
+        if ((keep >> j) & 1u) {
+            ++seen;
+            if (fa_normalise(t.b[j], skip_masked) != 'N') upto_base = seen;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kFiThreads) fi_events_kernel(const u8* __restrict__ d_file, u64 n, u8* __restrict__ tile_ev) {
+    __shared__ u32 sm[2 * kFiWarps];
+    FiThread t;
+    fi_load(d_file, n, t);
+    u32 h_in, r_in, th, tr;
+    fi_block_states(t, 0, 1, h_in, r_in, th, tr, sm);
+    if (threadIdx.x == 0) tile_ev[blockIdx.x] = u8(th | (tr << 2));
+}
+
+__global__ void __launch_bounds__(kFiThreads) fi_count_kernel(const u8* __restrict__ d_file, u64 n, const u8* __restrict__ tile_in,
+                                                             bool skip_masked, FiSum* __restrict__ tile_sum, u32* __restrict__ tile_base) {
+    __shared__ u32 sm[2 * kFiWarps];
+    __shared__ u64 s64[32];
+    FiThread t;
+    fi_load(d_file, n, t);
+    const u32 tin = tile_in[blockIdx.x];
+    u32 h_in, r_in, th, tr, keep, heads, upto;
+    fi_block_states(t, tin & 1u, (tin >> 1) & 1u, h_in, r_in, th, tr, sm);
+    fi_masks(t, h_in, r_in, keep, heads);
+    u64 packed, total, last;
+    fi_thread_counts(t, keep, heads, skip_masked, packed, upto);
+    const u64 exc = block_exclusive_scan(packed, SumOp(), total, s64);
+    block_exclusive_scan(upto ? u64((exc & 0xffffffffull) + upto) : u64(0), MaxOp(), last, s64);
+    if (threadIdx.x == 0) {
+        FiSum ts(0);
+        ts.kept = total & 0xffffffffull;
+        ts.headers = total >> 32;
+        tile_sum[blockIdx.x] = ts;
+        tile_base[blockIdx.x] = u32(last);      // kept bytes of the tile up to and including its last non-N one (0: none)
+    }
+}
+
+__global__ void __launch_bounds__(kFiThreads) fi_emit_kernel(const u8* __restrict__ d_file, u64 n, const u8* __restrict__ tile_in,
+                                                            const FiSum* __restrict__ tile_pre, const u64* __restrict__ tile_last,
+                                                            bool skip_masked, u8* __restrict__ strand, u64* __restrict__ rec,
+                                                            u64* __restrict__ run_cnt, u64* __restrict__ runs, u64 run_cap) {
+    __shared__ u32 sm[2 * kFiWarps];
+    __shared__ u64 s64[32];
+    __shared__ __align__(16) u8 stage[kFiTile + 16];
+    FiThread t;
+    fi_load(d_file, n, t);
+    const u32 tin = tile_in[blockIdx.x];
+    u32 h_in, r_in, th, tr, keep, heads, upto;
+    fi_block_states(t, tin & 1u, (tin >> 1) & 1u, h_in, r_in, th, tr, sm);
+    fi_masks(t, h_in, r_in, keep, heads);
+    u64 packed, total, last_total;
+    fi_thread_counts(t, keep, heads, skip_masked, packed, upto);
+    const u64 exc = block_exclusive_scan(packed, SumOp(), total, s64);
+    const u64 last_in_tile = block_exclusive_scan(upto ? u64((exc & 0xffffffffull) + upto) : u64(0), MaxOp(), last_total, s64);
+    const FiSum tile0 = tile_pre[blockIdx.x];
+    const u64 out0 = tile0.kept;
+    const u32 mis = u32(out0 & 15u);     // the strand buffer is 256-byte aligned: same misalignment in the staging area
+    u64 outpos = out0 + (exc & 0xffffffffull), hidx = tile0.headers + (exc >> 32);
+    const u64 after_last = last_in_tile ? out0 + last_in_tile : tile_last[blockIdx.x];
+    u64 trail = outpos - after_last;
+#pragma unroll
+    for (int j = 0; j < kFiBytes; ++j) {
+        if ((heads >> j) & 1u) { rec[2 * hidx] = t.base + j; rec[2 * hidx + 1] = outpos; ++hidx; }
+        if ((keep >> j) & 1u) {
+            const u8 v = fa_normalise(t.b[j], skip_masked);
+            stage[mis + u32(outpos - out0)] = v;
+            if (v != 'N') {
+                if (trail > kLongNRun) {
+                    const u64 slot = atomicAdd(reinterpret_cast<unsigned long long*>(run_cnt), 1ull);
+                    if (slot < run_cap) { runs[2 * slot] = outpos - trail; runs[2 * slot + 1] = trail; }
+                }
+                trail = 0;
+            } else {
+                ++trail;
+            }
+            ++outpos;
+        }
+    }
+    __syncthreads();
+    const u32 cnt = u32(total & 0xffffffffull);
+    const u32 head = min(cnt, (16u - mis) & 15u);
+    const u32 nvec = (cnt - head) / 16u;
+    if (threadIdx.x < head) strand[out0 + threadIdx.x] = stage[mis + threadIdx.x];
+    for (u32 v = threadIdx.x; v < nvec; v += kFiThreads)
+        *reinterpret_cast<uint4*>(strand + out0 + head + 16u * v) = *reinterpret_cast<const uint4*>(stage + mis + head + 16u * v);
+    for (u32 i = head + 16u * nvec + threadIdx.x; i < cnt; i += kFiThreads) strand[out0 + i] = stage[mis + i];
+}
+#endif  // __CUDACC__
 
 inline void ingest_fasta_device(const u8* d_file, u64 n, bool skip_masked, IngestPiece& out, cudaStream_t stream) {
-    using Acc = FlagAcc<u64>;
     out.kept = 0;
     out.rec_off.clear(); out.rec_pos.clear(); out.run_start.clear(); out.run_len.clear();
     if (n == 0) return;
-    DevBuf<u8> cls(n, stream);
-    u8* d_cls = cls.p;
-    {   // R: element 0 stands for the end of the file, element e >= 1 for byte n - e
-        auto flags = [=] __device__(u64 e) -> u32 {
-            if (e == 0) return 0u;
-            const u8 c = d_file[n - e];
-            return c == '\n' ? u32(FS_MARK_A) : (fa_space(c) ? 0u : u32(FS_MARK_B));
-        };
-        auto write = [=] __device__(u64 e, const Acc&, const Acc& inc) {
-            if (e == 0) return;
-            const u8 c = d_file[n - e];
-            d_cls[n - e] = (fa_blank(c) && inc.a >= inc.b) ? 1 : 0;
-        };
-        FlagScanPlan<u64> plan;
-        plan.prepare(flags, n + 1, (Acc*)nullptr, stream);
-        plan.finish(flags, write);
+    const u64 tiles = ceil_div(n, kFiTile);
+    DevBuf<u8> tile_ev(tiles, stream), tile_in(tiles, stream);
+    fi_events_kernel<<<unsigned(tiles), kFiThreads, 0, stream>>>(d_file, n, tile_ev.p);
+    KERNEL_CHECK();
+    count_launch();
+    {   // states entering each tile: the latest header event before it (none: not on a header line), the first rest event
+        // after it (none: the end of the file). "Latest event" = running maximum of (position, value) keys.
+        const u8* ev = tile_ev.p;
+        u8* tin = tile_in.p;
+        auto h_key = [=] __device__(u64 i) -> u64 { const u32 e = ev[i] & 3u; return e ? (((i + 1) << 1) | u64(e == FI_SET)) : 0; };
+        auto h_out = [=] __device__(u64 i, u64 exc, u64) { tin[i] = u8(exc ? (exc & 1) : 0); };
+        device_scan<u64, MaxOp>(h_key, h_out, tiles, (u64*)nullptr, stream);
+        auto r_key = [=] __device__(u64 i) -> u64 { const u32 e = (ev[tiles - 1 - i] >> 2) & 3u; return e ? (((i + 1) << 1) | u64(e == FI_SET)) : 0; };
+        auto r_out = [=] __device__(u64 i, u64 exc, u64) { tin[tiles - 1 - i] |= u8((exc ? (exc & 1) : 1) << 1); };
+        device_scan<u64, MaxOp>(r_key, r_out, tiles, (u64*)nullptr, stream);
     }
-    {   // H: element 0 is the (virtual) newline before the file, element e >= 1 is byte e - 1
-        auto flags = [=] __device__(u64 e) -> u32 {
-            if (e == 0) return 0u;
-            const u64 b = e - 1;
-            const u8 c = d_file[b];
-            if (c == '\n') return u32(FS_MARK_B);
-            return (c == '>' && (b == 0 || d_file[b - 1] == '\n')) ? u32(FS_MARK_A) : 0u;
-        };
-        auto write = [=] __device__(u64 e, const Acc& exc, const Acc& inc) {
-            if (e == 0) return;
-            const u64 b = e - 1;
-            const bool on_header = inc.a > inc.b;
-            const bool keep = !on_header && d_file[b] != '\n' && !d_cls[b];
-            d_cls[b] = u8((keep ? FA_KEEP : 0) | (inc.a != exc.a ? FA_HEADER : 0));
-        };
-        FlagScanPlan<u64> plan;
-        plan.prepare(flags, n + 1, (Acc*)nullptr, stream);
-        plan.finish(flags, write);
+    DevBuf<FiSum> tile_sum(tiles, stream), tile_pre(tiles, stream), d_total(1, stream);
+    DevBuf<u32> tile_base(tiles, stream);
+    DevBuf<u64> tile_last(tiles, stream), d_last(1, stream);
+    fi_count_kernel<<<unsigned(tiles), kFiThreads, 0, stream>>>(d_file, n, tile_in.p, skip_masked, tile_sum.p, tile_base.p);
+    KERNEL_CHECK();
+    count_launch();
+    {
+        const FiSum* sum = tile_sum.p;
+        FiSum* pre = tile_pre.p;
+        const u32* base = tile_base.p;
+        u64* last = tile_last.p;
+        auto in = [=] __device__(u64 i) -> FiSum { return sum[i]; };
+        auto wr = [=] __device__(u64 i, const FiSum& exc, const FiSum&) { pre[i] = exc; };
+        device_scan<FiSum, FiSumOp>(in, wr, tiles, d_total.p, stream);
+        auto lin = [=] __device__(u64 i) -> u64 { return base[i] ? pre[i].kept + base[i] : 0; };
+        auto lwr = [=] __device__(u64 i, u64 exc, u64) { last[i] = exc; };
+        device_scan<u64, MaxOp>(lin, lwr, tiles, d_last.p, stream);
     }
-    DevBuf<Acc> d_total(1, stream);
-    DevBuf<u64> d_rec;
-    {   // K
-        auto flags = [=] __device__(u64 b) -> u32 {
-            const u8 k = d_cls[b];
-            return ((k & FA_KEEP) ? u32(FS_CNT_C) : 0u) | ((k & FA_HEADER) ? u32(FS_CNT_D) : 0u);
-        };
-        FlagScanPlan<u64> plan;
-        plan.prepare(flags, n, d_total.p, stream);
-        Acc tot(0);
-        CUDA_CHECK(cudaMemcpyAsync(&tot, d_total.p, sizeof tot, cudaMemcpyDeviceToHost, stream));
+    FiSum tot(0);
+    u64 after_last = 0;
+    CUDA_CHECK(cudaMemcpyAsync(&tot, d_total.p, sizeof tot, cudaMemcpyDeviceToHost, stream));
+    CUDA_CHECK(cudaMemcpyAsync(&after_last, d_last.p, sizeof after_last, cudaMemcpyDeviceToHost, stream));
+    CUDA_CHECK(cudaStreamSynchronize(stream));
+    out.kept = tot.kept;
+    const u64 records = tot.headers;
+    const u64 cap = out.kept / (kLongNRun + 1) + 1;
+    out.strand.alloc(out.kept, stream);
+    DevBuf<u64> d_rec(2 * records, stream), d_runs(2 * cap + 1, stream);
+    CUDA_CHECK(cudaMemsetAsync(d_runs.p, 0, sizeof(u64), stream));
+    fi_emit_kernel<<<unsigned(tiles), kFiThreads, 0, stream>>>(d_file, n, tile_in.p, tile_pre.p, tile_last.p, skip_masked, out.strand.p,
+                                                               d_rec.p, d_runs.p, d_runs.p + 1, cap);
+    KERNEL_CHECK();
+    count_launch();
+    u64 h_cnt = 0;
+    std::vector<u64> h(2 * records);
+    if (records) CUDA_CHECK(cudaMemcpyAsync(h.data(), d_rec.p, h.size() * sizeof(u64), cudaMemcpyDeviceToHost, stream));
+    CUDA_CHECK(cudaMemcpyAsync(&h_cnt, d_runs.p, sizeof h_cnt, cudaMemcpyDeviceToHost, stream));
+    CUDA_CHECK(cudaStreamSynchronize(stream));
+    out.rec_off.resize(records); out.rec_pos.resize(records);
+    for (u64 r = 0; r < records; ++r) { out.rec_off[r] = h[2 * r]; out.rec_pos[r] = h[2 * r + 1]; }
+    h_cnt = std::min(h_cnt, cap);
+    std::vector<u64> hr(2 * h_cnt);
+    if (h_cnt) {
+        CUDA_CHECK(cudaMemcpyAsync(hr.data(), d_runs.p + 1, hr.size() * sizeof(u64), cudaMemcpyDeviceToHost, stream));
         CUDA_CHECK(cudaStreamSynchronize(stream));
-        out.kept = tot.c;
-        const u64 records = tot.d;
-        out.strand.alloc(out.kept, stream);
-        d_rec.alloc(2 * records, stream);
-        u8* d_strand = out.strand.p;
-        u64* rec = d_rec.p;
-        auto write = [=] __device__(u64 b, const Acc& exc, const Acc&) {
-            const u8 k = d_cls[b];
-            if (k & FA_KEEP) d_strand[exc.c] = fa_normalise(d_file[b], skip_masked);
-            if (k & FA_HEADER) { rec[2 * exc.d] = b; rec[2 * exc.d + 1] = exc.c; }
-        };
-        plan.finish(flags, write);
-        std::vector<u64> h(2 * records);
-        if (records) CUDA_CHECK(cudaMemcpyAsync(h.data(), rec, h.size() * sizeof(u64), cudaMemcpyDeviceToHost, stream));
-        CUDA_CHECK(cudaStreamSynchronize(stream));
-        out.rec_off.resize(records); out.rec_pos.resize(records);
-        for (u64 r = 0; r < records; ++r) { out.rec_off[r] = h[2 * r]; out.rec_pos[r] = h[2 * r + 1]; }
     }
-    const u64 m = out.kept;
-    if (m > kLongNRun) {   // N: element 0 is a virtual non-N byte before the strand, element e >= 1 is strand byte e - 1
-        const u8* d_strand = out.strand.p;
-        const u64 cap = m / (kLongNRun + 1) + 1;
-        DevBuf<u64> d_runs(2 * cap + 1, stream);
-        CUDA_CHECK(cudaMemsetAsync(d_runs.p, 0, sizeof(u64), stream));
-        u64* cnt = d_runs.p;
-        u64* runs = d_runs.p + 1;
-        auto flags = [=] __device__(u64 e) -> u32 {
-            if (e == 0) return 0u;
-            return d_strand[e - 1] != 'N' ? u32(FS_MARK_A) : 0u;
-        };
-        auto write = [=] __device__(u64 e, const Acc&, const Acc& inc) {
-            if (e == 0 || d_strand[e - 1] != 'N') return;
-            if (e != m && d_strand[e] == 'N') return;             // not the last byte of its run
-            const u64 first = inc.a;                             // element a = byte a - 1 is the last non-N one
-            const u64 len = e - first;
-            if (len > kLongNRun) {
-                const u64 slot = atomicAdd(reinterpret_cast<unsigned long long*>(cnt), 1ull);
-                if (slot < cap) { runs[2 * slot] = first; runs[2 * slot + 1] = len; }
-            }
-        };
-        FlagScanPlan<u64> plan;
-        plan.prepare(flags, m + 1, (Acc*)nullptr, stream);
-        plan.finish(flags, write);
-        u64 h_cnt = 0;
-        CUDA_CHECK(cudaMemcpyAsync(&h_cnt, cnt, sizeof h_cnt, cudaMemcpyDeviceToHost, stream));
-        CUDA_CHECK(cudaStreamSynchronize(stream));
-        h_cnt = std::min(h_cnt, cap);
-        std::vector<u64> h(2 * h_cnt);
-        if (h_cnt) CUDA_CHECK(cudaMemcpyAsync(h.data(), runs, h.size() * sizeof(u64), cudaMemcpyDeviceToHost, stream));
-        CUDA_CHECK(cudaStreamSynchronize(stream));
-        std::vector<std::pair<u64, u64>> v(h_cnt);
-        for (u64 i = 0; i < h_cnt; ++i) v[i] = {h[2 * i], h[2 * i + 1]};
-        std::sort(v.begin(), v.end());
-        for (auto& p : v) { out.run_start.push_back(p.first); out.run_len.push_back(p.second); }
-    }
+    std::vector<std::pair<u64, u64>> v(h_cnt);
+    for (u64 i = 0; i < h_cnt; ++i) v[i] = {hr[2 * i], hr[2 * i + 1]};
+    if (out.kept - after_last > kLongNRun) v.push_back({after_last, out.kept - after_last});   // the run that ends the strand
+    std::sort(v.begin(), v.end());
+    for (auto& p : v) { out.run_start.push_back(p.first); out.run_len.push_back(p.second); }
 }
 
 // chunks_to_process of one file (src/bin/asgart.rs:317-366 applied per fragment, :381-387): inside each fragment the
