@@ -80,42 +80,68 @@ __device__ __forceinline__ unsigned lanemask_gt() {
     return m;
 }
 
+// ---- byte classification, four bytes per instruction (SWAR; exact for every byte value, no carries between bytes) ----
+// flags: 0x80 in every byte of x that is zero
+__device__ __forceinline__ u32 sw_zero(u32 x) { return ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x) & 0x80808080u; }
+__device__ __forceinline__ u32 sw_eq(u32 w, u32 k4) { return sw_zero(w ^ k4); }
+// flags: 0x80 in every byte of w below 0x21 (control characters and the blank: every white-space byte is among them)
+__device__ __forceinline__ u32 sw_below_21(u32 w) { return ~(((w & 0x7F7F7F7Fu) + 0x5F5F5F5Fu) | w) & 0x80808080u; }
+// the four flag bits of a word as bits 0..3 (byte 0 = bit 0)
+__device__ __forceinline__ u32 sw_movemask(u32 f) { return ((f >> 7) * 0x01020408u) >> 24; }
+
 struct FiThread {
-    u8 b[kFiBytes];
-    u8 prev;        // the byte before b[0] ('\n' before the file)
-    int valid;      // bytes of this thread inside the file
+    u32 w[kFiBytes / 4];   // the thread's 32 bytes, little endian: byte j = w[j / 4] >> 8 * (j % 4)
+    int valid;             // bytes of this thread inside the file
     u64 base;
+    u32 vmask;             // bit j: byte j is inside the file
+    u32 nl, space, heads;  // bit j: byte j is '\n' / white space / a '>' that opens a line
     u32 h_last, r_first;   // this thread's last header event / first rest event
 };
 
 __device__ __forceinline__ void fi_load(const u8* __restrict__ d_file, u64 n, FiThread& t) {
     t.base = u64(blockIdx.x) * kFiTile + u64(threadIdx.x) * kFiBytes;
     t.valid = t.base >= n ? 0 : int(n - t.base < u64(kFiBytes) ? n - t.base : u64(kFiBytes));
+    t.vmask = t.valid == kFiBytes ? 0xffffffffu : ((1u << t.valid) - 1u);
     if (t.valid == kFiBytes) {
         const uint4* p = reinterpret_cast<const uint4*>(d_file + t.base);
         const uint4 v0 = __ldg(p), v1 = __ldg(p + 1);
-        const u32 w[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-#pragma unroll
-        for (int j = 0; j < kFiBytes; ++j) t.b[j] = u8(w[j >> 2] >> ((j & 3) * 8));
+        t.w[0] = v0.x; t.w[1] = v0.y; t.w[2] = v0.z; t.w[3] = v0.w;
+        t.w[4] = v1.x; t.w[5] = v1.y; t.w[6] = v1.z; t.w[7] = v1.w;
     } else {
 #pragma unroll
-        for (int j = 0; j < kFiBytes; ++j) t.b[j] = j < t.valid ? d_file[t.base + j] : u8('\n');
-    }
-    t.prev = (t.base == 0 || t.valid == 0) ? u8('\n') : d_file[t.base - 1];
-    u32 hl = FI_NONE, rf = FI_NONE;
-    u8 p = t.prev;
+        for (int q = 0; q < kFiBytes / 4; ++q) {
+            u32 x = 0;
 #pragma unroll
-    for (int j = 0; j < kFiBytes; ++j) {
-        const u8 c = t.b[j];
-        if (j < t.valid) {
-            if (c == '\n') hl = FI_CLR;
-            else if (c == '>' && p == '\n') hl = FI_SET;
-            if (rf == FI_NONE) rf = c == '\n' ? u32(FI_SET) : (fa_space(c) ? u32(FI_NONE) : u32(FI_CLR));
+            for (int r = 0; r < 4; ++r) { const int j = 4 * q + r; x |= u32(j < t.valid ? d_file[t.base + j] : u8('\n')) << (8 * r); }
+            t.w[q] = x;
         }
-        p = c;
     }
-    t.h_last = hl;
-    t.r_first = rf;
+    const u32 prev_nl = (t.base == 0 || t.valid == 0) ? 1u : u32(d_file[t.base - 1] == '\n');
+    u32 nl = 0, gt = 0, low = 0;
+#pragma unroll
+    for (int q = 0; q < kFiBytes / 4; ++q) {
+        nl |= sw_movemask(sw_eq(t.w[q], 0x0A0A0A0Au)) << (4 * q);
+        gt |= sw_movemask(sw_eq(t.w[q], 0x3E3E3E3Eu)) << (4 * q);
+        low |= sw_movemask(sw_below_21(t.w[q])) << (4 * q);
+    }
+    nl &= t.vmask; gt &= t.vmask; low &= t.vmask;
+    u32 space = nl;
+    if (low != nl) {                       // some other control character or blank: the remaining white-space values
+#pragma unroll
+        for (int q = 0; q < kFiBytes / 4; ++q) {
+            const u32 x = t.w[q];
+            const u32 f = sw_eq(x, 0x20202020u) | sw_eq(x, 0x09090909u) | sw_eq(x, 0x0B0B0B0Bu) | sw_eq(x, 0x0C0C0C0Cu) | sw_eq(x, 0x0D0D0D0Du);
+            space |= sw_movemask(f) << (4 * q);
+        }
+        space &= t.vmask;
+    }
+    t.nl = nl;
+    t.space = space;
+    t.heads = gt & ((nl << 1) | prev_nl);
+    const u32 ev = t.heads | nl;            // header machine: '>' at a line start sets, '\n' clears; the last event counts
+    t.h_last = ev ? (((t.heads >> (31 - __clz(ev))) & 1u) ? u32(FI_SET) : u32(FI_CLR)) : u32(FI_NONE);
+    const u32 rv = nl | (~space & t.vmask);  // rest machine: '\n' sets, a non-white byte clears; the first event counts
+    t.r_first = rv ? (((nl >> (__ffs(rv) - 1)) & 1u) ? u32(FI_SET) : u32(FI_CLR)) : u32(FI_NONE);
 }
 
 // states entering this thread from the left (header) and from the right (rest), given those entering the tile;
@@ -142,47 +168,53 @@ __device__ __forceinline__ void fi_block_states(const FiThread& t, u32 tile_h_in
     __syncthreads();
 }
 
-// keep mask and header-start mask of this thread's bytes
-__device__ __forceinline__ void fi_masks(const FiThread& t, u32 h_in, u32 r_in, u32& keep, u32& heads) {
-    u32 on_header = 0, newline = 0, trailing = 0;
-    heads = 0;
-    u32 h = h_in;
-    u8 p = t.prev;
-#pragma unroll
-    for (int j = 0; j < kFiBytes; ++j) {
-        const u8 c = t.b[j];
-        if (c == '\n') { h = 0; newline |= 1u << j; }
-        else if (c == '>' && p == '\n') { h = 1; heads |= 1u << j; }
-        on_header |= h << j;
-        p = c;
-    }
-    u32 r = r_in;
-#pragma unroll
-    for (int j = kFiBytes - 1; j >= 0; --j) {
-        const u8 c = t.b[j];
-        if (j < t.valid) {
-            if (c == '\n') r = 1;
-            else if (!fa_space(c)) r = 0;
-            else trailing |= r << j;
+// keep mask of this thread's bytes: not on a header line, not '\n', not trailing white space
+__device__ __forceinline__ u32 fi_keep_mask(const FiThread& t, u32 h_in, u32 r_in) {
+    if (t.valid == 0) return 0;
+    u32 on_header;
+    if (t.heads == 0) {                     // no header starts here: the entering state holds up to the first '\n'
+        on_header = h_in ? (t.nl ? ((1u << (__ffs(t.nl) - 1)) - 1u) : 0xffffffffu) : 0u;
+    } else {
+        on_header = 0;
+        u32 h = h_in;
+        for (int j = 0; j < t.valid; ++j) {
+            if ((t.nl >> j) & 1u) h = 0;
+            else if ((t.heads >> j) & 1u) h = 1;
+            on_header |= h << j;
         }
     }
-    const u32 vmask = t.valid == kFiBytes ? 0xffffffffu : ((1u << t.valid) - 1u);
-    keep = ~on_header & ~newline & ~trailing & vmask;
-    heads &= vmask;
+    const u32 blank = t.space & ~t.nl;
+    u32 trailing = 0;
+    if (blank) {                            // a blank is trailing iff its successor is '\n', a trailing blank, or (last byte) r_in
+        const u32 inject = r_in << (t.valid - 1);
+        for (;;) {
+            const u32 next = blank & (((t.nl | trailing) >> 1) | inject);
+            if (next == trailing) break;
+            trailing = next;
+        }
+    }
+    return ~(on_header | t.nl | trailing) & t.vmask;
 }
 
-// kept | header starts << 32 of this thread, and the number of its kept bytes up to and including the last non-N one
-__device__ __forceinline__ void fi_thread_counts(const FiThread& t, u32 keep, u32 heads, bool skip_masked, u64& packed, u32& upto_base) {
-    packed = u64(__popc(keep)) | (u64(__popc(heads)) << 32);
-    u32 seen = 0;
-    upto_base = 0;
+// flags of the bytes that normalise to a base (A, C, G, T; src/bin/asgart.rs:291-301) and the normalised words
+__device__ __forceinline__ u32 fi_base_mask(const FiThread& t, bool skip_masked, u32* norm /* kFiBytes / 4, may be null */) {
+    u32 base = 0;
 #pragma unroll
-    for (int j = 0; j < kFiBytes; ++j) {
-        if ((keep >> j) & 1u) {
-            ++seen;
-            if (fa_normalise(t.b[j], skip_masked) != 'N') upto_base = seen;
-        }
+    for (int q = 0; q < kFiBytes / 4; ++q) {
+        // upper-casing: clearing bit 5 maps a,c,g,t onto A,C,G,T and no other byte value onto them
+        const u32 u = skip_masked ? t.w[q] : (t.w[q] & 0xDFDFDFDFu);
+        const u32 f = sw_eq(u, 0x41414141u) | sw_eq(u, 0x43434343u) | sw_eq(u, 0x47474747u) | sw_eq(u, 0x54545454u);
+        base |= sw_movemask(f) << (4 * q);
+        if (norm) { const u32 bm = (f >> 7) * 0xFFu; norm[q] = (u & bm) | (0x4E4E4E4Eu & ~bm); }
     }
+    return base & t.vmask;
+}
+
+// kept | header starts << 32 of this thread, and the number of its kept bytes up to and including the last base
+__device__ __forceinline__ void fi_thread_counts(const FiThread& t, u32 keep, u32 base, u64& packed, u32& upto_base) {
+    packed = u64(__popc(keep)) | (u64(__popc(t.heads)) << 32);
+    const u32 kb = keep & base;
+    upto_base = kb ? u32(__popc(keep & (0xffffffffu >> __clz(kb)))) : 0u;
 }
 
 __global__ void __launch_bounds__(kFiThreads) fi_events_kernel(const u8* __restrict__ d_file, u64 n, u8* __restrict__ tile_ev) {
@@ -201,11 +233,11 @@ __global__ void __launch_bounds__(kFiThreads) fi_count_kernel(const u8* __restri
     FiThread t;
     fi_load(d_file, n, t);
     const u32 tin = tile_in[blockIdx.x];
-    u32 h_in, r_in, th, tr, keep, heads, upto;
+    u32 h_in, r_in, th, tr, upto;
     fi_block_states(t, tin & 1u, (tin >> 1) & 1u, h_in, r_in, th, tr, sm);
-    fi_masks(t, h_in, r_in, keep, heads);
+    const u32 keep = fi_keep_mask(t, h_in, r_in);
     u64 packed, total, last;
-    fi_thread_counts(t, keep, heads, skip_masked, packed, upto);
+    fi_thread_counts(t, keep, fi_base_mask(t, skip_masked, nullptr), packed, upto);
     const u64 exc = block_exclusive_scan(packed, SumOp(), total, s64);
     block_exclusive_scan(upto ? u64((exc & 0xffffffffull) + upto) : u64(0), MaxOp(), last, s64);
     if (threadIdx.x == 0) {
@@ -213,7 +245,7 @@ __global__ void __launch_bounds__(kFiThreads) fi_count_kernel(const u8* __restri
         ts.kept = total & 0xffffffffull;
         ts.headers = total >> 32;
         tile_sum[blockIdx.x] = ts;
-        tile_base[blockIdx.x] = u32(last);      // kept bytes of the tile up to and including its last non-N one (0: none)
+        tile_base[blockIdx.x] = u32(last);      // kept bytes of the tile up to and including its last base (0: none)
     }
 }
 
@@ -227,36 +259,46 @@ __global__ void __launch_bounds__(kFiThreads) fi_emit_kernel(const u8* __restric
     FiThread t;
     fi_load(d_file, n, t);
     const u32 tin = tile_in[blockIdx.x];
-    u32 h_in, r_in, th, tr, keep, heads, upto;
+    u32 h_in, r_in, th, tr, upto;
     fi_block_states(t, tin & 1u, (tin >> 1) & 1u, h_in, r_in, th, tr, sm);
-    fi_masks(t, h_in, r_in, keep, heads);
+    const u32 keep = fi_keep_mask(t, h_in, r_in);
+    u32 norm[kFiBytes / 4];
+    const u32 base = fi_base_mask(t, skip_masked, norm);
     u64 packed, total, last_total;
-    fi_thread_counts(t, keep, heads, skip_masked, packed, upto);
+    fi_thread_counts(t, keep, base, packed, upto);
     const u64 exc = block_exclusive_scan(packed, SumOp(), total, s64);
     const u64 last_in_tile = block_exclusive_scan(upto ? u64((exc & 0xffffffffull) + upto) : u64(0), MaxOp(), last_total, s64);
     const FiSum tile0 = tile_pre[blockIdx.x];
     const u64 out0 = tile0.kept;
     const u32 mis = u32(out0 & 15u);     // the strand buffer is 256-byte aligned: same misalignment in the staging area
-    u64 outpos = out0 + (exc & 0xffffffffull), hidx = tile0.headers + (exc >> 32);
-    const u64 after_last = last_in_tile ? out0 + last_in_tile : tile_last[blockIdx.x];
-    u64 trail = outpos - after_last;
-#pragma unroll
-    for (int j = 0; j < kFiBytes; ++j) {
-        if ((heads >> j) & 1u) { rec[2 * hidx] = t.base + j; rec[2 * hidx + 1] = outpos; ++hidx; }
-        if ((keep >> j) & 1u) {
-            const u8 v = fa_normalise(t.b[j], skip_masked);
-            stage[mis + u32(outpos - out0)] = v;
-            if (v != 'N') {
-                if (trail > kLongNRun) {
-                    const u64 slot = atomicAdd(reinterpret_cast<unsigned long long*>(run_cnt), 1ull);
-                    if (slot < run_cap) { runs[2 * slot] = outpos - trail; runs[2 * slot + 1] = trail; }
-                }
-                trail = 0;
-            } else {
-                ++trail;
-            }
-            ++outpos;
+    const u64 outpos = out0 + (exc & 0xffffffffull);
+    if (t.heads) {                       // one (file offset, strand position) pair per record
+        u64 hidx = tile0.headers + (exc >> 32);
+        for (u32 m = t.heads; m; m &= m - 1) {
+            const int j = __ffs(m) - 1;
+            rec[2 * hidx] = t.base + j;
+            rec[2 * hidx + 1] = outpos + __popc(keep & ((1u << j) - 1u));
+            ++hidx;
         }
+    }
+    const u32 kb = keep & base;
+    if (kb) {                            // an N-run longer than 5000 is reported by the first base after it
+        const u64 after_last = last_in_tile ? out0 + last_in_tile : tile_last[blockIdx.x];
+        const u64 first_base = outpos + __popc(keep & ((1u << (__ffs(kb) - 1)) - 1u));
+        const u64 len = first_base - after_last;
+        if (len > kLongNRun) {
+            const u64 slot = atomicAdd(reinterpret_cast<unsigned long long*>(run_cnt), 1ull);
+            if (slot < run_cap) { runs[2 * slot] = after_last; runs[2 * slot + 1] = len; }
+        }
+    }
+    u32 at = mis + u32(outpos - out0);
+    if (keep == 0xffffffffu && (at & 3u) == 0) {
+#pragma unroll
+        for (int q = 0; q < kFiBytes / 4; ++q) *reinterpret_cast<u32*>(stage + at + 4 * q) = norm[q];
+    } else {
+#pragma unroll
+        for (int j = 0; j < kFiBytes; ++j)
+            if ((keep >> j) & 1u) stage[at++] = u8(norm[j >> 2] >> ((j & 3) * 8));
     }
     __syncthreads();
     const u32 cnt = u32(total & 0xffffffffull);

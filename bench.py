@@ -157,6 +157,52 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+# ---------------------------------------------------------------------------------------------------- FASTA ingest
+def fasta_bytes(seq: np.ndarray, frags, width: int = 60) -> np.ndarray:
+    """The strand as a `width`-column multiFASTA, one record per fragment (numpy only: 3 GB in a few seconds)."""
+    parts = []
+    for name, pos, ln in frags:
+        parts.append(np.frombuffer(f">{name} synthetic\n".encode(), dtype=np.uint8))
+        body = seq[pos:pos + ln]
+        full = ln // width * width
+        rows = np.empty((ln // width, width + 1), dtype=np.uint8)
+        rows[:, :width] = body[:full].reshape(-1, width)
+        rows[:, width] = 10
+        parts.append(rows.reshape(-1))
+        if ln > full:
+            parts.append(body[full:])
+            parts.append(np.frombuffer(b"\n", dtype=np.uint8))
+    return np.concatenate(parts)
+
+
+def measure_ingest(ctx, prep, peak_gbs: float):
+    """prepare_data on the device: the workload as a 60-column multiFASTA in pinned host memory ->
+    strand + fragment map + chunks in HBM. Not part of `value` / `e2e` (the metric starts at the strand, like the
+    reference's SearchDuplications step); reported next to them."""
+    import torch
+    fa = fasta_bytes(np.asarray(prep.strand)[:-1], prep.map)
+    pinned = torch.empty(len(fa), dtype=torch.uint8).pin_memory()
+    pinned.numpy()[:] = fa
+    del fa
+    view = pinned.numpy()
+    best = None
+    for _ in range(3):
+        ctx.reset_stats()
+        t0 = time.perf_counter()
+        got = ctx.ingest([view], False, names=["bench.fa"])
+        wall = (time.perf_counter() - t0) * 1e3
+        s = ctx.stats()
+        alg = 3 * s["ingest_bytes"] + (got.n1 - 1)          # three reads per file byte, one write per kept byte
+        row = {"file_bytes": int(s["ingest_bytes"]), "records": int(s["ingest_records"]), "ms_wall": wall, "ms_h2d": s["ms_h2d"],
+               "ms_scans": s["ms_ingest"], "ms_pack": s["ms_pack"], "scan_alg_GBps": alg / max(s["ms_ingest"], 1e-9) / 1e6,
+               "gpu_launches": int(s["launches_total"])}
+        row["scan_frac_of_hbm_peak"] = row["scan_alg_GBps"] / peak_gbs
+        assert got.map == prep.map and got.chunks == [tuple(c) for c in prep.chunks] and got.n1 == len(prep.strand)
+        if best is None or row["ms_wall"] < best["ms_wall"]:
+            best = row
+    return best
+
+
 # ---------------------------------------------------------------------------------------------------- our arm
 def run_ours(args):
     import torch
@@ -269,7 +315,7 @@ def run_ours(args):
         if os.path.exists(tpath):
             try:
                 tj = json.load(open(tpath))
-                if tj.get("pairs_per_launch") == n1:      # the capture is of this workload's launch
+                if tj.get("algorithmic_bytes_per_launch") == int(scat_bytes):      # the capture is of this very launch shape
                     traffic = tj.get("rs_scatter_kernel_dram_bytes_per_launch")
             except Exception:
                 traffic = None
@@ -323,6 +369,8 @@ def run_ours(args):
                            f"reference's libdivsufsort64 (1 thread, as build.rs builds it) + oracle port of the Rust probe "
                            f"loop/automaton/post-steps on {cores} threads over {len(s_chunks)} chunks (no rustc in this image)"),
                 "phases_s": {k: round(v, 3) for k, v in r.items() if k.endswith("_s")}, "families": r["families"]}
+        if world == 1 and not args.no_ingest:
+            line["ingest"] = measure_ingest(ctx, prep, peak)
         print(json.dumps(line), flush=True)
     if dist is not None:
         ctx.dist_shutdown()
@@ -341,6 +389,7 @@ def main():
     ap.add_argument("--scale-n", type=int, default=0, help="override the config's genome length (bp)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ingest", action="store_true", help="skip the FASTA-ingest measurement (N=1 only)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

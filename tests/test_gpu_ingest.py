@@ -66,6 +66,11 @@ def test_ingest_line_and_record_shapes(tmp_path, skip_masked):
         b"\n\n",
         b">a\n   \n \t \n>b\n\x0b\x0cAC\x0b\x0c\n",                                  # lines of blanks only; VT / FF
     ]
+    # every byte value, in random order and in runs: exercises the four-bytes-per-instruction classification (bytes >= 0x80,
+    # control characters, '>' after a random '\n', blanks before a random '\n')
+    blobs.append(b">bin\n" + rng.integers(0, 256, size=20000, dtype=np.uint8).tobytes().replace(b"\n>", b"\n?"))   # ids must stay UTF-8
+    blobs.append(b">runs\n" + b"".join(bytes([v]) * 37 for v in range(256)) + b"\n" + bytes(range(256)) * 3)
+    blobs.append(b">ws\n" + rng.choice(np.frombuffer(b"AC \t\r\n\x0b\x0c>", dtype=np.uint8), size=30000).tobytes())
     for i, blob in enumerate(blobs):
         _check(tmp_path, [blob], skip_masked, tag=f"s{i}_")
     _check(tmp_path, blobs[:4], skip_masked, tag="multi")                            # several files: running offset
