@@ -87,7 +87,7 @@ SYMBOLS = [
     "asgart_b200_synth_fragments",
     "asgart_b200_build_index_group", "asgart_b200_dist_unique_id", "asgart_b200_ctx_dist_init", "asgart_b200_ctx_dist_shutdown",
     "asgart_b200_ctx_ingest_begin", "asgart_b200_ctx_ingest_fasta", "asgart_b200_ctx_ingest_file",
-    "asgart_b200_ctx_ingest_finish", "asgart_b200_ctx_download_strand",
+    "asgart_b200_ctx_ingest_finish", "asgart_b200_ctx_download_strand", "asgart_b200_run_files_passes",
 ]
 
 _lib = None
@@ -158,6 +158,7 @@ def load() -> C.CDLL:
         "asgart_b200_free_string": (None, [vp]),
         "asgart_b200_out_filename": (vp, [C.c_char_p, C.c_char_p, C.c_char_p, PS]),
         "asgart_b200_run_files": (vp, [C.c_char_p, PS, i32, C.POINTER(C.c_char_p)]),
+        "asgart_b200_run_files_passes": (vp, [C.c_char_p, PS, i32, i32, C.POINTER(C.c_char_p)]),
         "asgart_b200_synth_length": (i64, [i32, i32, i64]),
         "asgart_b200_synth_fill": (i64, [i32, i32, i64, C.c_uint64, i64, i32, vp, i64, i32]),
         "asgart_b200_synth_fragments": (i64, [i32, i32, i64, vp, i64, vp, vp, i64]),

@@ -454,6 +454,21 @@ def search_duplications(files: Sequence[str], settings: RunSettings, device: int
         L.asgart_b200_free_string(p)
 
 
+def search_duplications_passes(files: Sequence[str], passes: Sequence[RunSettings], device: int = 0) -> str:
+    """Several runs (e.g. direct and -RC) over one index, combined as `asgart-slice` combines their JSON files
+    (RunResult::from_files, src/structs.rs:114-141): strand and settings of the first pass, families concatenated."""
+    L = _lib.load()
+    arr = (_lib.Settings * len(passes))(*[p.to_c() for p in passes])
+    err = C.c_char_p()
+    p = L.asgart_b200_run_files_passes("\n".join(files).encode(), arr, len(passes), device, C.byref(err))
+    if not p:
+        raise AsgartB200Error(-1, err.value.decode() if err.value else "run failed")
+    try:
+        return C.string_at(p).decode()
+    finally:
+        L.asgart_b200_free_string(p)
+
+
 # ---------------------------------------------------------------------------------------------- synthetic inputs
 def synth_genome(config: int, part: int = 0, scale_n: int = 0, seed: int = 1, n_pairs: int = 0, rc_percent: int = 0,
                  threads: int = 8, out: Optional[np.ndarray] = None):

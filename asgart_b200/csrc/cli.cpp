@@ -1,6 +1,6 @@
 // cli.cpp — `asgart-b200 FILES... [flags]`: the command line of src/bin/asgart.rs:564-631 for the duplication-search
 // path, driving the device operator through the C ABI and writing the same JSON file the reference writes
-// (naming rule src/bin/asgart.rs:695-719). --trim and --compute-score are outside the path.
+// (naming rule src/bin/asgart.rs:695-719). --trim is outside the path.
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -22,6 +22,8 @@ static void usage() {
             "      --prefix <P>            prefix to prepend to the default output file name\n"
             "      --out <FILE>            set the output file name\n"
             "      --device <N>            CUDA device [default: 0]\n"
+            "      --with-direct           (with -R/-C) also run the direct pass on the same index and write both, combined as\n"
+            "                              `asgart-slice` combines the two runs' files\n"
             "      --threads, --chunk-size accepted and ignored (the reference ignores --chunk-size too)\n"
             "  -v                          verbose\n");
 }
@@ -32,7 +34,7 @@ int main(int argc, char** argv) {
     uint64_t gap = 100;
     std::string prefix, out;
     std::vector<std::string> files;
-    int device = 0, verbose = 0;
+    int device = 0, verbose = 0, with_direct = 0;
     auto need = [&](int& i) -> const char* { if (i + 1 >= argc) { usage(); exit(2); } return argv[++i]; };
     for (int i = 1; i < argc; ++i) {
         std::string a = argv[i];
@@ -45,6 +47,7 @@ int main(int argc, char** argv) {
         else if (a == "--device") device = atoi(need(i));
         else if (a == "--threads" || a == "--chunk-size") need(i);
         else if (a == "--compute-score") st.compute_score = 1;
+        else if (a == "--with-direct") with_direct = 1;
         else if (a == "--trim") { fprintf(stderr, "asgart-b200: %s is outside the accelerated path\n", a.c_str()); return 2; }
         else if (a == "-h" || a == "--help") { usage(); return 0; }
         else if (a == "--reverse") st.reverse = 1;
@@ -64,7 +67,10 @@ int main(int argc, char** argv) {
     std::string joined;
     for (size_t i = 0; i < files.size(); ++i) joined += (i ? "\n" : "") + files[i];
     const char* err = nullptr;
-    char* js = asgart_b200_run_files(joined.c_str(), &st, device, &err);
+    asgart_b200_settings passes[2] = {st, st};
+    passes[1].reverse = passes[1].complement = 0;
+    const int n_passes = (with_direct && (st.reverse || st.complement)) ? 2 : 1;
+    char* js = asgart_b200_run_files_passes(joined.c_str(), passes, n_passes, device, &err);
     if (!js) { fprintf(stderr, "asgart-b200: %s\n", err ? err : "failed"); return 1; }
     char* name = asgart_b200_out_filename(joined.c_str(), prefix.c_str(), out.empty() ? nullptr : out.c_str(), &st);
     FILE* f = fopen(name, "wb");

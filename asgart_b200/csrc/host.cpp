@@ -588,36 +588,58 @@ char* asgart_b200_out_filename(const char* files, const char* prefix, const char
     return r;
 }
 
-// bin/asgart.rs:731-822: prepare_data -> SearchDuplications -> FilterNs -> ReOrder -> ReduceOverlap -> Sort -> JSON.
-// prepare_data runs on the device too (GPU-side FASTA ingest): the files' bytes go to HBM as they are read.
-char* asgart_b200_run_files(const char* files, const asgart_b200_settings* st, int32_t device, const char** err) {
+// bin/asgart.rs:731-822: prepare_data -> SearchDuplications -> FilterNs -> ReOrder -> ReduceOverlap -> Sort -> JSON,
+// for one or several passes over ONE index. prepare_data runs on the device too (GPU-side FASTA ingest): the files'
+// bytes go to HBM as they are read. Several passes combine as RunResult::from_files does for their JSON files
+// (structs.rs:114-141): strand and settings of the first, families concatenated in pass order.
+char* asgart_b200_run_files_passes(const char* files, const asgart_b200_settings* passes, int32_t n_passes, int32_t device,
+                                   const char** err) {
     static thread_local std::string msg;
     if (err) *err = nullptr;
     auto failf = [&](const std::string& m) -> char* { msg = m; if (err) *err = msg.c_str(); return nullptr; };
+    if (!passes || n_passes < 1) return failf("no passes");
+    for (int32_t i = 1; i < n_passes; ++i)
+        if ((passes[i].skip_masked != 0) != (passes[0].skip_masked != 0))
+            return failf("passes over one index must agree on skip_masked (it changes the strand)");
     const std::vector<std::string> fl = split_lines(files);
     if (fl.empty()) return failf("no input files");
     asgart_b200_ctx* ctx = nullptr;
     int rc = asgart_b200_ctx_create(device, &ctx);
     if (rc) return failf("no usable CUDA device (code " + std::to_string(rc) + "); this build has no CPU path");
     asgart_b200_prepared* p = nullptr;
-    asgart_b200_result* res = nullptr;
     char* js = nullptr;
     rc = asgart_b200_ctx_ingest_begin(ctx);
-    for (size_t i = 0; !rc && i < fl.size(); ++i) rc = asgart_b200_ctx_ingest_file(ctx, fl[i].c_str(), int32_t(st->skip_masked));
+    for (size_t i = 0; !rc && i < fl.size(); ++i) rc = asgart_b200_ctx_ingest_file(ctx, fl[i].c_str(), int32_t(passes[0].skip_masked));
     if (!rc) rc = asgart_b200_ctx_ingest_finish(ctx, files, &p);
     if (rc) {
         failf(asgart_b200_ctx_last_error(ctx));
     } else {
+        std::vector<uint64_t> fam_off{0};
+        std::vector<asgart_b200_protosd> sds;
         rc = asgart_b200_ctx_build_index(ctx);
-        if (!rc) rc = asgart_b200_ctx_search(ctx, p->chunks.data(), int64_t(p->chunks.size()), st,
-                                            ASGART_B200_POST_ALL | (st->compute_score ? ASGART_B200_POST_COMPUTE_SCORE : 0u), &res);
+        for (int32_t i = 0; !rc && i < n_passes; ++i) {
+            asgart_b200_result* res = nullptr;
+            rc = asgart_b200_ctx_search(ctx, p->chunks.data(), int64_t(p->chunks.size()), &passes[i],
+                                        ASGART_B200_POST_ALL | (passes[i].compute_score ? ASGART_B200_POST_COMPUTE_SCORE : 0u), &res);
+            if (!rc) {
+                const int64_t nf = asgart_b200_result_n_families(res);
+                const uint64_t* off = asgart_b200_result_family_offsets(res);
+                const asgart_b200_protosd* r = asgart_b200_result_sds(res);
+                for (int64_t f = 0; f < nf; ++f) fam_off.push_back(sds.size() + off[f + 1]);
+                sds.insert(sds.end(), r, r + off[nf]);
+            }
+            asgart_b200_result_free(res);
+        }
         if (rc) failf(std::string("device pipeline failed: ") + asgart_b200_ctx_last_error(ctx));
-        else js = asgart_b200_to_json(p, st, asgart_b200_result_family_offsets(res), asgart_b200_result_n_families(res), asgart_b200_result_sds(res));
+        else js = asgart_b200_to_json(p, &passes[0], fam_off.data(), int64_t(fam_off.size()) - 1, sds.data());
     }
-    asgart_b200_result_free(res);
     asgart_b200_ctx_destroy(ctx);
     if (p) asgart_b200_prepared_free(p);
     return js;
+}
+
+char* asgart_b200_run_files(const char* files, const asgart_b200_settings* st, int32_t device, const char** err) {
+    return asgart_b200_run_files_passes(files, st, 1, device, err);
 }
 
 // ---- synthetic genomes ---------------------------------------------------------------------------------

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — the hot path (SA build + LUT + probe search + arm automaton + post-steps) on synthetic genomes.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--config 1..4] [--scale-n BP] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config 1..5] [--scale-n BP] [--impl ours|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 ... bench.py --gpus N ...
 
 One JSON line on rank 0. A "step" = one whole pass of the path over the workload genome:
@@ -38,14 +38,16 @@ CONFIG_FLAGS = {
     2: dict(reverse=True, complement=True, skip_masked=True),
     3: dict(reverse=True, complement=True, max_cardinality=500),
     4: dict(reverse=True, complement=True),
+    5: dict(reverse=True, complement=True, probe_size=32, gap_size=200),
 }
 CONFIG_NAMES = {
     1: "C1 synthetic 10 Mbp single-FASTA, 40 planted direct pairs, direct only",
     2: "C2 synthetic 57 Mbp chrY-sized, planted direct+RC duplications, -RC -S",
     3: "C3 synthetic 250 Mbp chr1-sized, -RC, max_cardinality=500",
     4: "C4 synthetic 3.1 Gbp 24-fragment multiFASTA, -RC",
+    5: "C5 cross-genome: two synthetic 1 Gbp 10-fragment genomes with shared planted segments, -RC, k=32, g=200",
 }
-FULL_N = {1: 10_000_000, 2: 57_227_415, 3: 248_956_422, 4: 3_088_269_832}
+FULL_N = {1: 10_000_000, 2: 57_227_415, 3: 248_956_422, 4: 3_088_269_832, 5: 2_000_000_000}
 METRIC = "bp/s searched end-to-end (SA build + search + clustering; -RC, k=20, g=100)"
 
 
@@ -95,8 +97,17 @@ def make_workload(config: int, scale_n: int):
     import asgart_b200 as ab
     flags = CONFIG_FLAGS[config]
     st = ab.RunSettings(**flags)
-    g, fr = ab.synth_genome(config, scale_n=scale_n, threads=os.cpu_count() or 8)
-    prep = ab.Prepared.from_memory(ab.normalise(g, st.skip_masked), fr, f"synthC{config}.fa")
+    threads = os.cpu_count() or 8
+    if config == 5:     # `asgart A.fa B.fa`: the two genomes concatenated with a running offset (src/bin/asgart.rs:375-395)
+        ga, fa = ab.synth_genome(5, part=0, scale_n=scale_n // 2, threads=threads)
+        gb, fb = ab.synth_genome(5, part=1, scale_n=scale_n // 2, threads=threads)
+        g = np.concatenate([ga, gb])
+        fr = fa + [(nm, pos + len(ga), ln) for nm, pos, ln in fb]
+        names = "synthC5_A.fa, synthC5_B.fa"
+    else:
+        g, fr = ab.synth_genome(config, scale_n=scale_n, threads=threads)
+        names = f"synthC{config}.fa"
+    prep = ab.Prepared.from_memory(ab.normalise(g, st.skip_masked), fr, names)
     return st, prep
 
 
@@ -385,7 +396,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--config", type=int, default=4, choices=[1, 2, 3, 4])
+    ap.add_argument("--config", type=int, default=4, choices=[1, 2, 3, 4, 5])
     ap.add_argument("--scale-n", type=int, default=0, help="override the config's genome length (bp)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -249,6 +249,14 @@ ASGART_B200_API char *asgart_b200_out_filename(const char *files, const char *pr
 /* whole `asgart FILES...` run on one device: prepare_data -> index -> search -> post-steps -> JSON text (malloc'd) */
 ASGART_B200_API char *asgart_b200_run_files(const char *files, const asgart_b200_settings *settings, int32_t device,
                                             const char **err);
+/* Several passes over ONE index. The reference needs one `asgart` invocation per orientation (-R / -C / -RC runs never
+ * report direct duplications, src/bin/asgart.rs:207-218) — each rebuilding the suffix array — and `asgart-slice a.json
+ * b.json` to combine them. Here prepare_data and the index are built once, every settings entry is one pass (they must
+ * agree on skip_masked, which changes the strand), and the JSON is what RunResult::from_files (src/structs.rs:114-141)
+ * gives for the passes' files in this order: strand and settings of the first pass, families of all passes concatenated
+ * (the merge itself; asgart-slice's filters are not part of this). */
+ASGART_B200_API char *asgart_b200_run_files_passes(const char *files, const asgart_b200_settings *passes, int32_t n_passes,
+                                                   int32_t device, const char **err);
 
 /* ---- GPU-side FASTA ingest ----------------------------------------------------------------
  * read_fasta + find_chunks_to_process of prepare_data (src/bin/asgart.rs:278-366) on the device, for the raw bytes of

@@ -153,3 +153,62 @@ def test_ingest_then_search_equals_host_prepared_path(tmp_path):
         js = ab.search_duplications(files, st)                                        # run_files goes through the ingest
         assert js == oracle.run_files(files, _osettings(st), threads=4)
         assert json.loads(js)["strand"]["name"] == ", ".join(files)
+
+
+def test_c5_cross_genome_two_files(tmp_path):
+    """BASELINE configs[4] scaled down: `asgart A.fa B.fa -k 32 -g 200 -RC` on two 10-fragment genomes that share planted
+    segments (3 Mbp each here). Two files -> running offset, 20 fragments, probe_size 32 (two-word window compares),
+    step 16, max_gap 232; families identical to the oracle's and some duplicons pair a fragment of A with one of B."""
+    files = []
+    for part, tag in ((0, "A"), (1, "B")):
+        g, fr = ab.synth_genome(5, part=part, scale_n=3_000_000)
+        text = g.tobytes().decode()
+        p = tmp_path / f"genome{tag}.fa"
+        p.write_bytes(_fasta([(nm + " synthetic", text[pos:pos + ln]) for nm, pos, ln in fr]))
+        files.append(str(p))
+    st = ab.RunSettings(probe_size=32, gap_size=200, reverse=True, complement=True)
+    want_prep = oracle.Prepared.from_files(files, False)
+    sa = oracle.best_suffix_array(want_prep.strand)
+    want = oracle.search(want_prep.strand, sa, want_prep.chunks, _osettings(st), oracle.POST_ALL, threads=4)
+    with ab.Context(0) as ctx:
+        prep = ctx.ingest(files, False)
+        assert len(prep.map) == 20 and prep.map == want_prep.map and prep.chunks == want_prep.chunks
+        ctx.build_index()
+        assert ctx.check_sa() == 0
+        got = ctx.search(prep.chunks, st, ab.POST_ALL)
+        assert got.as_lists() == want.families.as_lists()
+        half = prep.map[10][1]                                                     # first base of genome B
+        cross = sum(1 for fam in got.as_lists() for sd in fam if sd[0] < half <= sd[1])
+        assert cross > 0
+        js = prep.to_json(st, got)
+        assert js == want_prep.to_json(_osettings(st), want.families)
+        assert json.loads(js)["settings"]["max_gap_size"] == 232
+        # the direct pass over the same index (what asgart-slice would merge with the -RC run)
+        st_d = ab.RunSettings(probe_size=32, gap_size=200)
+        got_d = ctx.search(prep.chunks, st_d, ab.POST_ALL)
+        want_d = oracle.search(want_prep.strand, sa, want_prep.chunks, _osettings(st_d), oracle.POST_ALL, threads=4)
+        assert got_d.as_lists() == want_d.families.as_lists()
+
+
+def test_passes_over_one_index_combine_like_asgart_slice(tmp_path):
+    """Direct + -RC passes over one index = RunResult::from_files (src/structs.rs:114-141) of the two runs' JSON files:
+    strand and settings of the first, families concatenated in input order. Also through the CLI (--with-direct)."""
+    import subprocess
+    g, fr = ab.synth_genome(2, scale_n=1_500_000)
+    fa = tmp_path / "y.fa"
+    fa.write_bytes(_fasta([("synthY", g.tobytes().decode())]))
+    files = [str(fa)]
+    rc, direct = ab.RunSettings(reverse=True, complement=True, skip_masked=True), ab.RunSettings(skip_masked=True)
+    runs = [json.loads(oracle.run_files(files, _osettings(st), threads=4)) for st in (rc, direct)]
+    want = {"strand": runs[0]["strand"], "settings": runs[0]["settings"], "families": runs[0]["families"] + runs[1]["families"]}
+    got = json.loads(ab.search_duplications_passes(files, [rc, direct]))
+    assert got == want
+    assert len(runs[0]["families"]) > 0 and len(runs[1]["families"]) > 0
+    assert {sd["reversed"] for f in got["families"] for sd in f} == {True, False}
+    with pytest.raises(ab.AsgartB200Error, match="skip_masked"):
+        ab.search_duplications_passes(files, [rc, ab.RunSettings()])
+    cli = os.path.join(os.path.dirname(ab.__file__), "asgart-b200")
+    out = tmp_path / "both.json"
+    r = subprocess.run([cli, "-RCS", "--with-direct", "--out", str(out), str(fa)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    assert json.loads(out.read_text()) == want
