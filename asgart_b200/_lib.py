@@ -88,6 +88,7 @@ SYMBOLS = [
     "asgart_b200_build_index_group", "asgart_b200_dist_unique_id", "asgart_b200_ctx_dist_init", "asgart_b200_ctx_dist_shutdown",
     "asgart_b200_ctx_ingest_begin", "asgart_b200_ctx_ingest_fasta", "asgart_b200_ctx_ingest_file",
     "asgart_b200_ctx_ingest_finish", "asgart_b200_ctx_download_strand", "asgart_b200_run_files_passes",
+    "asgart_b200_ctx_build_index_trim", "asgart_b200_effective_trim",
 ]
 
 _lib = None
@@ -115,6 +116,8 @@ def load() -> C.CDLL:
         "asgart_b200_ctx_load_strand": (i32, [vp, vp, i64]),
         "asgart_b200_ctx_build_index": (i32, [vp]),
         "asgart_b200_ctx_set_index_bits": (i32, [vp, i32]),
+        "asgart_b200_ctx_build_index_trim": (i32, [vp, C.c_uint64, C.c_uint64]),
+        "asgart_b200_effective_trim": (i32, [C.c_uint64, C.c_uint64, i64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
         "asgart_b200_build_index_group": (i32, [C.POINTER(vp), i32]),
         "asgart_b200_dist_unique_id": (i32, [vp, i64]),
         "asgart_b200_ctx_dist_init": (i32, [vp, i32, i32, vp, i64]),

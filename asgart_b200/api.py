@@ -105,6 +105,13 @@ def r_divsufsort(dna, device: Optional[int] = None, index_bits: int = 0) -> np.n
     return sa
 
 
+def effective_trim(trim: Tuple[int, int], n_plus_1: int) -> Optional[Tuple[int, int]]:
+    """prepare_data's --trim validation (src/bin/asgart.rs:432-463): the effective (start, stop) or None when skipped."""
+    a, b = C.c_uint64(), C.c_uint64()
+    ok = _lib.load().asgart_b200_effective_trim(int(trim[0]), int(trim[1]), int(n_plus_1), C.byref(a), C.byref(b))
+    return (a.value, b.value) if ok else None
+
+
 def dist_unique_id() -> bytes:
     """Rank 0's id for Context.dist_init (send it to the other ranks, e.g. with torch.distributed.broadcast)."""
     L = _lib.load()
@@ -196,8 +203,16 @@ class Context:
     def set_index_bits(self, bits: int):
         self._check(self.L.asgart_b200_ctx_set_index_bits(self.h, bits))
 
-    def build_index(self):
-        self._check(self.L.asgart_b200_ctx_build_index(self.h))
+    def build_index(self, trim: Optional[Tuple[int, int]] = None):
+        """Suffix array + LUT. `trim` = the raw --trim values: validated like prepare_data does (src/bin/asgart.rs:432-463);
+        when they survive, the index covers strand[start..stop] only (src/bin/asgart.rs:142-147)."""
+        self.sa_len = self.n1
+        eff = effective_trim(trim, self.n1) if trim is not None else None
+        if eff is None:
+            self._check(self.L.asgart_b200_ctx_build_index(self.h))
+        else:
+            self._check(self.L.asgart_b200_ctx_build_index_trim(self.h, eff[0], eff[1]))
+            self.sa_len = eff[1] - eff[0] + 1
 
     def dist_init(self, rank: int, world: int, unique_id: bytes):
         """Join a group of `world` processes (one per GPU): build_index becomes a collective, sharded build."""
@@ -211,9 +226,10 @@ class Context:
         sa = np.ascontiguousarray(sa, dtype=np.int64)
         assert len(sa) == self.n1
         self._check(self.L.asgart_b200_ctx_upload_sa(self.h, _ptr(sa)))
+        self.sa_len = self.n1
 
     def download_sa(self) -> np.ndarray:
-        sa = np.empty(self.n1, dtype=np.int64)
+        sa = np.empty(getattr(self, "sa_len", self.n1) or self.n1, dtype=np.int64)
         self._check(self.L.asgart_b200_ctx_download_sa(self.h, _ptr(sa)))
         return sa
 

@@ -66,6 +66,7 @@ struct asgart_b200_ctx {
     cudaStream_t stream = nullptr;
     std::string err;
     u64 n1 = 0;
+    u64 sa_len = 0;    // entries of the suffix array: n1, or b - a + 1 for an index built with --trim (a, b)
     bool have_strand = false, have_index = false;
     int want_bits = 0, idx_bits = 0;
     DevBuf<u8> d_text;
@@ -292,6 +293,43 @@ void build_index_t(asgart_b200_ctx* ctx) {
     tlut.stop();
     ctx->st.ms_sa_build += tsa.ms() - hook.ms;
     ctx->st.ms_lut += tlut.ms() + hook.ms;
+}
+
+template <typename IdxT>
+void build_index_trim_t(asgart_b200_ctx* ctx, u64 a, u64 b) {
+    auto& ix = IxOf<IdxT>::get(ctx);
+    cudaStream_t s = ctx->stream;
+    EventTimer tsa(s), tlut(s);
+    tsa.start();
+    const u64 m1 = b - a + 1;
+    DevBuf<u8> sub(m1, s);
+    CUDA_CHECK(cudaMemcpyAsync(sub.p, ctx->d_text.p + a, b - a, cudaMemcpyDeviceToDevice, s));
+    CUDA_CHECK(cudaMemsetAsync(sub.p + (b - a), '$', 1, s));
+    ix.sa.alloc(m1, s);
+    SaStats ss;
+    ss.sort = &ctx->t_sort; ss.gather = &ctx->t_gather; ss.rank = &ctx->t_rank; ss.scatter = &ctx->t_scatter; ss.scatter_main = &ctx->t_scatter_main;
+    {
+        DevBuf<IdxT> rank(m1, s);
+        build_suffix_array<IdxT>(sub.p, m1, ix.sa.p, rank.p, s, &ss, nullptr);
+    }
+    if (a) {
+        add_offset_kernel<IdxT><<<unsigned(std::min<u64>(ceil_div(m1, 256), u64(kNumSMs) * 16)), 256, 0, s>>>(ix.sa.p, m1, IdxT(a));
+        KERNEL_CHECK();
+        count_launch();
+    }
+    ctx->st.sa_rounds = ss.rounds;
+    tsa.stop();
+    tlut.start();
+    ix.lut_lo.alloc(kLutSize, s);
+    ix.lut_hi.alloc(kLutSize, s);
+    ix.deep.release();
+    ix.deep_depth = 0;
+    lut_literal_kernel<IdxT><<<unsigned(ceil_div(kLutSize, 128)), 128, 0, s>>>(ctx->d_text.p, ctx->n1, ix.sa.p, m1, ix.lut_lo.p, ix.lut_hi.p);
+    KERNEL_CHECK();
+    count_launch();
+    tlut.stop();
+    ctx->st.ms_sa_build += tsa.ms();
+    ctx->st.ms_lut += tlut.ms();
 }
 
 template <typename T>
@@ -1000,9 +1038,41 @@ int32_t asgart_b200_ctx_build_index(asgart_b200_ctx* ctx) {
         if (ctx->idx_bits == 32) { ctx->ix64 = Index64(); build_index_t<u32>(ctx); }
         else { ctx->ix32 = Index32(); build_index_t<u64>(ctx); }
         CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        ctx->sa_len = ctx->n1;
         ctx->have_index = true;
         return ASGART_B200_OK;
     });
+}
+
+// --trim (src/bin/asgart.rs:142-147): suffix array of strand[a..b]+'$' shifted by a; LUT by the reference's own bisection
+// over the whole strand (lut_literal_kernel); no deep table, so every probe takes the literal search (Q9).
+int32_t asgart_b200_ctx_build_index_trim(asgart_b200_ctx* ctx, uint64_t a, uint64_t b) {
+    return guarded(ctx, [&]() -> int32_t {
+        if (!ctx->have_strand) return fail(ctx, ASGART_B200_ESTATE, "build_index_trim before load_strand");
+        if (ctx->group && ctx->group->world > 1) return fail(ctx, ASGART_B200_ESTATE, "--trim builds on one device");
+        if (!(a < b) || b > ctx->n1 - 1) return fail(ctx, ASGART_B200_EINVAL, "trim needs start < stop <= strand length (see asgart_b200_effective_trim)");
+        ctx->have_index = false;
+        ctx->idx_bits = pick_bits(ctx);
+        if (ctx->idx_bits == 32 && ctx->n1 >= 0xFFFFFFFEull) return fail(ctx, ASGART_B200_EINVAL, "32-bit indices need n+1 < 2^32-2");
+        if (ctx->idx_bits == 32) { ctx->ix64 = Index64(); build_index_trim_t<u32>(ctx, a, b); }
+        else { ctx->ix32 = Index32(); build_index_trim_t<u64>(ctx, a, b); }
+        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        ctx->sa_len = b - a + 1;
+        ctx->have_index = true;
+        return ASGART_B200_OK;
+    });
+}
+
+// prepare_data's validation of --trim (src/bin/asgart.rs:432-463; n_plus_1 = strand length with '$'): stop is clamped to
+// the last base; returns 1 and the effective values, or 0 when the reference skips trimming.
+int32_t asgart_b200_effective_trim(uint64_t start, uint64_t stop, int64_t n_plus_1, uint64_t* eff_start, uint64_t* eff_stop) {
+    if (n_plus_1 < 1) return 0;
+    const uint64_t len = uint64_t(n_plus_1);
+    if (stop >= len) stop = len - 1;
+    if (stop <= start || start >= len) return 0;
+    if (eff_start) *eff_start = start;
+    if (eff_stop) *eff_stop = stop;
+    return 1;
 }
 
 // ---- sharded index build ------------------------------------------------------------------------------------
@@ -1093,6 +1163,7 @@ int32_t asgart_b200_ctx_upload_sa(asgart_b200_ctx* ctx, const int64_t* SA) {
             build_lut<u64>(ctx);
         }
         CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        ctx->sa_len = ctx->n1;
         ctx->have_index = true;
         return ASGART_B200_OK;
     });
@@ -1102,8 +1173,8 @@ int32_t asgart_b200_ctx_download_sa(asgart_b200_ctx* ctx, int64_t* SA) {
     return guarded(ctx, [&]() -> int32_t {
         if (!ctx->have_index) return fail(ctx, ASGART_B200_ESTATE, "download_sa before build_index");
         if (!SA) return fail(ctx, ASGART_B200_EINVAL, "null SA");
-        if (ctx->idx_bits == 32) download_as_i64<u32>(ctx->ix32.sa.p, SA, ctx->n1, ctx->stream);
-        else download_as_i64<u64>(ctx->ix64.sa.p, SA, ctx->n1, ctx->stream);
+        if (ctx->idx_bits == 32) download_as_i64<u32>(ctx->ix32.sa.p, SA, ctx->sa_len, ctx->stream);
+        else download_as_i64<u64>(ctx->ix64.sa.p, SA, ctx->sa_len, ctx->stream);
         return ASGART_B200_OK;
     });
 }
@@ -1112,6 +1183,7 @@ int32_t asgart_b200_ctx_check_sa(asgart_b200_ctx* ctx, int64_t* n_bad) {
     return guarded(ctx, [&]() -> int32_t {
         if (!ctx->have_index) return fail(ctx, ASGART_B200_ESTATE, "check_sa before build_index");
         if (!n_bad) return fail(ctx, ASGART_B200_EINVAL, "null output");
+        if (ctx->sa_len != ctx->n1) return fail(ctx, ASGART_B200_ESTATE, "check_sa: the index was built with --trim (it is not a suffix array of the strand)");
         if (ctx->idx_bits == 32) *n_bad = check_sa_t<u32>(ctx); else *n_bad = check_sa_t<u64>(ctx);
         return ASGART_B200_OK;
     });

@@ -1,6 +1,6 @@
 // cli.cpp — `asgart-b200 FILES... [flags]`: the command line of src/bin/asgart.rs:564-631 for the duplication-search
 // path, driving the device operator through the C ABI and writing the same JSON file the reference writes
-// (naming rule src/bin/asgart.rs:695-719). --trim is outside the path.
+// (naming rule src/bin/asgart.rs:695-719).
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -19,6 +19,7 @@ static void usage() {
             "  -R, --reverse               Search for reversed duplications\n"
             "  -C, --complement            Search for complemented duplications\n"
             "  -S, --skip-masked           Ignore soft-masked repeated zones (lowercased regions)\n"
+            "      --trim <START> <STOP>   Trim the first strand: only duplications whose right arm lies in [START, STOP) are searched\n"
             "      --prefix <P>            prefix to prepend to the default output file name\n"
             "      --out <FILE>            set the output file name\n"
             "      --device <N>            CUDA device [default: 0]\n"
@@ -48,7 +49,7 @@ int main(int argc, char** argv) {
         else if (a == "--threads" || a == "--chunk-size") need(i);
         else if (a == "--compute-score") st.compute_score = 1;
         else if (a == "--with-direct") with_direct = 1;
-        else if (a == "--trim") { fprintf(stderr, "asgart-b200: %s is outside the accelerated path\n", a.c_str()); return 2; }
+        else if (a == "--trim") { st.has_trim = 1; st.trim_a = strtoull(need(i), nullptr, 10); st.trim_b = strtoull(need(i), nullptr, 10); }
         else if (a == "-h" || a == "--help") { usage(); return 0; }
         else if (a == "--reverse") st.reverse = 1;
         else if (a == "--complement") st.complement = 1;

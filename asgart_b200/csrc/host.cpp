@@ -601,6 +601,9 @@ char* asgart_b200_run_files_passes(const char* files, const asgart_b200_settings
     for (int32_t i = 1; i < n_passes; ++i)
         if ((passes[i].skip_masked != 0) != (passes[0].skip_masked != 0))
             return failf("passes over one index must agree on skip_masked (it changes the strand)");
+    for (int32_t i = 1; i < n_passes; ++i)
+        if (passes[i].has_trim != passes[0].has_trim || passes[i].trim_a != passes[0].trim_a || passes[i].trim_b != passes[0].trim_b)
+            return failf("passes over one index must agree on trim (it changes the index)");
     const std::vector<std::string> fl = split_lines(files);
     if (fl.empty()) return failf("no input files");
     asgart_b200_ctx* ctx = nullptr;
@@ -616,7 +619,14 @@ char* asgart_b200_run_files_passes(const char* files, const asgart_b200_settings
     } else {
         std::vector<uint64_t> fam_off{0};
         std::vector<asgart_b200_protosd> sds;
-        rc = asgart_b200_ctx_build_index(ctx);
+        // --trim (bin/asgart.rs:432-463 validation, :142-147 index); the raw values stay in the settings block of the JSON
+        uint64_t ta = 0, tb = 0;
+        int64_t n_plus_1 = 0;
+        asgart_b200_prepared_strand(p, &n_plus_1);
+        if (passes[0].has_trim && asgart_b200_effective_trim(passes[0].trim_a, passes[0].trim_b, n_plus_1, &ta, &tb))
+            rc = asgart_b200_ctx_build_index_trim(ctx, ta, tb);
+        else
+            rc = asgart_b200_ctx_build_index(ctx);
         for (int32_t i = 0; !rc && i < n_passes; ++i) {
             asgart_b200_result* res = nullptr;
             rc = asgart_b200_ctx_search(ctx, p->chunks.data(), int64_t(p->chunks.size()), &passes[i],

@@ -55,8 +55,9 @@ typedef struct asgart_b200_partial asgart_b200_partial;
 
 /* mirror of RunSettings (src/structs.rs:36-58). max_gap_size is ALREADY gap_size + probe_size
  * (src/bin/asgart.rs:681). threads_count has no meaning here; compute_score is the
- * post-step bit ASGART_B200_POST_COMPUTE_SCORE. trim is carried for the JSON
- * settings block only (--trim is out of scope). */
+ * post-step bit ASGART_B200_POST_COMPUTE_SCORE. trim holds the RAW command-line values (they go into the
+ * JSON settings block as they are, src/bin/asgart.rs:691); asgart_b200_run_files builds the trimmed index from them
+ * (asgart_b200_ctx_build_index_trim), ctx_search itself does not look at them. */
 typedef struct asgart_b200_settings {
     uint64_t probe_size;
     uint32_t max_gap_size;
@@ -112,6 +113,17 @@ ASGART_B200_API const char *asgart_b200_ctx_last_error(const asgart_b200_ctx *ct
 ASGART_B200_API int32_t asgart_b200_ctx_load_strand(asgart_b200_ctx *ctx, const uint8_t *T, int64_t n_plus_1);
 /* Suffix array (replaces r_divsufsort, :149) + 8-mer LUT (replaces Searcher::new, :151; src/searcher.rs:99-143) */
 ASGART_B200_API int32_t asgart_b200_ctx_build_index(asgart_b200_ctx *ctx);
+/* The index of a `--trim start stop` run (src/bin/asgart.rs:142-147): suffix array of strand[start..stop] + '$' with every
+ * entry shifted by start (stop - start + 1 entries; ctx_download_sa returns that many), while the LUT and every
+ * comparison of the search read the WHOLE strand, exactly as the reference does (near `stop` the array is not
+ * sorted for what it is compared with, so the LUT comes from the reference's own sa_search bisection run step for step on
+ * the device, and every probe takes the literal lock-step search). Only duplications whose right arm lies inside the
+ * slice are found; chunks are NOT trimmed. start < stop <= n: pass the values through asgart_b200_effective_trim first,
+ * which restates prepare_data's clamping (src/bin/asgart.rs:432-463) — it returns 0 when the reference skips trimming
+ * (then call ctx_build_index). One device only. */
+ASGART_B200_API int32_t asgart_b200_ctx_build_index_trim(asgart_b200_ctx *ctx, uint64_t start, uint64_t stop);
+ASGART_B200_API int32_t asgart_b200_effective_trim(uint64_t start, uint64_t stop, int64_t n_plus_1, uint64_t *eff_start,
+                                                   uint64_t *eff_stop);
 /* Sharded index build (the reference builds its suffix array on one thread, src/bin/asgart.rs:473-479, and has no
  * multi-device mode): the members of a group split the suffixes by initial-key range, keep the rank array block-cyclic
  * in each other's memory (peer stores / loads over NVLink) and end with the whole index on every member, bit-identical

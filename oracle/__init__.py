@@ -49,10 +49,11 @@ class Settings(C.Structure):
 
 
 def make_settings(probe_size=20, gap_size=100, min_length=1000, max_cardinality=500, reverse=False,
-                  complement=False, skip_masked=False, compute_score=False) -> Settings:
-    """RunSettings as bin/asgart.rs:679-692 builds it: max_gap_size = gap_size + probe_size."""
+                  complement=False, skip_masked=False, compute_score=False, trim=None) -> Settings:
+    """RunSettings as bin/asgart.rs:679-692 builds it: max_gap_size = gap_size + probe_size; trim = the raw CLI pair."""
+    t = trim or (0, 0)
     return Settings(probe_size, gap_size + probe_size, int(reverse), int(complement), int(skip_masked), min_length,
-                    max_cardinality, 0, int(compute_score), 0, 0)
+                    max_cardinality, int(trim is not None), int(compute_score), int(t[0]), int(t[1]))
 
 
 _lib = None
@@ -80,6 +81,13 @@ def lib() -> C.CDLL:
         L.oracle_search.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(Settings),
                                     C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.oracle_search.restype = C.c_void_p
+        L.oracle_search_trim.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
+                                         C.POINTER(Settings), C.c_int, C.c_int]
+        L.oracle_search_trim.restype = C.c_void_p
+        L.oracle_sa_search_literal.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]
+        L.oracle_sa_search_literal.restype = C.c_int64
+        L.oracle_effective_trim.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p]
+        L.oracle_effective_trim.restype = C.c_int
         L.oracle_result_from_arrays.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
         L.oracle_result_from_arrays.restype = C.c_void_p
         L.oracle_result_post.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int]
@@ -309,6 +317,47 @@ def search(text_with_dollar, sa, chunks: Sequence[Tuple[int, int]], settings: Se
     )
 
 
+def effective_trim(trim: Tuple[int, int], strand_len_with_dollar: int) -> Optional[Tuple[int, int]]:
+    """prepare_data's validation of --trim (bin/asgart.rs:432-463): None when the reference skips trimming."""
+    out = np.zeros(2, dtype=np.uint64)
+    ok = lib().oracle_effective_trim(int(trim[0]), int(trim[1]), int(strand_len_with_dollar), _ptr(out))
+    return (int(out[0]), int(out[1])) if ok else None
+
+
+def trimmed_suffix_array(text_with_dollar, trim: Tuple[int, int]) -> np.ndarray:
+    """bin/asgart.rs:142-147: suffix array of strand[a..b] + '$', every entry shifted by a."""
+    t = as_strand(text_with_dollar)
+    a, b = trim
+    sub = np.concatenate([t[a:b], np.frombuffer(b"$", dtype=np.uint8)])
+    return best_suffix_array(sub) + a
+
+
+def sa_search_literal(text, pattern: bytes, sa: np.ndarray) -> Tuple[int, int]:
+    """sa_search (libdivsufsort/lib/utils.c:282-349) step for step: (first index, count)."""
+    t = as_strand(text)
+    p = as_strand(pattern)
+    sa = np.ascontiguousarray(sa, dtype=np.int64)
+    idx = C.c_int64()
+    n = lib().oracle_sa_search_literal(_ptr(t), len(t), _ptr(p), len(p), _ptr(sa), len(sa), C.byref(idx))
+    return idx.value, n
+
+
+def search_trim(text_with_dollar, trim: Tuple[int, int], chunks: Sequence[Tuple[int, int]], settings: Settings,
+                post_mask: int = POST_ALL, threads: int = 1) -> Families:
+    """SearchDuplications::run with --trim (bin/asgart.rs:137-258): the suffix array covers strand[a..b] only, the LUT
+    and every comparison read the whole strand. `trim` is the effective one (see effective_trim)."""
+    t = as_strand(text_with_dollar)
+    sa = np.ascontiguousarray(trimmed_suffix_array(t, trim), dtype=np.int64)
+    ch = np.ascontiguousarray(np.array(chunks, dtype=np.uint64).reshape(-1, 2))
+    h = lib().oracle_search_trim(_ptr(t), len(t), _ptr(sa), len(sa), _ptr(ch), len(ch), C.byref(settings), post_mask, threads)
+    if not h:
+        raise RefPanic("the reference panics on this input (ComputeScore)")
+    try:
+        return _copy_result(h)
+    finally:
+        lib().oracle_result_free(h)
+
+
 def post_steps(fam: Families, text_with_dollar, post_mask: int) -> Families:
     t = as_strand(text_with_dollar)
     off = np.ascontiguousarray(fam.fam_offsets, dtype=np.int64)
@@ -387,7 +436,10 @@ class Prepared:
 def run_files(files: Sequence[str], settings: Settings, threads: int = 1) -> str:
     """The whole reference pipeline on FASTA files -> JSON text (bin/asgart.rs:731-822 + exporters.rs:12-25)."""
     prep = Prepared.from_files(files, bool(settings.skip_masked))
-    sa = best_suffix_array(prep.strand)
     mask = POST_ALL | (POST_COMPUTE_SCORE if settings.compute_score else 0)   # bin/asgart.rs:744-746
+    eff = effective_trim((settings.trim_a, settings.trim_b), len(prep.strand)) if settings.has_trim else None
+    if eff is not None:                                                       # bin/asgart.rs:142-147
+        return prep.to_json(settings, search_trim(prep.strand, eff, prep.chunks, settings, mask, threads))
+    sa = best_suffix_array(prep.strand)
     out = search(prep.strand, sa, prep.chunks, settings, mask, threads)
     return prep.to_json(settings, out.families)

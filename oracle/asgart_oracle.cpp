@@ -144,6 +144,66 @@ int64_t sa_searchb_restated(const uint8_t* T, int64_t Tsize, const uint8_t* P, i
 }
 
 // ---------------------------------------------------------------------------------------------
+// The same search, step for step (utils.c:244-255 _compare, :282-349 sa_search): one bisection until a suffix matches P,
+// then a lower-bound bisection of the left part and an upper-bound bisection of the right part, every comparison
+// skipping the prefix already known to match (`match` counters). Identical to the restatement above whenever SA is
+// sorted for T; it differs when it is not — `--trim` hands a suffix array of strand[a..b]+'$' (shifted by a) together
+// with the WHOLE strand (bin/asgart.rs:142-155), so the last suffixes before b are compared beyond the
+// '$' they were sorted with. Checked against the reference's own sa_searchb64 (tests/test_oracle_ref.py).
+// ---------------------------------------------------------------------------------------------
+int compare_skip(const uint8_t* T, int64_t Tsize, const uint8_t* P, int64_t Psize, int64_t suf, int64_t* match) {
+    int64_t i = suf + *match, j = *match;
+    int r = 0;
+    while (i < Tsize && j < Psize) {
+        r = int(T[i]) - int(P[j]);
+        if (r != 0) break;
+        ++i; ++j;
+    }
+    *match = j;
+    if (r != 0) return r;
+    return j != Psize ? -1 : 0;
+}
+
+int64_t sa_search_literal(const uint8_t* T, int64_t Tsize, const uint8_t* P, int64_t Psize, const int64_t* SA,
+                          int64_t SAsize, int64_t* idx) {
+    *idx = -1;
+    if (Tsize == 0 || SAsize == 0) return 0;
+    if (Psize == 0) { *idx = 0; return SAsize; }
+    int64_t i = 0, j = 0, k = 0, lmatch = 0, rmatch = 0;
+    int64_t size = SAsize, half = size >> 1;
+    while (size > 0) {
+        int64_t match = std::min(lmatch, rmatch);
+        const int r = compare_skip(T, Tsize, P, Psize, SA[i + half], &match);
+        if (r < 0) {
+            i += half + 1;
+            half -= (size & 1) ^ 1;
+            lmatch = match;
+        } else if (r > 0) {
+            rmatch = match;
+        } else {
+            int64_t lsize = half, rsize = size - half - 1;
+            j = i; k = i + half + 1;
+            int64_t llmatch = lmatch, lrmatch = match;
+            for (int64_t h = lsize >> 1; lsize > 0; lsize = h, h >>= 1) {       // first suffix >= P in the left part
+                int64_t m = std::min(llmatch, lrmatch);
+                if (compare_skip(T, Tsize, P, Psize, SA[j + h], &m) < 0) { j += h + 1; h -= (lsize & 1) ^ 1; llmatch = m; }
+                else lrmatch = m;
+            }
+            int64_t rlmatch = match, rrmatch = rmatch;
+            for (int64_t h = rsize >> 1; rsize > 0; rsize = h, h >>= 1) {       // first suffix > P in the right part
+                int64_t m = std::min(rlmatch, rrmatch);
+                if (compare_skip(T, Tsize, P, Psize, SA[k + h], &m) <= 0) { k += h + 1; h -= (rsize & 1) ^ 1; rlmatch = m; }
+                else rrmatch = m;
+            }
+            break;
+        }
+        size = half; half >>= 1;
+    }
+    *idx = (k - j) > 0 ? j : i;
+    return k - j;
+}
+
+// ---------------------------------------------------------------------------------------------
 // superslice::Ext::equal_range_by (third-party crate, version constraint "1.0", source not in the
 // reference tree; call site searcher.rs:164). Published algorithm: lower and upper bound searched in
 // lock step with the same halving sequence; `size -= half` (not size = half), one final probe each.
@@ -181,14 +241,16 @@ struct Searcher {
     }
 
     // searcher.rs:99-143: all 5^8 8-mers over ALPHABET, each through sa_searchb64 on the whole SA
-    Searcher(const uint8_t* dna, usize dna_len, const int64_t* sa, usize sa_len, usize off) : offset(off) {
+    // `literal`: sa_search step for step (needed when sa is not sorted for dna: --trim)
+    Searcher(const uint8_t* dna, usize dna_len, const int64_t* sa, usize sa_len, usize off, bool literal = false) : offset(off) {
         cache.reserve(400000);
         uint8_t p[8];
         int d[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         for (;;) {
             for (int j = 0; j < 8; ++j) p[j] = ALPHABET[d[j]];
             int64_t out = 0;
-            int64_t count = sa_searchb_restated(dna, int64_t(dna_len), p, 8, sa, 0, int64_t(sa_len), &out);
+            int64_t count = literal ? sa_search_literal(dna, int64_t(dna_len), p, 8, sa, int64_t(sa_len), &out)
+                                    : sa_searchb_restated(dna, int64_t(dna_len), p, 8, sa, 0, int64_t(sa_len), &out);
             cache[indexize(p)] = {usize(out), usize(out) + usize(count)};
             int j = 7;  // odometer: last letter varies fastest, like the nested loops :108-115
             while (j >= 0 && ++d[j] == 5) { d[j] = 0; --j; }
@@ -358,9 +420,10 @@ std::vector<Family> automaton_search_duplications(const uint8_t* needle, usize n
 std::vector<Family> search_duplications_step(const uint8_t* strand, usize strand_len, const int64_t* sa,
                                              const std::vector<std::pair<usize, usize>>& chunks,
                                              const RunSettings& settings, int threads, double* t_lut,
-                                             double* t_search, Counters* ctr) {
+                                             double* t_search, Counters* ctr, usize sa_len = 0) {
     auto t0 = std::chrono::steady_clock::now();
-    Searcher searcher(strand, strand_len, sa, strand_len, 0);  // :151-155
+    // sa_len != 0: --trim, sa is the (shifted) suffix array of a slice of the strand (:142-147)
+    Searcher searcher(strand, strand_len, sa, sa_len ? sa_len : strand_len, 0, sa_len != 0);  // :151-155
     auto t1 = std::chrono::steady_clock::now();
 
     std::vector<std::vector<Family>> results(chunks.size());
@@ -537,7 +600,7 @@ void step_sort(std::vector<Family>& fams) {  // :53-65 (sort_by is stable)
 
 // ---------------------------------------------------------------------------------------------
 // bin/asgart.rs:273-471 prepare_data: read_fasta (:278-313), find_chunks_to_process (:317-366),
-// concatenation + '$' (:375-430). --trim is out of scope.
+// concatenation + '$' (:375-430). --trim: validation in oracle_effective_trim, search in oracle_search_trim.
 // ---------------------------------------------------------------------------------------------
 struct Prepared {
     std::string file_names;
@@ -887,6 +950,39 @@ void* oracle_search(const uint8_t* T, int64_t n1, const int64_t* SA, const uint6
         counters[3] = ctr.skipped_card; counters[4] = ctr.matches; counters[5] = ctr.alg_bytes;
     }
     return r;
+}
+
+// the same with --trim: SA = suffix array of strand[a..b]+'$' shifted by a (sa_len = b - a + 1 entries), built by the caller
+void* oracle_search_trim(const uint8_t* T, int64_t n1, const int64_t* SA, int64_t sa_len, const uint64_t* chunks,
+                         int64_t n_chunks, const oracle_settings* s, int post_mask, int threads) {
+    RunSettings st = to_settings(s);
+    std::vector<std::pair<usize, usize>> ch;
+    for (int64_t i = 0; i < n_chunks; ++i) ch.push_back({usize(chunks[2 * i]), usize(chunks[2 * i + 1])});
+    Result* r = new Result();
+    r->fams = search_duplications_step(T, usize(n1), SA, ch, st, threads, nullptr, nullptr, nullptr, usize(sa_len));
+    if (post_mask & 1) step_filter_ns(r->fams, T);
+    if (post_mask & 2) step_reorder(r->fams);
+    if (post_mask & 4) step_reduce_overlap(r->fams);
+    if (post_mask & 16) {
+        try { step_compute_score(r->fams, T, usize(n1)); } catch (const RefPanic&) { delete r; return nullptr; }
+    }
+    if (post_mask & 8) step_sort(r->fams);
+    return r;
+}
+
+int64_t oracle_sa_search_literal(const uint8_t* T, int64_t Tsize, const uint8_t* P, int64_t Psize, const int64_t* SA,
+                                 int64_t SAsize, int64_t* idx) {
+    return sa_search_literal(T, Tsize, P, Psize, SA, SAsize, idx);
+}
+
+// prepare_data's validation of --trim (bin/asgart.rs:432-463; strand_len includes the '$'): returns 0 when trimming is
+// skipped, else 1 with the effective (start, stop)
+int oracle_effective_trim(uint64_t shift, uint64_t stop, uint64_t strand_len, uint64_t* out) {
+    if (stop >= strand_len) stop = strand_len - 1;
+    if (stop <= shift) return 0;
+    if (shift >= strand_len) return 0;
+    out[0] = shift; out[1] = stop;
+    return 1;
 }
 
 void* oracle_result_from_arrays(const int64_t* fam_offsets, int64_t n_fam, const uint64_t* fields,

@@ -81,6 +81,47 @@ def test_lut_matches_reference_sa_searchb64():
     assert int((hi2 - lo2).sum()) == (len(t2) - 1) - 7
 
 
+@needs_ref
+def test_literal_sa_search_matches_reference_on_a_trimmed_index():
+    """--trim hands sa_searchb64 the suffix array of strand[a..b]+'$' (shifted) together with the WHOLE strand
+    (bin/asgart.rs:142-155): near b the array is not sorted for the text it is compared with, and only the literal
+    bisection reproduces the reference. All non-empty 5^8 keys, a sample of empty ones and random longer patterns."""
+    from tests import cases
+    t = oracle.as_strand(cases.stress_text(17, n=30000, n_dups=12))
+    t = np.concatenate([t, np.frombuffer(b"$", dtype=np.uint8)]) if t[-1] != ord("$") else t
+    R = oracle.ref()
+    rng = np.random.default_rng(1)
+    letters = np.frombuffer(b"ATGCN", dtype=np.uint8)
+    differs = 0
+    for (a, b) in [(0, len(t) - 1), (1000, 20000), (12345, 12399), (29000, len(t) - 1), (7, 8), (5000, 5009)]:
+        sa = np.ascontiguousarray(oracle.trimmed_suffix_array(t, (a, b)), dtype=np.int64)
+        assert len(sa) == b - a + 1 and sa[0] == b
+        pats = [bytes(t[i:i + 8]) for i in range(max(a, b - 40), min(b + 9, len(t) - 8))]          # around the cut
+        pats += [bytes(t[i:i + l]) for i, l in zip(rng.integers(a, max(a + 1, b - 1), 400), rng.integers(1, 25, 400))]
+        pats += [bytes(rng.choice(letters, size=8)) for _ in range(1500)]
+        for p in pats:
+            if b"$" in p or len(p) == 0:
+                continue
+            pa = np.frombuffer(p, dtype=np.uint8)
+            out = C.c_int64()
+            cnt = R.sa_searchb64(t.ctypes.data, len(t), pa.ctypes.data, len(pa), sa.ctypes.data, len(sa), C.byref(out), 0, len(sa))
+            assert oracle.sa_search_literal(t, p, sa) == (out.value, cnt), (a, b, p)
+            i2 = C.c_int64()
+            c2 = oracle.lib().oracle_sa_searchb(t.ctypes.data, len(t), pa.ctypes.data, len(pa), sa.ctypes.data, len(sa), C.byref(i2), 0, len(sa))
+            differs += (i2.value, c2) != (out.value, cnt)
+    assert differs > 0     # the plain lower/upper-bound restatement is NOT enough here: the literal one is needed
+
+
+def test_effective_trim():
+    """prepare_data's --trim validation (bin/asgart.rs:432-463); strand length includes the '$'."""
+    assert oracle.effective_trim((5, 100), 50) == (5, 49)
+    assert oracle.effective_trim((5, 49), 50) == (5, 49)
+    assert oracle.effective_trim((5, 5), 50) is None and oracle.effective_trim((9, 3), 50) is None
+    assert oracle.effective_trim((49, 1000), 50) is None          # stop clamps to 49 <= shift
+    assert oracle.effective_trim((60, 1000), 50) is None
+    assert oracle.effective_trim((0, 1), 50) == (0, 1)
+
+
 def test_golden_fixtures():
     """Fixtures generated from the reference's C library (tests/golden/make_golden.py); runs without oracle/_ref."""
     with open(os.path.join(GOLD, "sa_golden.json")) as f:
