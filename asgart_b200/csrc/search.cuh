@@ -344,7 +344,7 @@ __device__ __forceinline__ void probe_account(const ProbeParams<IdxT>& P, const 
     }
 }
 
-constexpr int kProbeLinear = 8;  // deep buckets up to this size are compared in one go instead of bisected
+// deep buckets up to LINEAR suffixes are compared in one go instead of bisected (template parameter of the kernel)
 
 // One lane per probe position. Probes whose first deep_depth bases are all ACGT start from the deep table's bucket
 // (a few suffixes) and compare them all at once; the equal range of a monotone comparator does not depend on how it is
@@ -352,8 +352,8 @@ constexpr int kProbeLinear = 8;  // deep buckets up to this size are compared in
 // other probe (N among the first bases, flagged bucket, no deep table) takes probe_literal, in this kernel when
 // P.deferred is null and in probe_deferred_kernel otherwise (keeps the long bisections out of the short warps); probes
 // with long match intervals leave the filter pass to that kernel as well.
-template <typename IdxT>
-__global__ void __launch_bounds__(256) probe_search_kernel(const ProbeParams<IdxT> P) {
+template <typename IdxT, int kProbeLinear, int MINB>
+__global__ void __launch_bounds__(256, MINB) probe_search_kernel(const ProbeParams<IdxT> P) {
     const u64 g = P.p_begin + u64(blockIdx.x) * blockDim.x + threadIdx.x;
     const bool in_range = g < P.p_end;
     ProbeState S;
