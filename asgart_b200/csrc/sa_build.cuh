@@ -106,6 +106,159 @@ __global__ void __launch_bounds__(kInitThreads) init_keys_kernel(const u8* __res
 }
 
 
+// ---- first re-ranking (step 2): group heads, rank by sorted position and the two work lists, from the sorted initial keys ----
+// The generic flag scan (scan.cuh) spends ~80 (reduce) + ~160 (output) instructions per element on this pass — at 3.1 G
+// suffixes it is bound by issue slots, not by HBM. Here one thread owns 8 consecutive keys (four 128-bit loads), the
+// flags of its keys need two neighbour keys only, and the scan state is three words per thread:
+//   latest head inside the tile (1-based, 0 = none)   -> running maximum
+//   #unsorted ordinary | #unsorted pure << 16          -> running sums   (pure: all p0 symbols equal, the run round's share)
+//   #unsorted ordinary heads                           -> running sum
+constexpr int kHpThreads = 256;
+constexpr int kHpItems = 8;
+constexpr int kHpTile = kHpThreads * kHpItems;
+
+struct HpThreadAcc {
+    u32 head1, cd, e;
+    HpThreadAcc() = default;
+    __host__ __device__ explicit HpThreadAcc(int) : head1(0), cd(0), e(0) {}
+};
+struct HpThreadOp {
+    __device__ __forceinline__ HpThreadAcc operator()(const HpThreadAcc& x, const HpThreadAcc& y) const {
+        HpThreadAcc r(0);
+        r.head1 = x.head1 > y.head1 ? x.head1 : y.head1;
+        r.cd = x.cd + y.cd;
+        r.e = x.e + y.e;
+        return r;
+    }
+};
+struct HpTileAcc {   // per tile / grand total: head1 = 1-based index (inside the member's piece) of the latest head
+    u64 head1, c, d, e;
+    HpTileAcc() = default;
+    __host__ __device__ explicit HpTileAcc(int) : head1(0), c(0), d(0), e(0) {}
+};
+struct HpTileOp {
+    __device__ __forceinline__ HpTileAcc operator()(const HpTileAcc& x, const HpTileAcc& y) const {
+        HpTileAcc r(0);
+        r.head1 = x.head1 > y.head1 ? x.head1 : y.head1;
+        r.c = x.c + y.c; r.d = x.d + y.d; r.e = x.e + y.e;
+        return r;
+    }
+};
+
+// this thread's 8 keys, its flag masks (bit j = key j) and its summary
+struct HpThread {
+    u64 k[kHpItems];
+    u64 i0;
+    u32 valid, head, unsorted, pure;
+};
+
+__device__ __forceinline__ void hp_load(const u64* __restrict__ kk, u64 n, u64 rep_unit, u64 sym_mask, HpThread& t) {
+    t.i0 = u64(blockIdx.x) * kHpTile + u64(threadIdx.x) * kHpItems;
+    const u32 cnt = t.i0 >= n ? 0u : u32(n - t.i0 < u64(kHpItems) ? n - t.i0 : u64(kHpItems));
+    t.valid = (1u << cnt) - 1u;
+    t.head = t.unsorted = t.pure = 0;
+    if (cnt == 0) return;
+    if (cnt == kHpItems) {
+        const ulonglong2* p = reinterpret_cast<const ulonglong2*>(kk + t.i0);
+#pragma unroll
+        for (int q = 0; q < kHpItems / 2; ++q) { const ulonglong2 v = p[q]; t.k[2 * q] = v.x; t.k[2 * q + 1] = v.y; }
+    } else {
+#pragma unroll
+        for (int j = 0; j < kHpItems; ++j) t.k[j] = u32(j) < cnt ? kk[t.i0 + j] : 0;
+    }
+    const bool has_prev = t.i0 > 0, has_next = t.i0 + cnt < n;
+    const u64 prev = has_prev ? kk[t.i0 - 1] : 0, next = has_next ? kk[t.i0 + cnt] : 0;
+    u32 tail = 0;
+#pragma unroll
+    for (int j = 0; j < kHpItems; ++j) {
+        if (u32(j) < cnt) {
+            const u64 cur = t.k[j];
+            const bool hd = j == 0 ? (!has_prev || prev != cur) : (t.k[j - 1] != cur);
+            const bool tl = u32(j) + 1 == cnt ? (!has_next || next != cur) : (t.k[j + 1] != cur);
+            t.head |= u32(hd) << j;
+            tail |= u32(tl) << j;
+            t.pure |= u32(cur == (cur & sym_mask) * rep_unit) << j;
+        }
+    }
+    t.unsorted = ~(t.head & tail) & t.valid;
+}
+
+__device__ __forceinline__ HpThreadAcc hp_thread_acc(const HpThread& t) {
+    HpThreadAcc a(0);
+    a.head1 = t.head ? u32(threadIdx.x) * kHpItems + (31 - __clz(t.head)) + 1 : 0u;
+    const u32 ord = t.unsorted & ~t.pure;
+    a.cd = u32(__popc(ord)) | (u32(__popc(t.unsorted & t.pure)) << 16);
+    a.e = u32(__popc(ord & t.head));
+    return a;
+}
+
+__global__ void __launch_bounds__(kHpThreads) hp_reduce_kernel(const u64* __restrict__ kk, u64 n, u64 rep_unit, u64 sym_mask,
+                                                               HpTileAcc* __restrict__ tile_acc) {
+    __shared__ HpThreadAcc sm[32];
+    HpThread t;
+    hp_load(kk, n, rep_unit, sym_mask, t);
+    HpThreadAcc total;
+    block_exclusive_scan(hp_thread_acc(t), HpThreadOp(), total, sm);
+    if (threadIdx.x == 0) {
+        HpTileAcc r(0);
+        r.head1 = total.head1 ? u64(blockIdx.x) * kHpTile + total.head1 : 0;
+        r.c = total.cd & 0xffffu; r.d = total.cd >> 16; r.e = total.e;
+        tile_acc[blockIdx.x] = r;
+    }
+}
+
+// rpos[i] = b0 + index of the head of i's group; unsorted suffixes go to the ordinary list (ga, ia; hsa = list index of every
+// group's first entry) or, when their p0 symbols are all equal, to the run round's list (gs, is)
+template <typename IdxT>
+__global__ void __launch_bounds__(kHpThreads) hp_emit_kernel(const u64* __restrict__ kk, const IdxT* __restrict__ vv, u64 n, u64 rep_unit,
+                                                             u64 sym_mask, const HpTileAcc* __restrict__ tile_pre, IdxT b0,
+                                                             IdxT* __restrict__ rpos, IdxT* __restrict__ ga, IdxT* __restrict__ ia,
+                                                             IdxT* __restrict__ hsa, IdxT* __restrict__ gs, IdxT* __restrict__ is) {
+    __shared__ HpThreadAcc sm[32];
+    HpThread t;
+    hp_load(kk, n, rep_unit, sym_mask, t);
+    HpThreadAcc total;
+    const HpThreadAcc exc = block_exclusive_scan(hp_thread_acc(t), HpThreadOp(), total, sm);
+    if (t.valid == 0) return;
+    const HpTileAcc pre = tile_pre[blockIdx.x];
+    const u64 tile0 = u64(blockIdx.x) * kHpTile;
+    u64 head1 = exc.head1 ? tile0 + exc.head1 : pre.head1;     // 1-based index of the latest head before this thread
+    u64 c = pre.c + (exc.cd & 0xffffu), d = pre.d + (exc.cd >> 16), e = pre.e + exc.e;
+    IdxT hd[kHpItems];
+#pragma unroll
+    for (int j = 0; j < kHpItems; ++j) {
+        if ((t.head >> j) & 1u) head1 = t.i0 + j + 1;
+        hd[j] = b0 + IdxT(head1 - 1);
+    }
+    if (t.valid == (1u << kHpItems) - 1u) {
+        if constexpr (sizeof(IdxT) == 4) {
+            uint4* o = reinterpret_cast<uint4*>(rpos + t.i0);
+            o[0] = make_uint4(u32(hd[0]), u32(hd[1]), u32(hd[2]), u32(hd[3]));
+            o[1] = make_uint4(u32(hd[4]), u32(hd[5]), u32(hd[6]), u32(hd[7]));
+        } else {
+            ulonglong2* o = reinterpret_cast<ulonglong2*>(rpos + t.i0);
+#pragma unroll
+            for (int q = 0; q < kHpItems / 2; ++q) o[q] = make_ulonglong2(u64(hd[2 * q]), u64(hd[2 * q + 1]));
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < kHpItems; ++j) if ((t.valid >> j) & 1u) rpos[t.i0 + j] = hd[j];
+    }
+    if (t.unsorted == 0) return;
+#pragma unroll
+    for (int j = 0; j < kHpItems; ++j) {
+        if ((t.unsorted >> j) & 1u) {
+            const IdxT idx = vv[t.i0 + j];
+            if ((t.pure >> j) & 1u) { gs[d] = hd[j]; is[d] = idx; ++d; }
+            else {
+                ga[c] = hd[j]; ia[c] = idx;
+                if ((t.head >> j) & 1u) hsa[e++] = IdxT(c);
+                ++c;
+            }
+        }
+    }
+}
+
 // ---- sharded build: key-range selection -----------------------------------------------------------------------
 // histogram of the first `psym` symbols (b bits each) of every suffix: the members cut their key ranges from it
 __global__ void __launch_bounds__(256) key_prefix_hist_kernel(const u8* __restrict__ text, u64 n, const uint16_t* __restrict__ code, int b,
@@ -435,45 +588,34 @@ void build_suffix_array(const u8* d_text, u64 n, IdxT* d_sa, const RankView<IdxT
 
         if (hook) hook->on_sorted_keys(k, n_loc, base, n, b, p0, h_code, stream, grp);
         phase("lookup tables");
-        DevBuf<Acc> d_total(1, stream);
         const u64* kk = k;
         const IdxT* vv = sa_loc;
-        const u64 nl = n_loc;
-        auto in = [kk, nl, rep_unit, sym_mask] __device__(u64 i) {
-            const u64 cur = kk[i];
-            const bool head = i == 0 || kk[i - 1] != cur;
-            const bool tail = i + 1 == nl || kk[i + 1] != cur;
-            const bool uns = !(head && tail);
-            const bool pure = cur == (cur & sym_mask) * rep_unit;
-            return (head ? FS_MARK_A : 0u) | ((uns && !pure) ? FS_CNT_C : 0u) | ((uns && pure) ? FS_CNT_D : 0u) |
-                   ((uns && !pure && head) ? FS_CNT_E : 0u);
-        };
         if (st && st->rank) st->rank->begin();
-        FlagScanPlan<IdxT> plan;
-        plan.prepare(in, n_loc, d_total.p, stream);
-        Acc tot;
-        sync_read(&tot, d_total.p, sizeof tot);
-        UA = u64(tot.c); US = u64(tot.d); NGA = u64(tot.e);
+        const u64 hp_tiles = ceil_div(n_loc, u64(kHpTile));
+        DevBuf<HpTileAcc> hp_acc(hp_tiles, stream), hp_pre(hp_tiles, stream), hp_total(1, stream);
+        HpTileAcc tot(0);
+        if (n_loc) {
+            hp_reduce_kernel<<<unsigned(hp_tiles), kHpThreads, 0, stream>>>(kk, n_loc, rep_unit, sym_mask, hp_acc.p);
+            KERNEL_CHECK();
+            count_launch();
+            const HpTileAcc* acc = hp_acc.p;
+            HpTileAcc* pre = hp_pre.p;
+            device_scan<HpTileAcc, HpTileOp>([acc] __device__(u64 i) -> HpTileAcc { return acc[i]; },
+                                             [pre] __device__(u64 i, const HpTileAcc& exc, const HpTileAcc&) { pre[i] = exc; }, hp_tiles,
+                                             hp_total.p, stream);
+            sync_read(&tot, hp_total.p, sizeof tot);
+        }
+        UA = tot.c; US = tot.d; NGA = tot.e;
         GA.alloc(UA, stream); IA.alloc(UA, stream); HSA.alloc(NGA, stream);
         GS.alloc(US, stream); IS.alloc(US, stream);
-        IdxT *ga = GA.p, *ia = IA.p, *hsa = HSA.p, *gs = GS.p, *is = IS.p;
         // rank by sorted position goes to the dead half of the value ping-pong, then to text order by the sliced scatter
         IdxT* rpos = va;
-        const IdxT b0 = IdxT(base);
-        plan.finish(in, [=] __device__(u64 i, const Acc& exc, const Acc& inc) {
-            const u64 cur = kk[i];
-            const bool head = i == 0 || kk[i - 1] != cur;
-            const bool tail = i + 1 == nl || kk[i + 1] != cur;
-            const IdxT idx = vv[i];
-            const IdxT hd = b0 + inc.a;   // the group head's index in the suffix array
-            rpos[i] = hd;
-            if (head && tail) return;
-            if (cur == (cur & sym_mask) * rep_unit) { gs[exc.d] = hd; is[exc.d] = idx; }
-            else {
-                ga[exc.c] = hd; ia[exc.c] = idx;
-                if (head) hsa[exc.e] = exc.c;
-            }
-        });
+        if (n_loc) {
+            hp_emit_kernel<IdxT><<<unsigned(hp_tiles), kHpThreads, 0, stream>>>(kk, vv, n_loc, rep_unit, sym_mask, hp_pre.p, IdxT(base), rpos,
+                                                                                GA.p, IA.p, HSA.p, GS.p, IS.p);
+            KERNEL_CHECK();
+            count_launch();
+        }
         // the sorted keys are dead from here on: both key buffers serve as scratch of the sort-back scatter
         if (!grp) inverse_scatter<IdxT>(d_sa, rpos, n, d_rank.base[0], n, stream, k, ka);
         else if (n_loc) {
