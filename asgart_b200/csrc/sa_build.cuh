@@ -822,7 +822,9 @@ void build_suffix_array(const u8* d_text, u64 n, IdxT* d_sa, const RankView<IdxT
             const bool tail_new = c + 1 == Uc || gg[c + 1] != g || k2[c + 1] != kv;
             const IdxT idx = ii[c];
             const IdxT ng = g + (inc.b - inc.a);
-            *d_rank.ptr(u64(idx)) = ng;
+            // rank[] already holds g for every member of the old group: only suffixes that leave its first subgroup need the
+            // (random, 4-byte, possibly remote) store
+            if (ng != g) *d_rank.ptr(u64(idx)) = ng;
             if (head_new && tail_new) { d_sa[u64(g) + (c - u64(inc.a))] = idx; return; }
             g2[exc.c] = ng; i2[exc.c] = idx; d2[exc.c] = dd[c] + Hi;
             if (head_new) hs2[exc.d] = exc.c;
