@@ -7,10 +7,13 @@
 // with four sweeps over 57 M elements. So:
 //   out fits one slice          -> plain scatter
 //   a few slices (<= kSweepMax) -> one sweep over (idx, val) per slice, each writing only its slice's targets
-//   more, idx a permutation     -> sort the pairs back by target: two radix partition passes by bits [16, 32) of idx leave
+//   more, idx a permutation     -> sort the pairs back by target: two partition passes by bits [16, 32) of idx leave
 //                                  the pairs of every 65 536-target bucket contiguous (bucket b = pairs [b << 16, (b+1) << 16),
 //                                  because idx is a permutation); one block per bucket then scatters inside shared memory
-//                                  and writes its slice of `out` as whole lines. No random access reaches L2 or DRAM:
+//                                  and writes its slice of `out` as whole lines. The order inside a bucket is irrelevant, so
+//                                  the passes need not be stable: most significant digit first (regions of 2^24 targets,
+//                                  which a permutation fills exactly), then the next digit inside every region, each element
+//                                  ranked by one shared-memory atomic instead of the stable sort's ballot matching. No random access reaches L2 or DRAM:
 //                                  52 B of streamed traffic per element instead of a 64 B DRAM read-modify-write at
 //                                  random-access efficiency (C4, 3.1 G targets: 132 ms for the plain scatter).
 //   more, otherwise             -> plain scatter. Tried and dropped: one radix partition pass of the pairs by slice number
@@ -89,19 +92,129 @@ __global__ void __launch_bounds__(kBucketThreads, 1) bucket_scatter_kernel(const
     }
 }
 
+// ---- non-stable partition of (idx, val) pairs by an 8-bit digit of idx, optionally inside regions of `rt` tiles ----
+// Table row of (tile, digit): regions are laid out one after the other, digit-major inside a region, so one exclusive scan
+// of the whole table yields global offsets in (region, digit, tile) order. rt = number of tiles: one region, plain digit-major.
+constexpr int kPtThreads = 512;
+constexpr int kPtItems = 8;
+constexpr int kPtTile = kPtThreads * kPtItems;
+
+__device__ __forceinline__ u64 pt_row(u64 tile, u32 d, u64 rt) { return ((tile / rt) * 256 + d) * rt + tile % rt; }
+
+__global__ void __launch_bounds__(kPtThreads) pt_hist_kernel(const u32* __restrict__ idx, u64 n, int shift, u32* __restrict__ hist, u64 rt) {
+    __shared__ u32 h[256];
+    if (threadIdx.x < 256) h[threadIdx.x] = 0;
+    __syncthreads();
+    const u64 base = u64(blockIdx.x) * kPtTile;
+    const u32 cnt = u32(min(u64(kPtTile), n - base));
+    u32 k[kPtItems];
+#pragma unroll
+    for (int j = 0; j < kPtItems; ++j) { const u32 li = j * kPtThreads + threadIdx.x; if (li < cnt) k[j] = idx[base + li]; }
+#pragma unroll
+    for (int j = 0; j < kPtItems; ++j) { const u32 li = j * kPtThreads + threadIdx.x; if (li < cnt) atomicAdd(&h[(k[j] >> shift) & 255u], 1u); }
+    __syncthreads();
+    if (threadIdx.x < 256) hist[pt_row(blockIdx.x, threadIdx.x, rt)] = h[threadIdx.x];
+}
+
+__global__ void __launch_bounds__(kPtThreads) pt_scatter_kernel(const u32* __restrict__ idx, const u32* __restrict__ val, u64 n, int shift,
+                                                               const u32* __restrict__ offs, u64 rt, u32* __restrict__ oidx,
+                                                               u32* __restrict__ oval) {
+    __shared__ u32 cnt_d[256], tile_off[256], delta[256];
+    __shared__ __align__(16) u32 si[kPtTile], sv[kPtTile];
+    const u32 tid = threadIdx.x, lane = tid & 31u;
+    const u64 base = u64(blockIdx.x) * kPtTile;
+    const u32 cnt = u32(min(u64(kPtTile), n - base));
+    if (tid < 256) cnt_d[tid] = 0;
+    u32 k[kPtItems], v[kPtItems], slot[kPtItems];
+#pragma unroll
+    for (int j = 0; j < kPtItems; ++j) {
+        const u32 li = j * kPtThreads + tid;
+        if (li < cnt) { k[j] = idx[base + li]; v[j] = val[base + li]; }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < kPtItems; ++j) {
+        const u32 li = j * kPtThreads + tid;
+        if (li < cnt) slot[j] = atomicAdd(&cnt_d[(k[j] >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    if (tid < 32) {   // exclusive scan of the 256 digit counts: 8 per lane + warp scan
+        u32 c[8], ssum = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { c[j] = cnt_d[lane * 8 + j]; ssum += c[j]; }
+        u32 inc = ssum;
+#pragma unroll
+        for (int dd = 1; dd < 32; dd <<= 1) { const u32 o = __shfl_up_sync(0xffffffffu, inc, dd); if (lane >= u32(dd)) inc += o; }
+        u32 run = inc - ssum;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const u32 d = lane * 8 + j;
+            tile_off[d] = run;
+            delta[d] = offs[pt_row(blockIdx.x, d, rt)] - run;
+            run += c[j];
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < kPtItems; ++j) {
+        const u32 li = j * kPtThreads + tid;
+        if (li < cnt) {
+            const u32 lp = tile_off[(k[j] >> shift) & 255u] + slot[j];
+            si[lp] = k[j];
+            sv[lp] = v[j];
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < kPtItems; ++j) {
+        const u32 lp = j * kPtThreads + tid;
+        if (lp < cnt) {
+            const u32 kk = si[lp];
+            const u32 gp = delta[(kk >> shift) & 255u] + lp;
+            oidx[gp] = kk;
+            oval[gp] = sv[lp];
+        }
+    }
+}
+
+// one partition pass; `region_elems` = 0: the whole array is one region, else regions of that many elements (a multiple
+// of the tile) that the previous pass has made contiguous
+inline void partition_pass(const u32* idx, const u32* val, u64 n, int shift, u64 region_elems, u32* oidx, u32* oval, DevBuf<u32>& hist,
+                           DevBuf<u32>& offs, cudaStream_t stream) {
+    const u64 tiles = ceil_div(n, u64(kPtTile));
+    const u64 rt = region_elems ? region_elems / kPtTile : tiles;
+    const u64 table = ceil_div(tiles, rt) * 256 * rt;
+    hist.alloc(table, stream);
+    offs.alloc(table, stream);
+    if (region_elems) hist.zero();    // rows of tiles the last region does not have
+    pt_hist_kernel<<<unsigned(tiles), kPtThreads, 0, stream>>>(idx, n, shift, hist.p, rt);
+    KERNEL_CHECK();
+    const u32* hp = hist.p;
+    u32* op = offs.p;
+    device_scan<u32, SumOp>([hp] __device__(u64 i) { return hp[i]; }, [op] __device__(u64 i, u32 exc, u32) { op[i] = exc; }, table,
+                            (u32*)nullptr, stream);
+    pt_scatter_kernel<<<unsigned(tiles), kPtThreads, 0, stream>>>(idx, val, n, shift, offs.p, rt, oidx, oval);
+    KERNEL_CHECK();
+    count_launch(2);
+}
+
 // out[idx[i]] = val[i] for idx a permutation of [0, n), n < 2^32. ws_a and ws_b hold 2 * (n + 4) u32 each; `val` may be
 // overwritten (nothing here does), idx and val are left intact. All of idx/val/out/ws_* 16-byte aligned.
 inline void inverse_permutation_scatter(const u32* idx, const u32* val, u64 n, u32* out, u32* ws_a, u32* ws_b, cudaStream_t stream,
                                         FamilyTimer* timer = nullptr) {
     if (n == 0) return;
     const u64 half = (n + 3) / 4 * 4;   // the value halves stay 16-byte aligned
-    RadixScratch<u32> ws(n, stream);
     const int bits = bit_width_u64(n - 1);
     const u32 *ki = idx, *vi = val;
     u32* bufs[2] = {ws_a, ws_b};
     int w = 0;
-    for (int shift = kBucketBits; shift < bits; shift += 8) {
-        radix_pass<u32, u32>(ws, ki, vi, bufs[w], bufs[w] + half, shift, stream, timer, nullptr);
+    DevBuf<u32> hist, offs;
+    // most significant digit first; a digit at [24, 32) splits the pairs into regions of 2^24 targets = 2^24 pairs each
+    for (int shift = bits > kBucketBits ? kBucketBits + 8 * ((bits - kBucketBits - 1) / 8) : -1; shift >= kBucketBits; shift -= 8) {
+        const u64 region = (shift + 8 < bits) ? (u64(1) << (shift + 8)) : 0;
+        if (timer) timer->begin();
+        partition_pass(ki, vi, n, shift, region, bufs[w], bufs[w] + half, hist, offs, stream);
+        if (timer) timer->end(5, n * 4 * sizeof(u32));
         ki = bufs[w]; vi = bufs[w] + half;
         w ^= 1;
     }
