@@ -25,20 +25,10 @@
 #include <vector>
 
 #include "common.cuh"
+#include "fasta_core.h"
 #include "scan.cuh"
 
 namespace ab200 {
-
-constexpr u64 kLongNRun = 5000;   // src/bin/asgart.rs:326
-
-__host__ __device__ __forceinline__ bool fa_space(u8 c) { return c == ' ' || (c >= 9 && c <= 13); }   // ASCII isspace
-__host__ __device__ __forceinline__ bool fa_blank(u8 c) { return fa_space(c) && c != '\n'; }
-
-// src/bin/asgart.rs:291-301
-__host__ __device__ __forceinline__ u8 fa_normalise(u8 c, bool skip_masked) {
-    if (!skip_masked && c >= 'a' && c <= 'z') c = u8(c - 32);
-    return (c == 'A' || c == 'C' || c == 'G' || c == 'T' || c == 'N') ? c : u8('N');
-}
 
 struct IngestPiece {
     DevBuf<u8> strand;               // kept, normalised bytes of one file (no '$')
@@ -48,12 +38,6 @@ struct IngestPiece {
     std::vector<u64> run_start, run_len;   // maximal N-runs longer than kLongNRun, ascending, file-local strand coordinates
     std::vector<std::string> names;  // record ids (header up to the first white space), filled by the caller
 };
-
-constexpr int kFiThreads = 256;
-constexpr int kFiBytes = 32;
-constexpr int kFiWarps = kFiThreads / 32;
-constexpr u64 kFiTile = u64(kFiThreads) * kFiBytes;
-enum : u32 { FI_NONE = 0, FI_CLR = 1, FI_SET = 2 };
 
 // Tile-level prefixes, all with commutative operators (the generic scans of scan.cuh reduce in strided order):
 //   sums  kept bytes, header starts
@@ -80,24 +64,6 @@ __device__ __forceinline__ unsigned lanemask_gt() {
     return m;
 }
 
-// ---- byte classification, four bytes per instruction (SWAR; exact for every byte value, no carries between bytes) ----
-// flags: 0x80 in every byte of x that is zero
-__device__ __forceinline__ u32 sw_zero(u32 x) { return ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x) & 0x80808080u; }
-__device__ __forceinline__ u32 sw_eq(u32 w, u32 k4) { return sw_zero(w ^ k4); }
-// flags: 0x80 in every byte of w below 0x21 (control characters and the blank: every white-space byte is among them)
-__device__ __forceinline__ u32 sw_below_21(u32 w) { return ~(((w & 0x7F7F7F7Fu) + 0x5F5F5F5Fu) | w) & 0x80808080u; }
-// the four flag bits of a word as bits 0..3 (byte 0 = bit 0)
-__device__ __forceinline__ u32 sw_movemask(u32 f) { return ((f >> 7) * 0x01020408u) >> 24; }
-
-struct FiThread {
-    u32 w[kFiBytes / 4];   // the thread's 32 bytes, little endian: byte j = w[j / 4] >> 8 * (j % 4)
-    int valid;             // bytes of this thread inside the file
-    u64 base;
-    u32 vmask;             // bit j: byte j is inside the file
-    u32 nl, space, heads;  // bit j: byte j is '\n' / white space / a '>' that opens a line
-    u32 h_last, r_first;   // this thread's last header event / first rest event
-};
-
 __device__ __forceinline__ void fi_load(const u8* __restrict__ d_file, u64 n, FiThread& t) {
     t.base = u64(blockIdx.x) * kFiTile + u64(threadIdx.x) * kFiBytes;
     t.valid = t.base >= n ? 0 : int(n - t.base < u64(kFiBytes) ? n - t.base : u64(kFiBytes));
@@ -116,32 +82,7 @@ __device__ __forceinline__ void fi_load(const u8* __restrict__ d_file, u64 n, Fi
             t.w[q] = x;
         }
     }
-    const u32 prev_nl = (t.base == 0 || t.valid == 0) ? 1u : u32(d_file[t.base - 1] == '\n');
-    u32 nl = 0, gt = 0, low = 0;
-#pragma unroll
-    for (int q = 0; q < kFiBytes / 4; ++q) {
-        nl |= sw_movemask(sw_eq(t.w[q], 0x0A0A0A0Au)) << (4 * q);
-        gt |= sw_movemask(sw_eq(t.w[q], 0x3E3E3E3Eu)) << (4 * q);
-        low |= sw_movemask(sw_below_21(t.w[q])) << (4 * q);
-    }
-    nl &= t.vmask; gt &= t.vmask; low &= t.vmask;
-    u32 space = nl;
-    if (low != nl) {                       // some other control character or blank: the remaining white-space values
-#pragma unroll
-        for (int q = 0; q < kFiBytes / 4; ++q) {
-            const u32 x = t.w[q];
-            const u32 f = sw_eq(x, 0x20202020u) | sw_eq(x, 0x09090909u) | sw_eq(x, 0x0B0B0B0Bu) | sw_eq(x, 0x0C0C0C0Cu) | sw_eq(x, 0x0D0D0D0Du);
-            space |= sw_movemask(f) << (4 * q);
-        }
-        space &= t.vmask;
-    }
-    t.nl = nl;
-    t.space = space;
-    t.heads = gt & ((nl << 1) | prev_nl);
-    const u32 ev = t.heads | nl;            // header machine: '>' at a line start sets, '\n' clears; the last event counts
-    t.h_last = ev ? (((t.heads >> (31 - __clz(ev))) & 1u) ? u32(FI_SET) : u32(FI_CLR)) : u32(FI_NONE);
-    const u32 rv = nl | (~space & t.vmask);  // rest machine: '\n' sets, a non-white byte clears; the first event counts
-    t.r_first = rv ? (((nl >> (__ffs(rv) - 1)) & 1u) ? u32(FI_SET) : u32(FI_CLR)) : u32(FI_NONE);
+    fi_classify(t, (t.base == 0 || t.valid == 0) ? 1u : u32(d_file[t.base - 1] == '\n'));
 }
 
 // states entering this thread from the left (header) and from the right (rest), given those entering the tile;
@@ -166,55 +107,6 @@ __device__ __forceinline__ void fi_block_states(const FiThread& t, u32 tile_h_in
     for (int w = 0; w < kFiWarps; ++w) if (sm[w] != FI_NONE) tile_h = sm[w];
     for (int w = kFiWarps - 1; w >= 0; --w) if (sm[kFiWarps + w] != FI_NONE) tile_r = sm[kFiWarps + w];
     __syncthreads();
-}
-
-// keep mask of this thread's bytes: not on a header line, not '\n', not trailing white space
-__device__ __forceinline__ u32 fi_keep_mask(const FiThread& t, u32 h_in, u32 r_in) {
-    if (t.valid == 0) return 0;
-    u32 on_header;
-    if (t.heads == 0) {                     // no header starts here: the entering state holds up to the first '\n'
-        on_header = h_in ? (t.nl ? ((1u << (__ffs(t.nl) - 1)) - 1u) : 0xffffffffu) : 0u;
-    } else {
-        on_header = 0;
-        u32 h = h_in;
-        for (int j = 0; j < t.valid; ++j) {
-            if ((t.nl >> j) & 1u) h = 0;
-            else if ((t.heads >> j) & 1u) h = 1;
-            on_header |= h << j;
-        }
-    }
-    const u32 blank = t.space & ~t.nl;
-    u32 trailing = 0;
-    if (blank) {                            // a blank is trailing iff its successor is '\n', a trailing blank, or (last byte) r_in
-        const u32 inject = r_in << (t.valid - 1);
-        for (;;) {
-            const u32 next = blank & (((t.nl | trailing) >> 1) | inject);
-            if (next == trailing) break;
-            trailing = next;
-        }
-    }
-    return ~(on_header | t.nl | trailing) & t.vmask;
-}
-
-// flags of the bytes that normalise to a base (A, C, G, T; src/bin/asgart.rs:291-301) and the normalised words
-__device__ __forceinline__ u32 fi_base_mask(const FiThread& t, bool skip_masked, u32* norm /* kFiBytes / 4, may be null */) {
-    u32 base = 0;
-#pragma unroll
-    for (int q = 0; q < kFiBytes / 4; ++q) {
-        // upper-casing: clearing bit 5 maps a,c,g,t onto A,C,G,T and no other byte value onto them
-        const u32 u = skip_masked ? t.w[q] : (t.w[q] & 0xDFDFDFDFu);
-        const u32 f = sw_eq(u, 0x41414141u) | sw_eq(u, 0x43434343u) | sw_eq(u, 0x47474747u) | sw_eq(u, 0x54545454u);
-        base |= sw_movemask(f) << (4 * q);
-        if (norm) { const u32 bm = (f >> 7) * 0xFFu; norm[q] = (u & bm) | (0x4E4E4E4Eu & ~bm); }
-    }
-    return base & t.vmask;
-}
-
-// kept | header starts << 32 of this thread, and the number of its kept bytes up to and including the last base
-__device__ __forceinline__ void fi_thread_counts(const FiThread& t, u32 keep, u32 base, u64& packed, u32& upto_base) {
-    packed = u64(__popc(keep)) | (u64(__popc(t.heads)) << 32);
-    const u32 kb = keep & base;
-    upto_base = kb ? u32(__popc(keep & (0xffffffffu >> __clz(kb)))) : 0u;
 }
 
 __global__ void __launch_bounds__(kFiThreads) fi_events_kernel(const u8* __restrict__ d_file, u64 n, u8* __restrict__ tile_ev) {
@@ -384,29 +276,10 @@ inline void ingest_fasta_device(const u8* d_file, u64 n, bool skip_masked, Inges
     for (auto& p : v) { out.run_start.push_back(p.first); out.run_len.push_back(p.second); }
 }
 
-// chunks_to_process of one file (src/bin/asgart.rs:317-366 applied per fragment, :381-387): inside each fragment the
-// maximal regions between N-runs longer than kLongNRun; a run that crosses a fragment border counts on each side with the
-// part that lies there. `off` = strand position of the file's first base.
+// chunks_to_process and fragment table of one ingested file; `off` = strand position of the file's first base
 inline void ingest_chunks(const IngestPiece& p, u64 off, std::vector<asgart_b200_chunk>& chunks,
                           std::vector<u64>& frag_pos, std::vector<u64>& frag_len) {
-    size_t ri = 0;
-    const size_t R = p.rec_pos.size();
-    for (size_t r = 0; r < R; ++r) {
-        const u64 fs = p.rec_pos[r], fe = r + 1 < R ? p.rec_pos[r + 1] : p.kept;
-        frag_pos.push_back(off + fs);
-        frag_len.push_back(fe - fs);
-        const size_t first = chunks.size();
-        u64 cur = fs;
-        while (ri < p.run_start.size() && p.run_start[ri] + p.run_len[ri] <= fs) ++ri;
-        for (size_t j = ri; j < p.run_start.size() && p.run_start[j] < fe; ++j) {
-            const u64 ps = std::max(p.run_start[j], fs), pe = std::min(p.run_start[j] + p.run_len[j], fe);
-            if (pe - ps <= kLongNRun) continue;
-            if (ps > cur) chunks.push_back({off + cur, ps - cur});
-            cur = pe;
-        }
-        if (fe > cur) chunks.push_back({off + cur, fe - cur});
-        if (chunks.size() == first) chunks.push_back({off + fs, fe - fs});
-    }
+    chunks_from_runs(p.rec_pos, p.kept, p.run_start, p.run_len, off, chunks, frag_pos, frag_len);
 }
 
 }  // namespace ab200

@@ -9,12 +9,14 @@
 #include <vector>
 
 #include "../../asgart_b200/csrc/automaton_core.h"
+#include "../../asgart_b200/csrc/fasta_core.h"
 #include "../../asgart_b200/csrc/kmer_core.h"
 #include "../../include/asgart_b200.h"
 
 using namespace ab200;
 using u64 = uint64_t;
 using u32 = uint32_t;
+using i64 = int64_t;
 
 namespace {
 struct Chunk { u64 c0, len, n_probes, probe_base, needle_start; };
@@ -172,4 +174,82 @@ void emul_result_copy(void* h, int64_t* fam_off, uint64_t* fields) {
     if (!R->fields.empty()) memcpy(fields, R->fields.data(), R->fields.size() * 8);
 }
 void emul_result_free(void* h) { delete static_cast<Result*>(h); }
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// GPU-side FASTA ingest (fasta_ingest.cuh), one "thread" (32 file bytes) at a time with the functions of fasta_core.h:
+// classification, keep / base masks, per-thread counts exactly as the kernels use them. What the kernels do with warp
+// ballots and tile-level scans — carrying the two one-bit states and the running counts from thread to thread — is a
+// plain sequential carry here; the emit step restates fi_emit_kernel (records, compaction + normalisation, long N-runs
+// reported by the first base after them) and the host side of ingest_fasta_device / ingest_chunks.
+// Returns the number of kept bytes, or -1 when a buffer is too small.
+extern "C" int64_t emul_ingest(const uint8_t* file, int64_t n_, int skip_masked, uint8_t* strand, int64_t strand_cap, uint64_t* rec_off,
+                               uint64_t* rec_pos, int64_t rec_cap, int64_t* n_rec, uint64_t* chunks, int64_t chunk_cap, int64_t* n_chunks,
+                               uint64_t* frag, int64_t frag_cap, int64_t* n_frag) {
+    const u64 n = u64(n_);
+    const u64 nthreads = (n + kFiBytes - 1) / kFiBytes;
+    std::vector<FiThread> th(nthreads);
+    for (u64 g = 0; g < nthreads; ++g) {   // fi_load
+        FiThread& t = th[g];
+        t.base = g * kFiBytes;
+        t.valid = int(n - t.base < u64(kFiBytes) ? n - t.base : u64(kFiBytes));
+        t.vmask = t.valid == kFiBytes ? 0xffffffffu : ((1u << t.valid) - 1u);
+        for (int q = 0; q < kFiBytes / 4; ++q) {
+            u32 x = 0;
+            for (int r = 0; r < 4; ++r) { const int j = 4 * q + r; x |= u32(j < t.valid ? file[t.base + j] : uint8_t('\n')) << (8 * r); }
+            t.w[q] = x;
+        }
+        fi_classify(t, (t.base == 0 || t.valid == 0) ? 1u : u32(file[t.base - 1] == '\n'));
+    }
+    std::vector<u32> h_in(nthreads), r_in(nthreads);
+    u32 st = 0;
+    for (u64 g = 0; g < nthreads; ++g) { h_in[g] = st; if (th[g].h_last != FI_NONE) st = th[g].h_last == FI_SET; }
+    st = 1;
+    for (u64 g = nthreads; g-- > 0;) { r_in[g] = st; if (th[g].r_first != FI_NONE) st = th[g].r_first == FI_SET; }
+    std::vector<u64> roff, rpos, run_start, run_len;
+    u64 outpos = 0, after_last = 0;
+    for (u64 g = 0; g < nthreads; ++g) {
+        const FiThread& t = th[g];
+        const u32 keep = fi_keep_mask(t, h_in[g], r_in[g]);
+        u32 norm[kFiBytes / 4];
+        const u32 base = fi_base_mask(t, skip_masked != 0, norm);
+        u64 packed;
+        u32 upto;
+        fi_thread_counts(t, keep, base, packed, upto);
+        for (u32 m = t.heads; m; m &= m - 1) {
+            const int j = fc_ffs(m) - 1;
+            roff.push_back(t.base + j);
+            rpos.push_back(outpos + fc_popc(keep & ((1u << j) - 1u)));
+        }
+        const u32 kb = keep & base;
+        if (kb) {
+            const u64 first_base = outpos + fc_popc(keep & ((1u << (fc_ffs(kb) - 1)) - 1u));
+            const u64 len = first_base - after_last;
+            if (len > kLongNRun) { run_start.push_back(after_last); run_len.push_back(len); }
+        }
+        u64 at = outpos;
+        for (int j = 0; j < kFiBytes; ++j)
+            if ((keep >> j) & 1u) {
+                if (i64(at) >= strand_cap) return -1;
+                strand[at++] = uint8_t(norm[j >> 2] >> ((j & 3) * 8));
+            }
+        if (at - outpos != (packed & 0xffffffffull) || (packed >> 32) != u64(fc_popc(t.heads))) return -2;
+        if (upto) after_last = outpos + upto;
+        outpos = at;
+    }
+    const u64 kept = outpos;
+    if (kept - after_last > kLongNRun) { run_start.push_back(after_last); run_len.push_back(kept - after_last); }
+    if (i64(roff.size()) > rec_cap) return -1;
+    for (size_t r = 0; r < roff.size(); ++r) { rec_off[r] = roff[r]; rec_pos[r] = rpos[r]; }
+    *n_rec = i64(roff.size());
+    std::vector<asgart_b200_chunk> ch;
+    std::vector<u64> fpos, flen;
+    chunks_from_runs(rpos, kept, run_start, run_len, 0, ch, fpos, flen);
+    if (i64(ch.size()) > chunk_cap || i64(fpos.size()) > frag_cap) return -1;
+    for (size_t c = 0; c < ch.size(); ++c) { chunks[2 * c] = ch[c].start; chunks[2 * c + 1] = ch[c].length; }
+    for (size_t f = 0; f < fpos.size(); ++f) { frag[2 * f] = fpos[f]; frag[2 * f + 1] = flen[f]; }
+    *n_chunks = i64(ch.size());
+    *n_frag = i64(fpos.size());
+    return i64(kept);
 }

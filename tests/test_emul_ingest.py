@@ -1,0 +1,51 @@
+"""The arithmetic of the GPU-side FASTA ingest (asgart_b200/csrc/fasta_core.h: four-bytes-per-instruction classification,
+keep / base masks, per-thread counts, N-run reporting, chunk derivation) compiled for the host and run one "thread" at a
+time against the oracle's restatement of prepare_data (src/bin/asgart.rs:273-471). The warp / tile plumbing of the kernels
+is covered by tests/test_gpu_ingest.py on the same inputs."""
+import numpy as np
+import pytest
+
+import oracle
+from tests import emul_harness
+from tests.fasta_cases import fasta, line_and_record_blobs, n_run_records, rand_seq
+
+
+def _check(tmp_path, blob, skip_masked, tag):
+    p = tmp_path / f"{tag}.fa"
+    p.write_bytes(blob)
+    want = oracle.Prepared.from_files([str(p)], skip_masked)
+    strand, frags, chunks = emul_harness.ingest(blob, skip_masked)
+    assert np.array_equal(strand, want.strand[:-1]), tag
+    assert frags == want.map, tag
+    assert chunks == want.chunks, tag
+    return want
+
+
+@pytest.mark.parametrize("skip_masked", [False, True])
+def test_emul_ingest_line_and_record_shapes(tmp_path, skip_masked):
+    for i, blob in enumerate(line_and_record_blobs()):
+        _check(tmp_path, blob, skip_masked, f"s{i}")
+
+
+def test_emul_ingest_n_runs_and_chunks(tmp_path):
+    recs = n_run_records()
+    for width in (60, 31, 32, 33, 4096, 10 ** 9):
+        want = _check(tmp_path, fasta(recs, width=width), False, f"n{width}")
+        assert len(want.chunks) > len(recs)
+    _check(tmp_path, fasta(recs, eol="\r\n"), True, "crlf")
+    rng = np.random.default_rng(9)
+    s = lambda n: rand_seq(rng, n)   # noqa: E731
+    masked = fasta([("m", s(4000) + s(5200).lower() + s(3000) + s(4999).lower() + s(100))])
+    assert len(_check(tmp_path, masked, False, "m0").chunks) == 1
+    assert len(_check(tmp_path, masked, True, "m1").chunks) == 2
+
+
+def test_emul_ingest_random_files(tmp_path):
+    """Random mixes of bases, lower case, blanks, line ends and header starts at every alignment inside the 32-byte threads."""
+    rng = np.random.default_rng(21)
+    alphabet = np.frombuffer(b"ACGTacgtNn \t\r\n\n\n>xX-", dtype=np.uint8)
+    weights = np.array([8, 8, 8, 8, 2, 2, 2, 2, 3, 1, 1, 1, 1, 2, 2, 2, 1, 1, 1, 1], dtype=float)
+    for i in range(60):
+        n = int(rng.integers(1, 3000))
+        body = rng.choice(alphabet, size=n, p=weights / weights.sum()).tobytes()
+        _check(tmp_path, b">r" + str(i).encode() + b" d\n" + body, bool(i & 1), f"r{i}")

@@ -14,18 +14,7 @@ from tests.test_gpu_parity import _osettings
 pytestmark = pytest.mark.gpu
 
 
-def _fasta(records, width=60, eol="\n", final_eol=True) -> bytes:
-    out = []
-    for name, seq in records:
-        out.append(">" + name)
-        for i in range(0, len(seq), width):
-            out.append(seq[i:i + width])
-    s = eol.join(out)
-    return (s + (eol if final_eol else "")).encode()
-
-
-def _rand_seq(rng, n, alphabet="ACGT"):
-    return "".join(rng.choice(list(alphabet), size=n))
+from tests.fasta_cases import fasta as _fasta, line_and_record_blobs, n_run_records, rand_seq as _rand_seq  # noqa: E402
 
 
 def _check(tmp_path, blobs, skip_masked, tag="f"):
@@ -50,49 +39,16 @@ def _check(tmp_path, blobs, skip_masked, tag="f"):
 
 @pytest.mark.parametrize("skip_masked", [False, True])
 def test_ingest_line_and_record_shapes(tmp_path, skip_masked):
-    rng = np.random.default_rng(7)
-    a = _rand_seq(rng, 1000, "ACGTacgtNnRYKM-*xX")
-    b = _rand_seq(rng, 7321, "ACGTacgt")
-    blobs = [
-        _fasta([("chr1 some description", a), ("chr2", b)]),
-        _fasta([("chr1\tdesc", a), ("chr2", b)], eol="\r\n"),                       # CRLF
-        _fasta([("x", a), ("y", b)], final_eol=False),                              # no newline at the end of the file
-        _fasta([("x", a)], width=10 ** 9),                                          # one-line record
-        b"\n\n>lead empty lines\nACGT\nAC GT  \t\nGG\r\n\n\nTT \n>e1\n>e2 d\n\n>last\nNNNN>AC\n ACGT\nA",   # interior blanks, empty records, '>' inside a line
-        b">only header",
-        b">only header\n",
-        b">\nACGT\n",                                                                 # empty id
-        b"",                                                                          # empty file: no records
-        b"\n\n",
-        b">a\n   \n \t \n>b\n\x0b\x0cAC\x0b\x0c\n",                                  # lines of blanks only; VT / FF
-    ]
-    # every byte value, in random order and in runs: exercises the four-bytes-per-instruction classification (bytes >= 0x80,
-    # control characters, '>' after a random '\n', blanks before a random '\n')
-    blobs.append(b">bin\n" + rng.integers(0, 256, size=20000, dtype=np.uint8).tobytes().replace(b"\n>", b"\n?"))   # ids must stay UTF-8
-    blobs.append(b">runs\n" + b"".join(bytes([v]) * 37 for v in range(256)) + b"\n" + bytes(range(256)) * 3)
-    blobs.append(b">ws\n" + rng.choice(np.frombuffer(b"AC \t\r\n\x0b\x0c>", dtype=np.uint8), size=30000).tobytes())
+    blobs = line_and_record_blobs()
     for i, blob in enumerate(blobs):
         _check(tmp_path, [blob], skip_masked, tag=f"s{i}_")
     _check(tmp_path, blobs[:4], skip_masked, tag="multi")                            # several files: running offset
 
 
 def test_ingest_n_runs_and_chunks(tmp_path):
-    rng = np.random.default_rng(8)
+    rng = np.random.default_rng(9)
     s = lambda n: _rand_seq(rng, n)   # noqa: E731
-    N = lambda n: "N" * n             # noqa: E731
-    recs = [
-        ("short_and_edge", s(300) + N(5000) + s(700) + N(5001) + s(900) + N(12) + s(10)),
-        ("leading_short", N(100) + s(2000) + N(6000) + N(1) + s(50) + N(40)),
-        ("leading_long", N(7000) + s(3000) + N(9000)),
-        ("ends_with_3000", s(500) + N(3000)),
-        ("starts_with_3000", N(3000) + s(500)),                                      # 6000 across the border: no split
-        ("ends_with_6000", s(500) + N(6000)),
-        ("starts_with_6000", N(6000) + s(500) + "n" * 5500 + s(100)),               # lower-case n: N either way
-        ("all_n_long", N(20000)),
-        ("all_n_short", N(30)),
-        ("empty", ""),
-        ("tail", s(12345)),
-    ]
+    recs = n_run_records()
     for width in (60, 4096, 10 ** 9):
         want = _check(tmp_path, [_fasta(recs, width=width)], False, tag=f"n{width}_")
         assert len(want.chunks) > len(recs)
