@@ -15,6 +15,7 @@ OK, EINVAL, ENOMEM, ECUDA, ESTATE, ENODEVICE, EPANIC = 0, -1, -2, -3, -4, -5, -6
 POST_FILTER_NS, POST_REORDER, POST_REDUCE_OVERLAP, POST_SORT, POST_ALL = 1, 2, 4, 8, 15
 POST_COMPUTE_SCORE = 16
 LUT_SIZE = 390625
+SLICE_NO_DIRECT, SLICE_NO_REVERSED, SLICE_NO_UNCOMPLEMENTED, SLICE_NO_COMPLEMENTED, SLICE_NO_INTER, SLICE_NO_INTRA, SLICE_MIN_LENGTH = 1, 2, 4, 8, 16, 32, 64
 
 
 class Settings(C.Structure):
@@ -88,7 +89,8 @@ SYMBOLS = [
     "asgart_b200_build_index_group", "asgart_b200_dist_unique_id", "asgart_b200_ctx_dist_init", "asgart_b200_ctx_dist_shutdown",
     "asgart_b200_ctx_ingest_begin", "asgart_b200_ctx_ingest_fasta", "asgart_b200_ctx_ingest_file",
     "asgart_b200_ctx_ingest_finish", "asgart_b200_ctx_download_strand", "asgart_b200_run_files_passes",
-    "asgart_b200_ctx_build_index_trim", "asgart_b200_effective_trim",
+    "asgart_b200_ctx_build_index_trim", "asgart_b200_effective_trim", "asgart_b200_slice_families",
+    "asgart_b200_run_files_sliced",
 ]
 
 _lib = None
@@ -159,9 +161,11 @@ def load() -> C.CDLL:
         "asgart_b200_prepared_free": (None, [vp]),
         "asgart_b200_to_json": (vp, [vp, PS, vp, i64, vp]),
         "asgart_b200_free_string": (None, [vp]),
+        "asgart_b200_slice_families": (i32, [vp, vp, i64, vp, u32, C.c_uint64, i64, C.POINTER(vp)]),
         "asgart_b200_out_filename": (vp, [C.c_char_p, C.c_char_p, C.c_char_p, PS]),
         "asgart_b200_run_files": (vp, [C.c_char_p, PS, i32, C.POINTER(C.c_char_p)]),
         "asgart_b200_run_files_passes": (vp, [C.c_char_p, PS, i32, i32, C.POINTER(C.c_char_p)]),
+        "asgart_b200_run_files_sliced": (vp, [C.c_char_p, PS, i32, i32, u32, C.c_uint64, i64, C.POINTER(C.c_char_p)]),
         "asgart_b200_synth_length": (i64, [i32, i32, i64]),
         "asgart_b200_synth_fill": (i64, [i32, i32, i64, C.c_uint64, i64, i32, vp, i64, i32]),
         "asgart_b200_synth_fragments": (i64, [i32, i32, i64, vp, i64, vp, vp, i64]),

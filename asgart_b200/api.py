@@ -86,6 +86,22 @@ def _chunks_array(chunks: Sequence[Tuple[int, int]]) -> np.ndarray:
     return np.ascontiguousarray(np.array(list(chunks), dtype=np.uint64).reshape(-1, 2))
 
 
+def _take_result(L, rh) -> Families:
+    """Copy a library-owned asgart_b200_result into numpy arrays and free it."""
+    try:
+        nf = L.asgart_b200_result_n_families(rh)
+        ns = L.asgart_b200_result_n_sds(rh)
+        off = np.ctypeslib.as_array(C.cast(L.asgart_b200_result_family_offsets(rh), C.POINTER(C.c_uint64)), shape=(nf + 1,)).copy()
+        if ns:
+            buf = C.string_at(L.asgart_b200_result_sds(rh), ns * PROTOSD_DTYPE.itemsize)
+            sds = np.frombuffer(buf, dtype=PROTOSD_DTYPE).copy()
+        else:
+            sds = np.zeros(0, dtype=PROTOSD_DTYPE)
+        return Families(off, sds)
+    finally:
+        L.asgart_b200_result_free(rh)
+
+
 def device_count() -> int:
     return int(_lib.load().asgart_b200_device_count())
 
@@ -247,19 +263,7 @@ class Context:
 
     # -- search
     def _take(self, rh) -> Families:
-        try:
-            nf = self.L.asgart_b200_result_n_families(rh)
-            ns = self.L.asgart_b200_result_n_sds(rh)
-            off = np.ctypeslib.as_array(C.cast(self.L.asgart_b200_result_family_offsets(rh), C.POINTER(C.c_uint64)),
-                                        shape=(nf + 1,)).copy()
-            if ns:
-                buf = C.string_at(self.L.asgart_b200_result_sds(rh), ns * PROTOSD_DTYPE.itemsize)
-                sds = np.frombuffer(buf, dtype=PROTOSD_DTYPE).copy()
-            else:
-                sds = np.zeros(0, dtype=PROTOSD_DTYPE)
-            return Families(off, sds)
-        finally:
-            self.L.asgart_b200_result_free(rh)
+        return _take_result(self.L, rh)
 
     def search(self, chunks: Sequence[Tuple[int, int]], settings: RunSettings, post_mask: int = POST_ALL) -> Families:
         ch = _chunks_array(chunks)
@@ -399,6 +403,22 @@ class Prepared:
         if not h:
             raise ValueError("prepare_memory: bad fragment table")
         return cls(h)
+
+    def slice(self, fam: Families, no_direct=False, no_reversed=False, no_uncomplemented=False, no_complemented=False,
+              no_inter=False, no_intra=False, min_length: Optional[int] = None, max_family_members: Optional[int] = None) -> Families:
+        """asgart-slice's duplicon filters (src/bin/asgart-slice.rs:126-160) on families in memory; host code only."""
+        flags = (_lib.SLICE_NO_DIRECT * bool(no_direct) | _lib.SLICE_NO_REVERSED * bool(no_reversed)
+                 | _lib.SLICE_NO_UNCOMPLEMENTED * bool(no_uncomplemented) | _lib.SLICE_NO_COMPLEMENTED * bool(no_complemented)
+                 | _lib.SLICE_NO_INTER * bool(no_inter) | _lib.SLICE_NO_INTRA * bool(no_intra)
+                 | _lib.SLICE_MIN_LENGTH * (min_length is not None))
+        off = np.ascontiguousarray(fam.fam_offsets, dtype=np.uint64)
+        sds = np.ascontiguousarray(fam.sds, dtype=PROTOSD_DTYPE)
+        rh = C.c_void_p()
+        rc = self.L.asgart_b200_slice_families(self.h, _ptr(off), len(off) - 1, _ptr(sds) if len(sds) else None, flags, int(min_length or 0),
+                                               -1 if max_family_members is None else int(max_family_members), C.byref(rh))
+        if rc != 0:
+            raise AsgartB200Error(rc, "slice_families failed")
+        return _take_result(self.L, rh)
 
     def to_json(self, settings: RunSettings, fam: Families) -> str:
         st = settings.to_c()

@@ -47,11 +47,6 @@ struct StageA {
 
 using namespace ab200;
 
-struct asgart_b200_result {
-    std::vector<u64> fam_off;
-    std::vector<asgart_b200_protosd> sds;
-};
-
 struct asgart_b200_partial {
     u64 p_begin = 0, p_end = 0;
     std::vector<u32> bits;

@@ -22,6 +22,9 @@ static void usage() {
             "      --trim <START> <STOP>   Trim the first strand: only duplications whose right arm lies in [START, STOP) are searched\n"
             "      --prefix <P>            prefix to prepend to the default output file name\n"
             "      --out <FILE>            set the output file name\n"
+            "      --no-direct --no-reversed --no-uncomplemented --no-complemented --no-inter --no-intra\n"
+            "      --slice-min-length <N> --max-family-members <N>\n"
+            "                              asgart-slice's duplicon filters, applied before the file is written\n"
             "      --device <N>            CUDA device [default: 0]\n"
             "      --with-direct           (with -R/-C) also run the direct pass on the same index and write both, combined as\n"
             "                              `asgart-slice` combines the two runs' files\n"
@@ -36,6 +39,10 @@ int main(int argc, char** argv) {
     std::string prefix, out;
     std::vector<std::string> files;
     int device = 0, verbose = 0, with_direct = 0;
+    uint32_t slice_flags = 0;
+    uint64_t slice_min = 0;
+    long long slice_max = -1;
+    bool slice = false;
     auto need = [&](int& i) -> const char* { if (i + 1 >= argc) { usage(); exit(2); } return argv[++i]; };
     for (int i = 1; i < argc; ++i) {
         std::string a = argv[i];
@@ -49,6 +56,14 @@ int main(int argc, char** argv) {
         else if (a == "--threads" || a == "--chunk-size") need(i);
         else if (a == "--compute-score") st.compute_score = 1;
         else if (a == "--with-direct") with_direct = 1;
+        else if (a == "--no-direct") { slice = true; slice_flags |= ASGART_B200_SLICE_NO_DIRECT; }
+        else if (a == "--no-reversed") { slice = true; slice_flags |= ASGART_B200_SLICE_NO_REVERSED; }
+        else if (a == "--no-uncomplemented") { slice = true; slice_flags |= ASGART_B200_SLICE_NO_UNCOMPLEMENTED; }
+        else if (a == "--no-complemented") { slice = true; slice_flags |= ASGART_B200_SLICE_NO_COMPLEMENTED; }
+        else if (a == "--no-inter") { slice = true; slice_flags |= ASGART_B200_SLICE_NO_INTER; }
+        else if (a == "--no-intra") { slice = true; slice_flags |= ASGART_B200_SLICE_NO_INTRA; }
+        else if (a == "--slice-min-length") { slice = true; slice_flags |= ASGART_B200_SLICE_MIN_LENGTH; slice_min = strtoull(need(i), nullptr, 10); }
+        else if (a == "--max-family-members") { slice = true; slice_max = atoll(need(i)); }
         else if (a == "--trim") { st.has_trim = 1; st.trim_a = strtoull(need(i), nullptr, 10); st.trim_b = strtoull(need(i), nullptr, 10); }
         else if (a == "-h" || a == "--help") { usage(); return 0; }
         else if (a == "--reverse") st.reverse = 1;
@@ -71,7 +86,8 @@ int main(int argc, char** argv) {
     asgart_b200_settings passes[2] = {st, st};
     passes[1].reverse = passes[1].complement = 0;
     const int n_passes = (with_direct && (st.reverse || st.complement)) ? 2 : 1;
-    char* js = asgart_b200_run_files_passes(joined.c_str(), passes, n_passes, device, &err);
+    char* js = slice ? asgart_b200_run_files_sliced(joined.c_str(), passes, n_passes, device, slice_flags, slice_min, slice_max, &err)
+                     : asgart_b200_run_files_passes(joined.c_str(), passes, n_passes, device, &err);
     if (!js) { fprintf(stderr, "asgart-b200: %s\n", err ? err : "failed"); return 1; }
     char* name = asgart_b200_out_filename(joined.c_str(), prefix.c_str(), out.empty() ? nullptr : out.c_str(), &st);
     FILE* f = fopen(name, "wb");

@@ -17,6 +17,8 @@
 #include <thread>
 #include <vector>
 
+#include <new>
+
 #include "../../include/asgart_b200.h"
 #include "host_internal.h"
 
@@ -556,6 +558,45 @@ char* asgart_b200_to_json(const asgart_b200_prepared* p, const asgart_b200_setti
 
 void asgart_b200_free_string(char* s) { free(s); }
 
+// asgart-slice's filters (bin/asgart-slice.rs:126-160 over structs.rs:143-198) on families in memory
+int32_t asgart_b200_slice_families(const asgart_b200_prepared* p, const uint64_t* fam_off, int64_t n_fam, const asgart_b200_protosd* sds,
+                                   uint32_t flags, uint64_t min_length, int64_t max_family_members, asgart_b200_result** out) {
+    if (!p || !out || !fam_off || n_fam < 0 || (fam_off[n_fam] && !sds)) return ASGART_B200_EINVAL;
+    *out = nullptr;
+    static const std::string unknown = "unknown";   // bin/asgart.rs:784-800
+    auto chr = [&](uint64_t pos) -> const std::string& {
+        const Fragment* f = chr_by_pos(p->map, pos);
+        return f ? f->name : unknown;
+    };
+    auto keep = [&](const asgart_b200_protosd& sd) {
+        if ((flags & ASGART_B200_SLICE_NO_DIRECT) && !sd.reversed) return false;            // remove_direct keeps reversed ones
+        if ((flags & ASGART_B200_SLICE_NO_REVERSED) && sd.reversed) return false;
+        if ((flags & ASGART_B200_SLICE_NO_UNCOMPLEMENTED) && !sd.complemented) return false;
+        if ((flags & ASGART_B200_SLICE_NO_COMPLEMENTED) && sd.complemented) return false;
+        if (flags & (ASGART_B200_SLICE_NO_INTER | ASGART_B200_SLICE_NO_INTRA)) {
+            const bool same = chr(sd.left) == chr(sd.right);
+            if ((flags & ASGART_B200_SLICE_NO_INTER) && !same) return false;
+            if ((flags & ASGART_B200_SLICE_NO_INTRA) && same) return false;
+        }
+        if ((flags & ASGART_B200_SLICE_MIN_LENGTH) && std::min(sd.left_length, sd.right_length) < min_length) return false;
+        return true;
+    };
+    const bool drops_empty = flags != 0;   // every duplicon-level filter ends with families.retain(|f| !f.is_empty())
+    auto* r = new (std::nothrow) asgart_b200_result();
+    if (!r) return ASGART_B200_ENOMEM;
+    r->fam_off.push_back(0);
+    for (int64_t f = 0; f < n_fam; ++f) {
+        const size_t before = r->sds.size();
+        for (uint64_t j = fam_off[f]; j < fam_off[f + 1]; ++j) if (keep(sds[j])) r->sds.push_back(sds[j]);
+        const size_t members = r->sds.size() - before;
+        if (members == 0 && drops_empty) continue;
+        if (max_family_members >= 0 && members > size_t(max_family_members)) { r->sds.resize(before); continue; }
+        r->fam_off.push_back(r->sds.size());
+    }
+    *out = r;
+    return ASGART_B200_OK;
+}
+
 // bin/asgart.rs:642-654 (radix = file stems joined by '-'), :695-719, utils.rs:30-49 (extension forced to json)
 char* asgart_b200_out_filename(const char* files, const char* prefix, const char* out, const asgart_b200_settings* st) {
     std::string name;
@@ -592,8 +633,8 @@ char* asgart_b200_out_filename(const char* files, const char* prefix, const char
 // for one or several passes over ONE index. prepare_data runs on the device too (GPU-side FASTA ingest): the files'
 // bytes go to HBM as they are read. Several passes combine as RunResult::from_files does for their JSON files
 // (structs.rs:114-141): strand and settings of the first, families concatenated in pass order.
-char* asgart_b200_run_files_passes(const char* files, const asgart_b200_settings* passes, int32_t n_passes, int32_t device,
-                                   const char** err) {
+static char* run_files_impl(const char* files, const asgart_b200_settings* passes, int32_t n_passes, int32_t device,
+                            uint32_t slice_flags, uint64_t slice_min_length, int64_t slice_max_members, bool slice, const char** err) {
     static thread_local std::string msg;
     if (err) *err = nullptr;
     auto failf = [&](const std::string& m) -> char* { msg = m; if (err) *err = msg.c_str(); return nullptr; };
@@ -641,11 +682,29 @@ char* asgart_b200_run_files_passes(const char* files, const asgart_b200_settings
             asgart_b200_result_free(res);
         }
         if (rc) failf(std::string("device pipeline failed: ") + asgart_b200_ctx_last_error(ctx));
-        else js = asgart_b200_to_json(p, &passes[0], fam_off.data(), int64_t(fam_off.size()) - 1, sds.data());
+        else if (!slice) js = asgart_b200_to_json(p, &passes[0], fam_off.data(), int64_t(fam_off.size()) - 1, sds.data());
+        else {
+            asgart_b200_result* sl = nullptr;
+            rc = asgart_b200_slice_families(p, fam_off.data(), int64_t(fam_off.size()) - 1, sds.data(), slice_flags, slice_min_length,
+                                            slice_max_members, &sl);
+            if (rc) failf("slice_families failed");
+            else js = asgart_b200_to_json(p, &passes[0], sl->fam_off.data(), int64_t(sl->fam_off.size()) - 1, sl->sds.data());
+            delete sl;
+        }
     }
     asgart_b200_ctx_destroy(ctx);
     if (p) asgart_b200_prepared_free(p);
     return js;
+}
+
+char* asgart_b200_run_files_passes(const char* files, const asgart_b200_settings* passes, int32_t n_passes, int32_t device,
+                                   const char** err) {
+    return run_files_impl(files, passes, n_passes, device, 0, 0, -1, false, err);
+}
+
+char* asgart_b200_run_files_sliced(const char* files, const asgart_b200_settings* passes, int32_t n_passes, int32_t device,
+                                   uint32_t slice_flags, uint64_t min_length, int64_t max_family_members, const char** err) {
+    return run_files_impl(files, passes, n_passes, device, slice_flags, min_length, max_family_members, true, err);
 }
 
 char* asgart_b200_run_files(const char* files, const asgart_b200_settings* st, int32_t device, const char** err) {

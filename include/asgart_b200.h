@@ -269,6 +269,31 @@ ASGART_B200_API char *asgart_b200_run_files(const char *files, const asgart_b200
  * (the merge itself; asgart-slice's filters are not part of this). */
 ASGART_B200_API char *asgart_b200_run_files_passes(const char *files, const asgart_b200_settings *passes, int32_t n_passes,
                                                    int32_t device, const char **err);
+/* the same followed by asgart-slice's duplicon filters (asgart_b200_slice_families below) before the JSON is written */
+ASGART_B200_API char *asgart_b200_run_files_sliced(const char *files, const asgart_b200_settings *passes, int32_t n_passes,
+                                                   int32_t device, uint32_t slice_flags, uint64_t min_length,
+                                                   int64_t max_family_members, const char **err);
+
+/* ---- asgart-slice's duplicon filters on families in memory (host code, no device needed) -------
+ * What `asgart-slice` applies to a RunResult before it writes it (src/bin/asgart-slice.rs:126-160), in its order:
+ * --no-direct / --no-reversed / --no-uncomplemented / --no-complemented (RunResult::remove_*, src/structs.rs:143-169),
+ * --no-inter / --no-intra (:171-194; fragment names as the SD conversion assigns them, src/bin/asgart.rs:776-821, so
+ * "unknown" for a position outside every fragment), --min-length (min(left_length, right_length) >= it), every one followed
+ * by dropping the empty families (so families that were already empty stay when no such filter is given, as in the
+ * reference), then --max-family-members (families with more duplicons are dropped, :196-198). min_length counts only with
+ * ASGART_B200_SLICE_MIN_LENGTH (`--min-length 0` still drops empty families); max_family_members < 0 = not given. Not restated: --collapse, --no-inter-relaxed and the
+ * fragment selection (--keep/--restrict/--exclude-fragments), which rewrite the fragment map. */
+#define ASGART_B200_SLICE_NO_DIRECT          1u
+#define ASGART_B200_SLICE_NO_REVERSED        2u
+#define ASGART_B200_SLICE_NO_UNCOMPLEMENTED  4u
+#define ASGART_B200_SLICE_NO_COMPLEMENTED    8u
+#define ASGART_B200_SLICE_NO_INTER          16u
+#define ASGART_B200_SLICE_NO_INTRA          32u
+#define ASGART_B200_SLICE_MIN_LENGTH        64u
+ASGART_B200_API int32_t asgart_b200_slice_families(const asgart_b200_prepared *p, const uint64_t *family_offsets,
+                                                   int64_t n_families, const asgart_b200_protosd *sds, uint32_t flags,
+                                                   uint64_t min_length, int64_t max_family_members,
+                                                   asgart_b200_result **out);
 
 /* ---- GPU-side FASTA ingest ----------------------------------------------------------------
  * read_fasta + find_chunks_to_process of prepare_data (src/bin/asgart.rs:278-366) on the device, for the raw bytes of
