@@ -150,3 +150,14 @@ def test_synth_planted_pairs_found_by_oracle():
     sa = oracle.best_suffix_array(np.array(prep.strand))
     out = oracle.search(np.array(prep.strand), sa, prep.chunks, oracle.make_settings(), oracle.POST_ALL, threads=2)
     assert len(out.families.as_lists()) >= 2
+
+
+def test_effective_trim_matches_the_oracle():
+    """prepare_data's --trim validation (src/bin/asgart.rs:432-463) is host code: C ABI vs the oracle's restatement."""
+    import oracle
+    from asgart_b200.api import effective_trim
+    cases = [((5, 100), 50), ((5, 49), 50), ((5, 5), 50), ((9, 3), 50), ((49, 1000), 50), ((60, 1000), 50), ((0, 1), 50),
+             ((0, 0), 1), ((0, 5), 1), ((3, 2 ** 40), 2 ** 33)]
+    for trim, n1 in cases:
+        assert effective_trim(trim, n1) == oracle.effective_trim(trim, n1), (trim, n1)
+    assert effective_trim((5, 100), 50) == (5, 49) and effective_trim((9, 3), 50) is None
