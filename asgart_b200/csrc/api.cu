@@ -462,7 +462,7 @@ void run_probe_kernels(asgart_b200_ctx* ctx, ProbeParams<IdxT>& P, unsigned long
         P.deep = ix.deep.p; P.deep_depth = ix.deep_depth; P.q6_bits = q6.p; P.deferred = deferred.p;
     }
     // shape (LINEAR = 8 suffixes compared at once, 2 blocks per SM = 128 registers) picked on B200 at C4 size: more
-    // blocks per SM or a shorter LINEAR are slower, the kernel is bound by random DRAM sectors (profiles/r1_probe_variants.log)
+    // blocks per SM or a shorter LINEAR are slower, the kernel is bound by random DRAM sectors (profiles/r1_experiments.log)
     probe_search_kernel<IdxT, 8, 2><<<unsigned(ceil_div(np, 256)), 256, 0, s>>>(P);
     KERNEL_CHECK();
     count_launch();
