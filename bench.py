@@ -380,6 +380,12 @@ def run_ours(args):
                            f"reference's libdivsufsort64 (1 thread, as build.rs builds it) + oracle port of the Rust probe "
                            f"loop/automaton/post-steps on {cores} threads over {len(s_chunks)} chunks (no rustc in this image)"),
                 "phases_s": {k: round(v, 3) for k, v in r.items() if k.endswith("_s")}, "families": r["families"]}
+        try:    # the output side next to the path (FASTA parse and JSON write are reported separately)
+            t0 = time.perf_counter()
+            js = prep.to_json(st, fam)
+            line["json_write"] = {"ms": (time.perf_counter() - t0) * 1e3, "bytes": len(js), "where": "host (serde_json pretty layout, exporters.rs:12-25)"}
+        except Exception as e:   # never lose the bench line over the report
+            line["json_write"] = {"error": str(e)}
         if world == 1 and not args.no_ingest:
             line["ingest"] = measure_ingest(ctx, prep, peak)
         print(json.dumps(line), flush=True)
