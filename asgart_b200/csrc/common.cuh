@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstdint>
 #include <cstdio>
 #include <ctime>
@@ -45,6 +46,20 @@ struct LaunchCounter {
 extern thread_local LaunchCounter* g_launch_counter;
 inline void count_launch(u64 n = 1) {
     if (g_launch_counter) g_launch_counter->total += n;
+}
+
+// cudaFuncSetAttribute is per device: a kernel that needs more than 48 KB of dynamic shared memory has to be prepared on
+// every device that launches it (several contexts of one process may sit on different devices: build_index_group).
+// `prepared` is one bit per device; returns true when the caller still has to set the attribute on the current device —
+// it marks the device with device_prepared() AFTER setting it, so a second thread that sees the bit finds the attribute set.
+inline bool device_needs_prepare(const std::atomic<unsigned long long>& prepared, unsigned long long& bit) {
+    int dev = 0;
+    cuda_check(cudaGetDevice(&dev), "cudaGetDevice", __FILE__, __LINE__);
+    bit = 1ull << (unsigned(dev) & 63u);
+    return (prepared.load(std::memory_order_acquire) & bit) == 0;
+}
+inline void device_prepared(std::atomic<unsigned long long>& prepared, unsigned long long bit) {
+    prepared.fetch_or(bit, std::memory_order_release);
 }
 
 // Host-side stall accounting (developer aid: ASGART_B200_DEBUG_TIMING=1 prints it when a context is destroyed)

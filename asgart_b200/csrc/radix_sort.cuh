@@ -219,11 +219,12 @@ void radix_pass(RadixScratch<KeyT>& ws, const KeyT* kin, const ValT* vin, KeyT* 
     const u64 n = ws.n, tiles = ws.tiles, table = ws.table;
     if (n == 0) return;
     constexpr size_t smem32 = RsSmem<KeyT, ValT, u32, ITEMS>::bytes, smem64 = RsSmem<KeyT, ValT, u64, ITEMS>::bytes;
-    static bool attr_set = false;  // per (KeyT, ValT) instantiation
-    if (!attr_set) {
+    static std::atomic<unsigned long long> prepared{0};  // per (KeyT, ValT) instantiation, one bit per device
+    unsigned long long dev_bit = 0;
+    if (device_needs_prepare(prepared, dev_bit)) {
         CUDA_CHECK(cudaFuncSetAttribute(rs_scatter_kernel<KeyT, ValT, u32, ITEMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem32)));
         CUDA_CHECK(cudaFuncSetAttribute(rs_scatter_kernel<KeyT, ValT, u64, ITEMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem64)));
-        attr_set = true;
+        device_prepared(prepared, dev_bit);
     }
     if (timer) timer->begin();
     rs_hist_kernel<KeyT, ITEMS><<<unsigned(tiles), kRsThreads, 0, stream>>>(kin, n, shift, ws.hist.p, tiles);

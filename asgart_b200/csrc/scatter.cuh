@@ -218,11 +218,12 @@ inline void inverse_permutation_scatter(const u32* idx, const u32* val, u64 n, u
         ki = bufs[w]; vi = bufs[w] + half;
         w ^= 1;
     }
-    static bool attr_set = false;
+    static std::atomic<unsigned long long> prepared{0};   // one bit per device
     constexpr int smem = int(sizeof(u32)) << kBucketHalfBits;
-    if (!attr_set) {
+    unsigned long long dev_bit = 0;
+    if (device_needs_prepare(prepared, dev_bit)) {
         CUDA_CHECK(cudaFuncSetAttribute(bucket_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_set = true;
+        device_prepared(prepared, dev_bit);
     }
     if (timer) timer->begin();
     bucket_scatter_kernel<<<unsigned(ceil_div(n, u64(1) << kBucketBits)), kBucketThreads, smem, stream>>>(ki, vi, n, out);
