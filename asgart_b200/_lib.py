@@ -75,7 +75,7 @@ SYMBOLS = [
     "asgart_b200_divsufsort64", "asgart_b200_divsufsort64_ex", "asgart_b200_version", "asgart_b200_device_count",
     "asgart_b200_ctx_create", "asgart_b200_ctx_destroy", "asgart_b200_ctx_last_error", "asgart_b200_ctx_load_strand",
     "asgart_b200_ctx_build_index", "asgart_b200_ctx_set_index_bits", "asgart_b200_ctx_upload_sa",
-    "asgart_b200_ctx_download_sa", "asgart_b200_ctx_check_sa", "asgart_b200_ctx_download_lut", "asgart_b200_ctx_search",
+    "asgart_b200_ctx_download_sa", "asgart_b200_ctx_check_sa", "asgart_b200_ctx_sa_fingerprint", "asgart_b200_ctx_download_lut", "asgart_b200_ctx_search",
     "asgart_b200_ctx_probe_ranges", "asgart_b200_ctx_search_shard", "asgart_b200_partial_size",
     "asgart_b200_partial_serialize", "asgart_b200_partial_free", "asgart_b200_ctx_finish",
     "asgart_b200_ctx_search_shard_dev", "asgart_b200_ctx_finish_dev",
@@ -132,6 +132,7 @@ def load() -> C.CDLL:
         "asgart_b200_ctx_upload_sa": (i32, [vp, vp]),
         "asgart_b200_ctx_download_sa": (i32, [vp, vp]),
         "asgart_b200_ctx_check_sa": (i32, [vp, vp]),
+        "asgart_b200_ctx_sa_fingerprint": (i32, [vp, vp]),
         "asgart_b200_ctx_download_lut": (i32, [vp, vp, vp]),
         "asgart_b200_ctx_search": (i32, [vp, vp, i64, PS, u32, C.POINTER(vp)]),
         "asgart_b200_ctx_probe_ranges": (i32, [vp, vp, PS, vp, vp, i64]),

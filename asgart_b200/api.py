@@ -51,11 +51,47 @@ PROTOSD_DTYPE = np.dtype([("left", "<u8"), ("right", "<u8"), ("left_length", "<u
 assert PROTOSD_DTYPE.itemsize == C.sizeof(_lib.ProtoSD) == 40
 
 
+def families_digest(fam_offsets, fields, identity, flags) -> str:
+    """sha256 over Vec<ProtoSDsFamily> in the reference's own order (chunk -> flush -> arm creation, src/bin/asgart.rs:241-253):
+    family offsets as little-endian u64, then per duplicon (left, right, left_length, right_length) as u64, identity as f32
+    bits, (reversed, complemented) as bytes. Equal digests <=> equal families, order included."""
+    import hashlib
+    h = hashlib.sha256()
+    h.update(np.ascontiguousarray(fam_offsets).astype("<u8").tobytes())
+    h.update(np.ascontiguousarray(fields).astype("<u8").reshape(-1, 4).tobytes())
+    h.update(np.ascontiguousarray(identity).astype("<f4").tobytes())
+    h.update(np.ascontiguousarray(flags).astype("u1").reshape(-1, 2).tobytes())
+    return h.hexdigest()
+
+
+def sa_fingerprint_host(sa: np.ndarray) -> int:
+    """The order-sensitive 64-bit fingerprint Context.sa_fingerprint computes on the device, for a host array:
+    sum over i of splitmix64(SA[i] + i * 0x9E3779B97F4A7C15) mod 2^64 (numpy, chunked)."""
+    total = np.uint64(0)
+    step = 1 << 24
+    with np.errstate(over="ignore"):
+        for o in range(0, len(sa), step):
+            v = np.asarray(sa[o:o + step]).astype(np.uint64)
+            z = v + np.arange(o, o + len(v), dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15)
+            z = z + np.uint64(0x9E3779B97F4A7C15)
+            z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+            z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+            z = z ^ (z >> np.uint64(31))
+            total = total + z.sum(dtype=np.uint64)
+    return int(total)
+
+
 @dataclass
 class Families:
     """Vec<ProtoSDsFamily> as CSR: family f = sds[fam_offsets[f]:fam_offsets[f+1]] (structured array, ProtoSD layout)."""
     fam_offsets: np.ndarray
     sds: np.ndarray
+
+    def digest(self) -> str:
+        s = self.sds
+        fields = np.stack([s["left"], s["right"], s["left_length"], s["right_length"]], axis=1) if len(s) else np.zeros((0, 4), "<u8")
+        flags = np.stack([s["reversed"], s["complemented"]], axis=1) if len(s) else np.zeros((0, 2), "u1")
+        return families_digest(self.fam_offsets, fields, s["identity"], flags)
 
     def as_lists(self):
         out = []
@@ -254,6 +290,12 @@ class Context:
         bad = C.c_int64()
         self._check(self.L.asgart_b200_ctx_check_sa(self.h, C.byref(bad)))
         return bad.value
+
+    def sa_fingerprint(self) -> int:
+        """Order-sensitive 64-bit fingerprint of the index computed on the device (== sa_fingerprint_host of the array)."""
+        fp = C.c_uint64()
+        self._check(self.L.asgart_b200_ctx_sa_fingerprint(self.h, C.byref(fp)))
+        return fp.value
 
     def download_lut(self) -> Tuple[np.ndarray, np.ndarray]:
         lo = np.empty(_lib.LUT_SIZE, dtype=np.int64)

@@ -22,7 +22,7 @@
 
 namespace ab200 {
 thread_local LaunchCounter* g_launch_counter = nullptr;
-HostStalls g_host_stalls;
+thread_local HostStalls g_host_stalls;   // per thread: the members of build_index_group count their own stalls
 thread_local DevicePool* g_device_pool = nullptr;
 
 struct Index32 { DevBuf<u32> sa, lut_lo, lut_hi, deep; int deep_depth = 0; };
@@ -95,9 +95,9 @@ const u64 kPartialMagic = 0x4132303050415254ull;  // "A200PART"
 struct ApiGuard {
     asgart_b200_ctx* c;
     explicit ApiGuard(asgart_b200_ctx* ctx) : c(ctx) {
+        CUDA_CHECK(cudaSetDevice(ctx->device));   // may throw: the thread-locals are only set once nothing can fail any more
         g_launch_counter = &ctx->launches;
         g_device_pool = &ctx->pool;
-        CUDA_CHECK(cudaSetDevice(ctx->device));
     }
     ~ApiGuard() { g_launch_counter = nullptr; g_device_pool = nullptr; }
 };
@@ -251,6 +251,7 @@ struct LutHook : SaKeyHook {
 
 template <typename IdxT>
 void build_index_t(asgart_b200_ctx* ctx) {
+    NvtxRange nv("build_index");
     auto& ix = IxOf<IdxT>::get(ctx);
     EventTimer tsa(ctx->stream), tlut(ctx->stream);
     tsa.start();
@@ -398,6 +399,38 @@ i64 check_sa_t(asgart_b200_ctx* ctx) {
     return i64(h);
 }
 
+// order-sensitive 64-bit fingerprint of the index: sum over i of splitmix64(SA[i] + i * 0x9E3779B97F4A7C15) mod 2^64
+__device__ __forceinline__ u64 fp_mix(u64 z) {
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+template <typename IdxT>
+__global__ void __launch_bounds__(256) sa_fingerprint_kernel(const IdxT* __restrict__ sa, u64 n, unsigned long long* __restrict__ out) {
+    u64 acc = 0;
+    const u64 stride = u64(gridDim.x) * blockDim.x;
+    for (u64 i = u64(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) acc += fp_mix(u64(sa[i]) + i * 0x9E3779B97F4A7C15ull);
+#pragma unroll
+    for (int d = 16; d; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+    if ((threadIdx.x & 31u) == 0) atomicAdd(out, (unsigned long long)acc);
+}
+template <typename IdxT>
+u64 sa_fingerprint_t(asgart_b200_ctx* ctx) {
+    auto& ix = IxOf<IdxT>::get(ctx);
+    cudaStream_t s = ctx->stream;
+    DevBuf<unsigned long long> acc(1, s);
+    acc.zero();
+    const unsigned grid = unsigned(std::min<u64>(ceil_div(ctx->sa_len, 256), u64(kNumSMs) * 16));
+    sa_fingerprint_kernel<IdxT><<<grid, 256, 0, s>>>(ix.sa.p, ctx->sa_len, acc.p);
+    KERNEL_CHECK();
+    count_launch();
+    unsigned long long h = 0;
+    CUDA_CHECK(cudaMemcpyAsync(&h, acc.p, sizeof h, cudaMemcpyDeviceToHost, s));
+    CUDA_CHECK(cudaStreamSynchronize(s));
+    return u64(h);
+}
+
 // ---------------------------------------------------------------------------------------------- chunk plan
 int make_plan(asgart_b200_ctx* ctx, const asgart_b200_chunk* chunks, i64 n_chunks, const asgart_b200_settings* st, ChunkPlan& plan) {
     if (!chunks || n_chunks < 0 || !st) return fail(ctx, ASGART_B200_EINVAL, "null chunks/settings");
@@ -482,6 +515,7 @@ void run_probe_kernels(asgart_b200_ctx* ctx, ProbeParams<IdxT>& P, unsigned long
 
 template <typename IdxT>
 void run_stage_a(asgart_b200_ctx* ctx, const ChunkPlan& plan, const asgart_b200_settings* st, u64 p_begin, u64 p_end, StageA& A) {
+    NvtxRange nv("search/stage A: probe search + emit");
     auto& ix = IxOf<IdxT>::get(ctx);
     cudaStream_t s = ctx->stream;
     A.p_begin = p_begin; A.p_end = p_end;
@@ -549,13 +583,22 @@ void run_stage_a(asgart_b200_ctx* ctx, const ChunkPlan& plan, const asgart_b200_
 // ---------------------------------------------------------------------------------------------- post-steps
 // d_sds / d_off are replaced by the post-processed families
 void run_post(asgart_b200_ctx* ctx, DevBuf<asgart_b200_protosd>& d_sds, DevBuf<u64>& d_off, u64& n_fam, u64& n_sds, u32 post_mask) {
+    NvtxRange nv("post-steps: FilterNs/ReOrder/ReduceOverlap/Sort");
     cudaStream_t s = ctx->stream;
     if (n_fam == 0 || post_mask == 0) return;
     DevBuf<u8> keep(n_sds, s);
     if (post_mask & ASGART_B200_POST_FILTER_NS) {
-        n_content_kernel<<<unsigned(n_sds), 256, 0, s>>>(ctx->d_text.p, d_sds.p, n_sds, keep.p);
+        DevBuf<u32> oob(1, s);
+        oob.zero();
+        n_content_kernel<<<unsigned(n_sds), 256, 0, s>>>(ctx->d_text.p, ctx->n1, d_sds.p, n_sds, keep.p, oob.p);
         KERNEL_CHECK();
         count_launch();
+        u32 h_oob = 0;
+        CUDA_CHECK(cudaMemcpyAsync(&h_oob, oob.p, sizeof h_oob, cudaMemcpyDeviceToHost, s));
+        CUDA_CHECK(cudaStreamSynchronize(s));
+        if (h_oob)
+            throw CudaError(ASGART_B200_EPANIC, "FilterNs: an arm's inclusive range reaches past the strand; the reference panics here "
+                                                "(slice index out of range, src/structs.rs:455-466)");
     }
     DevBuf<u64> new_count(n_fam, s);
     post_family_kernel<<<unsigned(ceil_div(n_fam, 64)), 64, 0, s>>>(d_sds.p, d_off.p, n_fam, keep.p, post_mask, new_count.p);
@@ -593,6 +636,7 @@ void run_post(asgart_b200_ctx* ctx, DevBuf<asgart_b200_protosd>& d_sds, DevBuf<u
 // ComputeScore (src/bin/asgart.rs:98-111): the reference runs it between ReduceOverlap and Sort; the identity of a duplicon
 // depends on its own fields only and Sort only permutes, so it is computed on the final list.
 void run_score(asgart_b200_ctx* ctx, DevBuf<asgart_b200_protosd>& d_sds, u64 n_sds) {
+    NvtxRange nv("post-steps: ComputeScore");
     if (n_sds == 0) return;
     if (!ctx->have_strand) throw CudaError(ASGART_B200_ESTATE, "ComputeScore needs a loaded strand");
     LevStats ls;
@@ -634,6 +678,7 @@ __global__ void chunk_tc_kernel(const ChunkDev* __restrict__ chunks, u32 n_chunk
 void run_stage_b(asgart_b200_ctx* ctx, const ChunkPlan& plan, const asgart_b200_settings* st, const u32* d_bits, u64 n_events,
                  const u64* ev_probe, const u32* ev_cnt, const u64* ev_moff, const u64* matches, u64 n_matches, u32 post_mask,
                  asgart_b200_result* result) {
+    NvtxRange nv("search/stage B: automaton + families");
     cudaStream_t s = ctx->stream;
     EventTimer tauto(s), tpost(s);
     tauto.start();
@@ -1182,6 +1227,15 @@ int32_t asgart_b200_ctx_check_sa(asgart_b200_ctx* ctx, int64_t* n_bad) {
         if (!n_bad) return fail(ctx, ASGART_B200_EINVAL, "null output");
         if (ctx->sa_len != ctx->n1) return fail(ctx, ASGART_B200_ESTATE, "check_sa: the index was built with --trim (it is not a suffix array of the strand)");
         if (ctx->idx_bits == 32) *n_bad = check_sa_t<u32>(ctx); else *n_bad = check_sa_t<u64>(ctx);
+        return ASGART_B200_OK;
+    });
+}
+
+int32_t asgart_b200_ctx_sa_fingerprint(asgart_b200_ctx* ctx, uint64_t* fingerprint) {
+    return guarded(ctx, [&]() -> int32_t {
+        if (!ctx->have_index) return fail(ctx, ASGART_B200_ESTATE, "sa_fingerprint before build_index");
+        if (!fingerprint) return fail(ctx, ASGART_B200_EINVAL, "null output");
+        *fingerprint = ctx->idx_bits == 32 ? sa_fingerprint_t<u32>(ctx) : sa_fingerprint_t<u64>(ctx);
         return ASGART_B200_OK;
     });
 }

@@ -420,12 +420,18 @@ __global__ void __launch_bounds__(W * 32) automaton_segment_kernel(AutoBuffers B
 
 // ------------------------------------------------------------------------------------------------ post-steps
 // FilterNs: count of N over strand[p ..= p+len] for both arms (src/structs.rs:454-467), one block per duplicon
-__global__ void __launch_bounds__(256) n_content_kernel(const u8* __restrict__ text, const asgart_b200_protosd* __restrict__ sds, u64 n_sds,
-                                                        u8* __restrict__ keep) {
+// An arm whose inclusive range passes the end of the strand (n1 bytes, '$' included) makes the reference panic on the slice
+// (src/structs.rs:455-466); here it raises *oob and the duplicon is left alone — nothing is read out of bounds.
+__global__ void __launch_bounds__(256) n_content_kernel(const u8* __restrict__ text, u64 n1, const asgart_b200_protosd* __restrict__ sds,
+                                                        u64 n_sds, u8* __restrict__ keep, u32* __restrict__ oob) {
     __shared__ u64 s_l[8], s_r[8];
     const u64 j = blockIdx.x;
     if (j >= n_sds) return;
     const asgart_b200_protosd sd = sds[j];
+    if (sd.left >= n1 || sd.left_length >= n1 - sd.left || sd.right >= n1 || sd.right_length >= n1 - sd.right) {
+        if (threadIdx.x == 0) { keep[j] = 0; atomicOr(oob, 1u); }
+        return;
+    }
     u64 cl = 0, cr = 0;
     for (u64 p = sd.left + threadIdx.x; p <= sd.left + sd.left_length; p += 256) { u8 c = text[p]; cl += (c == 'N' || c == 'n'); }
     for (u64 p = sd.right + threadIdx.x; p <= sd.right + sd.right_length; p += 256) { u8 c = text[p]; cr += (c == 'N' || c == 'n'); }

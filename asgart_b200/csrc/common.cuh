@@ -1,6 +1,7 @@
 // common.cuh — error handling, stream-ordered device buffers, small device helpers (sm_100a).
 #pragma once
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 
 #include <atomic>
 #include <cstdint>
@@ -67,7 +68,7 @@ struct HostStalls {
     double alloc_ms = 0, sync_ms = 0;
     u64 allocs = 0, syncs = 0;
 };
-extern HostStalls g_host_stalls;
+extern thread_local HostStalls g_host_stalls;
 inline double host_now_ms() {
     timespec ts;
     clock_gettime(CLOCK_MONOTONIC, &ts);
@@ -169,6 +170,21 @@ struct DevBuf {
     }
     void zero() { if (p) CUDA_CHECK(cudaMemsetAsync(p, 0, n * sizeof(T), s)); }
     size_t bytes() const { return n * sizeof(T); }
+};
+
+// NVTX ranges around the phases of the pipeline (header-only NVTX3: a no-op unless a profiler is attached)
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange&) = delete;
+    NvtxRange& operator=(const NvtxRange&) = delete;
+};
+// consecutive phases of one function: next() closes the running range and opens the named one
+struct NvtxPhases {
+    bool open = false;
+    void next(const char* name) { if (open) nvtxRangePop(); nvtxRangePushA(name); open = true; }
+    void close() { if (open) nvtxRangePop(); open = false; }
+    ~NvtxPhases() { close(); }
 };
 
 inline int ceil_div_i(i64 a, i64 b) { return int((a + b - 1) / b); }

@@ -158,4 +158,61 @@ AB_HD uint32_t ceil_log2_u64(uint64_t v) {  // ceil(log2(v)), v >= 1
     return l;
 }
 
+
+// ---- the reference's 8-mer bucket search, probe for probe (row N4, --trim; libdivsufsort/lib/utils.c:282-349 sa_search as
+// called by Searcher::new, src/searcher.rs:118-128) ------------------------------------------------------------------
+// With --trim the array is not sorted for the text it is compared with near the trim end, so the result is
+// defined by WHICH suffixes the reference looks at, not by an order: every descent below visits the same middles and
+// skips the same already-matched symbols as the reference does. One descent = repeated halving of SA[lo, lo+len):
+// the middle suffix is compared with P from the first symbol that the two sides are not yet known to share; going right
+// keeps (middle, end), going left keeps [lo, middle). Three descents make a search: to the first suffix that equals P
+// (STOP_AT_EQUAL), then a lower bound over what was left of it and an upper bound over what was right of it.
+enum LiteralMode { STOP_AT_EQUAL = 0, LOWER_BOUND = 1, UPPER_BOUND = 2 };
+
+// sign of (suffix at `suf`) - P over the 8 symbols of P, reading from symbol `known` on; `known` becomes the number of
+// leading symbols found equal. A suffix that ends inside P is smaller.
+AB_HD int literal_cmp8(const uint8_t* T, int64_t tsize, const uint8_t* P, int64_t suf, int64_t& known) {
+    int64_t m = known;
+    int diff = 0;
+    for (; m < 8 && suf + m < tsize; ++m) {
+        diff = int(T[suf + m]) - int(P[m]);
+        if (diff) break;
+    }
+    known = m;
+    return diff ? diff : (m < 8 ? -1 : 0);
+}
+
+// returns true when MODE == STOP_AT_EQUAL met an equal suffix: [lo, lo+len) is then the interval that was being halved,
+// its middle lo + len/2 is that suffix and known_mid the symbols matched there (8)
+template <int MODE, typename IdxT>
+AB_HD bool literal_descent(const uint8_t* T, int64_t tsize, const uint8_t* P, const IdxT* SA, int64_t& lo, int64_t& len,
+                           int64_t& known_lo, int64_t& known_hi, int64_t& known_mid) {
+    while (len > 0) {
+        const int64_t mid = len >> 1;
+        int64_t m = known_lo < known_hi ? known_lo : known_hi;
+        const int r = literal_cmp8(T, tsize, P, int64_t(SA[lo + mid]), m);
+        if (MODE == STOP_AT_EQUAL && r == 0) { known_mid = m; return true; }
+        const bool right = (MODE == UPPER_BOUND) ? r <= 0 : r < 0;
+        if (right) { lo += mid + 1; len -= mid + 1; known_lo = m; }
+        else { len = mid; known_hi = m; }
+    }
+    return false;
+}
+
+// (first, count) as sa_search reports them: count suffixes from SA[first] on start with P; count == 0: first = where the
+// first descent ended (the reference's insertion point)
+template <typename IdxT>
+AB_HD void literal_bucket(const uint8_t* T, int64_t tsize, const uint8_t* P, const IdxT* SA, int64_t sa_size, int64_t& first,
+                          int64_t& count) {
+    int64_t lo = 0, len = sa_size, k_lo = 0, k_hi = 0, k_mid = 0;
+    if (!literal_descent<STOP_AT_EQUAL, IdxT>(T, tsize, P, SA, lo, len, k_lo, k_hi, k_mid)) { first = lo; count = 0; return; }
+    const int64_t mid = len >> 1;
+    int64_t a = lo, a_len = mid, a_lo = k_lo, a_hi = k_mid, unused = 0;
+    literal_descent<LOWER_BOUND, IdxT>(T, tsize, P, SA, a, a_len, a_lo, a_hi, unused);
+    int64_t b = lo + mid + 1, b_len = len - mid - 1, b_lo = k_mid, b_hi = k_hi;
+    literal_descent<UPPER_BOUND, IdxT>(T, tsize, P, SA, b, b_len, b_lo, b_hi, unused);
+    first = a;
+    count = b - a;
+}
+
 }  // namespace ab200

@@ -474,7 +474,10 @@ void build_suffix_array(const u8* d_text, u64 n, IdxT* d_sa, const RankView<IdxT
         dbg_t = t;
     };
 
+    NvtxRange nv_all("sa_build");
+    NvtxPhases nv;
     // ---- 0. alphabet
+    nv.next("sa_build/alphabet+ranges");
     DevBuf<unsigned long long> d_hist(256, stream);
     d_hist.zero();
     {
@@ -549,6 +552,7 @@ void build_suffix_array(const u8* d_text, u64 n, IdxT* d_sa, const RankView<IdxT
     }
     IdxT* const sa_loc = d_sa + base;
     phase("alphabet+ranges", n_loc);
+    nv.next("sa_build/init keys");
 
     {
         std::vector<int> shifts;
@@ -581,13 +585,16 @@ void build_suffix_array(const u8* d_text, u64 n, IdxT* d_sa, const RankView<IdxT
             count_launch(2);
         }
         phase("init keys", n_loc);
+        nv.next("sa_build/initial sort");
         radix_sort_pairs<u64, IdxT>(k, ka, v, va, n_loc, shifts.data(), int(shifts.size()), stream, st ? st->sort : nullptr,
                                     st ? st->scatter_main : nullptr);
         phase("initial sort", shifts.size());
+        nv.next("sa_build/lookup tables");
         if (grp && n_loc) CUDA_CHECK(cudaMemcpyAsync(sa_loc, v, n_loc * sizeof(IdxT), cudaMemcpyDeviceToDevice, stream));
 
         if (hook) hook->on_sorted_keys(k, n_loc, base, n, b, p0, h_code, stream, grp);
         phase("lookup tables");
+        nv.next("sa_build/heads+rank scatter");
         const u64* kk = k;
         const IdxT* vv = sa_loc;
         if (st && st->rank) st->rank->begin();
@@ -627,6 +634,7 @@ void build_suffix_array(const u8* d_text, u64 n, IdxT* d_sa, const RankView<IdxT
         if (st && st->rank) st->rank->end(4, 0);
         phase("heads+rank scatter", UA + US);
     }
+    nv.next("sa_build/run round");
 
     // ---- 3. run round: suffixes starting a run of >= p0 equal symbols are ordered by (symbol after the run, run length)
     // in one sort and then continue at depth = run length, instead of needing log2(run length) doubling rounds
@@ -715,6 +723,7 @@ void build_suffix_array(const u8* d_text, u64 n, IdxT* d_sa, const RankView<IdxT
     }
     GS.release(); IS.release();
     phase("run round", US);
+    nv.next("sa_build/doubling rounds");
 
     // ---- 4. merged work list: ordinary groups at depth p0, then the run groups at depth = run length
     U = UA + US2; NG = NGA + NGS2;
@@ -835,6 +844,7 @@ void build_suffix_array(const u8* d_text, u64 n, IdxT* d_sa, const RankView<IdxT
         H <<= 1;
     }
     phase("doubling rounds", st ? st->rounds : 0);
+    nv.next("sa_build/share SA pieces");
     if (grp) grp->share_pieces(d_sa, piece_off.data(), int(sizeof(IdxT)), stream);
     phase("share SA pieces");
 }

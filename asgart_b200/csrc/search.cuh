@@ -60,67 +60,21 @@ __global__ void lut_build_kernel(const u64* __restrict__ PT, const IdxT* __restr
 // Searcher::new with --trim (src/searcher.rs:99-143 over the array of src/bin/asgart.rs:142-147): SA holds the suffixes of
 // strand[a..b]+'$' (shifted by a) but sa_searchb64 compares them inside the WHOLE strand, so near b the array is not sorted
 // for what it is compared with and the bucket borders are whatever the reference's bisection lands on. One thread per
-// 8-mer runs that bisection step for step (libdivsufsort/lib/utils.c:244-255 _compare with its `match` skipping, :282-349
-// sa_search: one bisection until a suffix matches, then lower bound of the left part and upper bound of the right part).
-// Slot = 8-mer as base-5 number with digits A,C,G,N,T; empty buckets get lo = hi = the reference's insertion point.
-__device__ __forceinline__ int lit_compare(const u8* __restrict__ T, i64 Tsize, const u8* P, i64 suf, i64& match) {
-    i64 i = suf + match, j = match;
-    int r = 0;
-    while (i < Tsize && j < 8) {
-        r = int(T[i]) - int(P[j]);
-        if (r != 0) break;
-        ++i; ++j;
-    }
-    match = j;
-    if (r != 0) return r;
-    return j != 8 ? -1 : 0;
-}
-
+// 8-mer replays that probe sequence (literal_bucket, kmer_core.h). Slot = 8-mer as base-5 number with digits A,C,G,N,T;
+// empty buckets get lo = hi = the reference's insertion point.
 template <typename IdxT>
-__global__ void lut_literal_kernel(const u8* __restrict__ T, u64 Tsize_, const IdxT* __restrict__ SA, u64 SAsize_,
+__global__ void lut_literal_kernel(const u8* __restrict__ T, u64 Tsize, const IdxT* __restrict__ SA, u64 SAsize,
                                    IdxT* __restrict__ lut_lo, IdxT* __restrict__ lut_hi) {
     const u32 slot = blockIdx.x * blockDim.x + threadIdx.x;
     if (slot >= 390625u) return;
     u8 P[8];
-    {
-        u32 v = slot;
+    u32 v = slot;
 #pragma unroll
-        for (int j = 7; j >= 0; --j) { P[j] = u8("ACGNT"[v % 5u]); v /= 5u; }
-    }
-    const i64 Tsize = i64(Tsize_);
-    i64 i = 0, j = 0, k = 0, lmatch = 0, rmatch = 0;
-    i64 size = i64(SAsize_), half = size >> 1;
-    while (size > 0) {
-        i64 match = lmatch < rmatch ? lmatch : rmatch;
-        const int r = lit_compare(T, Tsize, P, i64(SA[i + half]), match);
-        if (r < 0) {
-            i += half + 1;
-            half -= (size & 1) ^ 1;
-            lmatch = match;
-        } else if (r > 0) {
-            rmatch = match;
-        } else {
-            i64 lsize = half, rsize = size - half - 1;
-            j = i; k = i + half + 1;
-            i64 llmatch = lmatch, lrmatch = match;
-            for (i64 h = lsize >> 1; lsize > 0; lsize = h, h >>= 1) {
-                i64 m = llmatch < lrmatch ? llmatch : lrmatch;
-                if (lit_compare(T, Tsize, P, i64(SA[j + h]), m) < 0) { j += h + 1; h -= (lsize & 1) ^ 1; llmatch = m; }
-                else lrmatch = m;
-            }
-            i64 rlmatch = match, rrmatch = rmatch;
-            for (i64 h = rsize >> 1; rsize > 0; rsize = h, h >>= 1) {
-                i64 m = rlmatch < rrmatch ? rlmatch : rrmatch;
-                if (lit_compare(T, Tsize, P, i64(SA[k + h]), m) <= 0) { k += h + 1; h -= (rsize & 1) ^ 1; rlmatch = m; }
-                else rrmatch = m;
-            }
-            break;
-        }
-        size = half; half >>= 1;
-    }
-    const i64 first = (k - j) > 0 ? j : i;
+    for (int j = 7; j >= 0; --j) { P[j] = u8("ACGNT"[v % 5u]); v /= 5u; }
+    int64_t first = 0, count = 0;
+    literal_bucket<IdxT>(T, int64_t(Tsize), P, SA, int64_t(SAsize), first, count);
     lut_lo[slot] = IdxT(first);
-    lut_hi[slot] = IdxT(first + (k - j));
+    lut_hi[slot] = IdxT(first + count);
 }
 
 template <typename IdxT>

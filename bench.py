@@ -111,25 +111,88 @@ def make_workload(config: int, scale_n: int):
     return st, prep
 
 
+def oracle_settings(st):
+    import oracle
+    return oracle.make_settings(probe_size=st.probe_size, gap_size=st.gap_size, min_length=st.min_duplication_length,
+                                max_cardinality=st.max_cardinality, reverse=st.reverse, complement=st.complement,
+                                skip_masked=st.skip_masked)
+
+
+def oracle_workload(config: int, scale_n: int):
+    """The workload as the REFERENCE side sees it: same generated bases, but normalisation table aside, the fragment
+    map, the chunk list and the '$' come from the oracle's restatement of prepare_data (src/bin/asgart.rs:273-471) — used
+    by the reference arm, cpu_baseline and tests/golden/make_families_golden.py, never by our arm."""
+    import asgart_b200 as ab
+    import oracle
+    flags = CONFIG_FLAGS[config]
+    st = ab.RunSettings(**flags)
+    threads = os.cpu_count() or 8
+    if config == 5:
+        ga, fa = ab.synth_genome(5, part=0, scale_n=scale_n // 2, threads=threads)
+        gb, fb = ab.synth_genome(5, part=1, scale_n=scale_n // 2, threads=threads)
+        fr = fa + [(nm, pos + len(ga), ln) for nm, pos, ln in fb]
+        g = np.concatenate([ga, gb])
+        del ga, gb
+        names = "synthC5_A.fa, synthC5_B.fa"
+    else:
+        g, fr = ab.synth_genome(config, scale_n=scale_n, threads=threads)
+        names = f"synthC{config}.fa"
+    g = ab.normalise(g, st.skip_masked)
+    prep = oracle.Prepared.from_memory(g, fr, names)
+    del g
+    return st, prep
+
+
 def searched_bp(prep) -> int:
     return int(sum(c[1] for c in prep.chunks))
+
+
+def golden(config: int):
+    """tests/golden/families_c<config>.json: the oracle's digests of the full-size config, made offline on the CPU."""
+    try:
+        with open(os.path.join(ROOT, "tests", "golden", f"families_c{config}.json")) as f:
+            return json.load(f)
+    except Exception:
+        return None
+
+
+def workload_config(config: int, scale_n: int, st, strand_bp: int, bp: int, n_chunks: int):
+    """The `config` object of the JSON line: the workload, identical for our arm and for --impl reference (which runs a
+    bounded sample of it and says so in cpu_baseline.sample / sample_bp)."""
+    return {"workload": CONFIG_NAMES[config], "strand_bp": strand_bp, "searched_bp": bp, "chunks": n_chunks,
+            "flags": CONFIG_FLAGS[config], "probe_size": st.probe_size, "gap_size": st.gap_size,
+            "min_duplication_length": st.min_duplication_length, "max_cardinality": st.max_cardinality,
+            "scale_n": scale_n or None,
+            "l2": "inputs larger than L2 (text + suffix array + sort buffers > 1 GB per step vs 126 MB L2); no flush needed"}
 
 
 # ---------------------------------------------------------------------------------------------------- reference arm
 def cpu_reference_pass(strand: np.ndarray, chunks, st, threads: int):
     """One pass of the reference algorithm on the CPU. The only place (with cpu_baseline) bench.py executes oracle/."""
     import oracle
-    so = oracle.make_settings(probe_size=st.probe_size, gap_size=st.gap_size, min_length=st.min_duplication_length,
-                              max_cardinality=st.max_cardinality, reverse=st.reverse, complement=st.complement,
-                              skip_masked=st.skip_masked)
+    from asgart_b200.api import families_digest
+    so = oracle_settings(st)
     kind = "reference" if oracle.ref() is not None else "port"
     t0 = time.perf_counter()
     sa = oracle.ref_divsufsort64(strand) if oracle.ref() is not None else oracle.suffix_array(strand)   # single thread, like build.rs builds it
     t1 = time.perf_counter()
     out = oracle.search(strand, sa, chunks, so, oracle.POST_ALL, threads=threads)
     t2 = time.perf_counter()
+    f = out.families
     return {"seconds": t2 - t0, "sa_s": t1 - t0, "lut_s": out.seconds["lut"], "search_s": out.seconds["search"],
-            "post_s": out.seconds["post"], "families": len(out.families.fam_offsets) - 1, "sa_kind": kind}
+            "post_s": out.seconds["post"], "families": len(f.fam_offsets) - 1, "duplicons": len(f.fields), "sa_kind": kind,
+            "families_sha256": families_digest(f.fam_offsets, f.fields, f.identity, f.flags)}
+
+
+REF_SAMPLE_BP = 57_227_415      # the reference arm's sample per step: the workload's generator scaled to C2's length
+
+
+def reference_sample_n(config: int, scale_n: int, passes: int) -> int:
+    """Genome length the CPU arm runs per step: the whole workload when it is small enough, else the same generator
+    scaled to REF_SAMPLE_BP (about 6-9 s per pass on 8-16 host cores), shrunk further when more than 25 passes are asked."""
+    full_n = scale_n or FULL_N[config]
+    cap = REF_SAMPLE_BP if passes <= 25 else max(2_000_000, REF_SAMPLE_BP * 25 // passes)
+    return min(full_n, cap)
 
 
 def run_reference(args):
@@ -138,11 +201,10 @@ def run_reference(args):
         return
     cores = os.cpu_count() or 1
     full_n = args.scale_n or FULL_N[args.config]
-    # bounded sample: ~0.4 us/bp of CPU work measured on this class of host; keep the whole run near two minutes
-    budget_bp = int(120.0 / 0.4e-6 / max(1, args.steps + args.warmup))
-    sample_n = min(full_n, max(2_000_000, budget_bp))
-    st, prep = make_workload(args.config, 0 if sample_n == FULL_N[args.config] else sample_n)
-    strand = np.array(prep.strand)
+    sample_n = args.ref_sample_bp or reference_sample_n(args.config, args.scale_n, args.steps + args.warmup)
+    sample_n = min(sample_n, full_n)
+    st, prep = oracle_workload(args.config, 0 if sample_n == FULL_N[args.config] else sample_n)   # chunker: the oracle's prepare_data
+    strand = prep.strand
     bp = searched_bp(prep)
     for _ in range(args.warmup):
         cpu_reference_pass(strand, prep.chunks, st, cores)
@@ -152,19 +214,36 @@ def run_reference(args):
         last = cpu_reference_pass(strand, prep.chunks, st, cores)
     dt = time.perf_counter() - t0
     value = bp * args.steps / dt
-    sample = (f"{'whole' if sample_n == full_n else 'scaled'} workload: {len(strand) - 1} bp generated by the same generator "
-              f"(config C{args.config}), {bp} bp in chunks; SA by the reference's libdivsufsort64 (1 thread) + oracle port of the "
-              f"Rust probe loop/automaton/post-steps ({cores} threads over {len(prep.chunks)} chunks)")
+    g = golden(args.config) if not args.scale_n else None
+    whole = sample_n == full_n
+    if whole:
+        full_bp, full_chunks = bp, len(prep.chunks)
+    elif g:
+        full_bp, full_chunks = g["searched_bp"], g["n_chunks"]
+    else:
+        full_bp, full_chunks = None, None
+    sample = (f"{'whole workload' if whole else 'bounded sample of the workload'}: {len(strand) - 1} of {full_n} bp "
+              f"(same generator and seeds, config C{args.config}{'' if whole else ', scaled'}), {bp} bp in {len(prep.chunks)} chunks cut by the "
+              f"oracle's prepare_data; SA by the reference's libdivsufsort64 (1 thread, as build.rs builds it) + oracle port of the "
+              f"Rust probe loop/automaton/post-steps ({cores} threads, one task per chunk; no rustc in this image)")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "bp/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "u8/int64", "data": "synthetic",
-        "config": {"workload": CONFIG_NAMES[args.config], "sample_bp": len(strand) - 1, "flags": CONFIG_FLAGS[args.config]},
+        "config": workload_config(args.config, args.scale_n, st, full_n, full_bp, full_chunks),
+        "sample_bp": len(strand) - 1, "full_bp": full_n, "sample_fraction": (len(strand) - 1) / full_n,
         "cpu_baseline": {"value": value, "unit": "bp/s", "cores": cores, "kind": last["sa_kind"] if last else "port", "sample": sample,
-                         "phases_s": {k: round(v, 3) for k, v in (last or {}).items() if k.endswith("_s")}},
+                         "phases_s": {k: round(v, 3) for k, v in (last or {}).items() if k.endswith("_s")},
+                         "families": last["families"] if last else None, "families_sha256": last["families_sha256"] if last else None},
         "e2e": {"value": value, "unit": "bp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if g:   # the one same-input CPU datapoint: the whole config, run offline by tests/golden/make_families_golden.py
+        sec = g["oracle_seconds"]
+        tot = sec["sa_divsufsort64_1thread"] + sec["lut"] + sec["search_automaton"] + sec["post"]
+        line["offline_full_config"] = {"seconds": round(tot, 2), "bp_per_s": g["searched_bp"] / tot, "phases_s": sec,
+                                       "families": g["families"], "families_sha256": g["families_sha256"],
+                                       "source": f"tests/golden/families_c{args.config}.json"}
     print(json.dumps(line), flush=True)
 
 
@@ -255,6 +334,8 @@ def run_ours(args):
         del d_strand
         torch.cuda.empty_cache()
     ctx = ab.Context(local)
+    if args.index_bits:
+        ctx.set_index_bits(args.index_bits)
     if dist is not None:
         from asgart_b200.dist import join_index_group
         join_index_group(ctx, dev)
@@ -312,7 +393,10 @@ def run_ours(args):
     ctx.reset_stats()
     ms_e2e, wall_e2e, fam2 = timed(step_e2e, args.steps)
     stats_e2e = ctx.stats()
-    assert fam2.as_lists() == fam.as_lists()
+    assert fam2.digest() == fam.digest()
+    digest = fam.digest()
+    g = golden(args.config) if not args.scale_n else None
+    digest_ok = (digest == g["families_sha256"]) if g else None     # None: no full-size golden for this run (scaled workload)
 
     if rank == 0:
         peak, peak_src = peaks()
@@ -332,15 +416,14 @@ def run_ours(args):
                 traffic = None
         line = {
             "metric": METRIC, "value": bp * K / (ms * 1e-3), "unit": "bp/s", "n_gpus": world, "steps": K, "warmup": args.warmup,
-            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32",
-            "data": "synthetic",
-            "config": {"workload": CONFIG_NAMES[args.config], "strand_bp": n1 - 1, "searched_bp": bp, "chunks": len(chunks),
-                       "flags": CONFIG_FLAGS[args.config], "probe_size": st.probe_size, "gap_size": st.gap_size,
-                       "parallelism": (f"index built by {world} GPUs together (suffix ranges by key, rank array in peer memory), "
-                                       f"then replicated; probe range x{world}" if world > 1 else "one GPU"),
-                       "l2": "inputs larger than L2 (text+SA+sort buffers > 1 GB per step vs 126 MB L2)",
-                       "timing": "CUDA events on the library stream around the K-step loop; wall clock agrees within ms_per_step_wall"},
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "u%d" % int(stats["sa_index_bits"]), "data": "synthetic",
+            "config": workload_config(args.config, args.scale_n, st, n1 - 1, bp, len(chunks)),
+            "parallelism": (f"index built by {world} GPUs together (suffix ranges by key, rank array in peer memory), "
+                            f"then replicated; probe range x{world}" if world > 1 else "one GPU"),
+            "timing": "CUDA events on the library stream around the K-step loop; wall clock agrees within ms_per_step_wall",
             "ms_per_step_wall": wall / K,
+            "families_sha256": digest, "families_match_oracle_golden": digest_ok,
             "clocks": clocks,
             "e2e": {"value": bp * K / (ms_e2e * 1e-3), "unit": "bp/s", "ms_per_step": ms_e2e / K,
                     "h2d_bytes_per_step": stats_e2e["h2d_bytes"] // K, "d2h_bytes_per_step": stats_e2e["d2h_bytes"] // K},
@@ -367,19 +450,27 @@ def run_ours(args):
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             full = n1 - 1
-            sample_n = min(full, 60_000_000)
-            if sample_n == full:
-                s_strand, s_chunks, s_bp = np.array(prep.strand), chunks, bp
-            else:
-                st2, prep2 = make_workload(args.config, sample_n)
-                s_strand, s_chunks, s_bp = np.array(prep2.strand), prep2.chunks, searched_bp(prep2)
+            sample_n = min(full, REF_SAMPLE_BP)
+            # the CPU side gets its strand, fragment map and chunk list from the oracle's prepare_data, not from our library
+            st2, prep2 = oracle_workload(args.config, args.scale_n if sample_n == full else sample_n)
+            s_strand, s_chunks, s_bp = prep2.strand, prep2.chunks, searched_bp(prep2)
             r = cpu_reference_pass(s_strand, s_chunks, st, cores)
             line["cpu_baseline"] = {
                 "value": s_bp / r["seconds"], "unit": "bp/s", "cores": cores, "kind": r["sa_kind"],
                 "sample": (f"{'whole workload' if sample_n == full else 'scaled workload'}: {len(s_strand) - 1} bp, one pass; SA by the "
                            f"reference's libdivsufsort64 (1 thread, as build.rs builds it) + oracle port of the Rust probe "
                            f"loop/automaton/post-steps on {cores} threads over {len(s_chunks)} chunks (no rustc in this image)"),
-                "phases_s": {k: round(v, 3) for k, v in r.items() if k.endswith("_s")}, "families": r["families"]}
+                "phases_s": {k: round(v, 3) for k, v in r.items() if k.endswith("_s")}, "families": r["families"],
+                "sample_bp": len(s_strand) - 1, "full_bp": full}
+            if sample_n == full:    # same input on both sides: the digests must agree
+                line["cpu_baseline"]["families_sha256"] = r["families_sha256"]
+                line["cpu_baseline"]["families_match_gpu"] = r["families_sha256"] == digest
+            if g:
+                sec = g["oracle_seconds"]
+                tot = sec["sa_divsufsort64_1thread"] + sec["lut"] + sec["search_automaton"] + sec["post"]
+                line["cpu_baseline"]["offline_full_config"] = {
+                    "seconds": round(tot, 2), "bp_per_s": g["searched_bp"] / tot, "cores": sec["threads"],
+                    "source": f"tests/golden/families_c{args.config}.json (the whole config, run offline on the CPU container)"}
         try:    # the output side next to the path (FASTA parse and JSON write are reported separately)
             t0 = time.perf_counter()
             js = prep.to_json(st, fam)
@@ -406,6 +497,8 @@ def main():
     ap.add_argument("--scale-n", type=int, default=0, help="override the config's genome length (bp)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--index-bits", type=int, default=0, choices=[0, 32, 64], help="force the suffix-index width (0 = auto)")
+    ap.add_argument("--ref-sample-bp", type=int, default=0, help="--impl reference: genome length per step (0 = bounded default)")
     ap.add_argument("--no-ingest", action="store_true", help="skip the FASTA-ingest measurement (N=1 only)")
     args = ap.parse_args()
     if args.impl == "reference":

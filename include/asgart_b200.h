@@ -149,6 +149,10 @@ ASGART_B200_API int32_t asgart_b200_ctx_download_sa(asgart_b200_ctx *ctx, int64_
  * (first symbols, then the ranks of the two suffixes one symbol further on). *n_bad = number of violations (0 = valid).
  * Lets a genome-scale index be validated without a CPU-side suffix array. */
 ASGART_B200_API int32_t asgart_b200_ctx_check_sa(asgart_b200_ctx *ctx, int64_t *n_bad);
+/* Order-sensitive 64-bit fingerprint of the suffix array, computed on the device: sum over i of
+ * splitmix64(SA[i] + i * 0x9E3779B97F4A7C15) mod 2^64. Lets a genome-scale index be compared with the output of the
+ * reference's divsufsort64 (src/divsufsort.rs:10) through one number instead of a 25 GB download. */
+ASGART_B200_API int32_t asgart_b200_ctx_sa_fingerprint(asgart_b200_ctx *ctx, uint64_t *fingerprint);
 /* LUT as 5^8 (lo, hi) pairs indexed by the 8-mer read as a base-5 number with digits A=0,C=1,G=2,N=3,T=4 (first
  * letter most significant). Empty buckets have lo == hi (value unspecified). */
 #define ASGART_B200_LUT_SIZE 390625

@@ -305,7 +305,7 @@ def search(text_with_dollar, sa, chunks: Sequence[Tuple[int, int]], settings: Se
     h = lib().oracle_search(_ptr(t), len(t), _ptr(sa), _ptr(ch), len(ch), C.byref(settings), post_mask, threads,
                             _ptr(secs), _ptr(ctr))
     if not h:
-        raise RefPanic("the reference panics on this input (ComputeScore)")
+        raise RefPanic("the reference panics on this input (FilterNs / ComputeScore slice or complement panic)")
     try:
         fam = _copy_result(h)
     finally:
@@ -351,7 +351,7 @@ def search_trim(text_with_dollar, trim: Tuple[int, int], chunks: Sequence[Tuple[
     ch = np.ascontiguousarray(np.array(chunks, dtype=np.uint64).reshape(-1, 2))
     h = lib().oracle_search_trim(_ptr(t), len(t), _ptr(sa), len(sa), _ptr(ch), len(ch), C.byref(settings), post_mask, threads)
     if not h:
-        raise RefPanic("the reference panics on this input (ComputeScore)")
+        raise RefPanic("the reference panics on this input (FilterNs / ComputeScore slice or complement panic)")
     try:
         return _copy_result(h)
     finally:
@@ -367,7 +367,7 @@ def post_steps(fam: Families, text_with_dollar, post_mask: int) -> Families:
     h = lib().oracle_result_from_arrays(_ptr(off), len(off) - 1, _ptr(fields), _ptr(ident), _ptr(flags))
     try:
         if lib().oracle_result_post(h, _ptr(t), len(t), post_mask) != 0:
-            raise RefPanic("the reference panics on this input (ComputeScore: '$' under complement, or arm past the strand)")
+            raise RefPanic("the reference panics on this input (FilterNs / ComputeScore: '$' under complement, or arm past the strand)")
         return _copy_result(h)
     finally:
         lib().oracle_result_free(h)

@@ -476,7 +476,12 @@ std::vector<Family> search_duplications_step(const uint8_t* strand, usize strand
 // Post-steps. structs.rs:454-467 n_content; bin/asgart.rs:81-96 FilterNs; :33-51 ReOrder;
 // :481-562 subsegment/overlap/merge/reduce_overlap; :53-65 Sort
 // ---------------------------------------------------------------------------------------------
-float n_content(const ProtoSD& sd, const uint8_t* strand) {  // structs.rs:454-467, inclusive ranges, f32
+struct RefPanic : std::runtime_error { using std::runtime_error::runtime_error; };
+
+// `n1` = strand.len() ('$' included): an inclusive range that passes it is a slice panic in the reference
+float n_content(const ProtoSD& sd, const uint8_t* strand, usize n1) {  // structs.rs:454-467, inclusive ranges, f32
+    if (sd.left >= n1 || sd.left_length >= n1 - sd.left || sd.right >= n1 || sd.right_length >= n1 - sd.right)
+        throw RefPanic("FilterNs: slice index out of range (structs.rs:455-466)");
     usize cl = 0, cr = 0;
     for (usize p = sd.left; p <= sd.left + sd.left_length; ++p) cl += (strand[p] == 'n' || strand[p] == 'N');
     for (usize p = sd.right; p <= sd.right + sd.right_length; ++p) cr += (strand[p] == 'n' || strand[p] == 'N');
@@ -485,12 +490,12 @@ float n_content(const ProtoSD& sd, const uint8_t* strand) {  // structs.rs:454-4
     return fmaxf(l, r);
 }
 
-void step_filter_ns(std::vector<Family>& fams, const uint8_t* strand) {  // bin/asgart.rs:81-96
+void step_filter_ns(std::vector<Family>& fams, const uint8_t* strand, usize n1) {  // bin/asgart.rs:81-96
     std::vector<Family> out;
     for (Family& f : fams) {
         Family kept;
         for (const ProtoSD& sd : f)
-            if (n_content(sd, strand) <= 0.2f) kept.push_back(sd);
+            if (n_content(sd, strand, n1) <= 0.2f) kept.push_back(sd);
         if (!kept.empty()) out.push_back(std::move(kept));
     }
     fams.swap(out);
@@ -554,7 +559,6 @@ void step_reduce_overlap(std::vector<Family>& fams) {  // :67-79
     for (Family& f : fams) f = reduce_overlap(f);
 }
 // structs.rs:28-34 — complement() of structs.rs: panics on anything outside the TR table (so on '$')
-struct RefPanic : std::runtime_error { using std::runtime_error::runtime_error; };
 uint8_t complement_strict(uint8_t n) {
     switch (n) {
         case 'A': return 'T'; case 'T': return 'A'; case 'G': return 'C'; case 'C': return 'G'; case 'N': return 'N';
@@ -933,7 +937,7 @@ void* oracle_search(const uint8_t* T, int64_t n1, const int64_t* SA, const uint6
     Result* r = new Result();
     r->fams = search_duplications_step(T, usize(n1), SA, ch, st, threads, &tl, &ts, counters ? &ctr : nullptr);
     auto t0 = std::chrono::steady_clock::now();
-    if (post_mask & 1) step_filter_ns(r->fams, T);
+    try { if (post_mask & 1) step_filter_ns(r->fams, T, usize(n1)); } catch (const RefPanic&) { delete r; return nullptr; }
     if (post_mask & 2) step_reorder(r->fams);
     if (post_mask & 4) step_reduce_overlap(r->fams);
     if (post_mask & 16) {   // ComputeScore sits between ReduceOverlap and Sort (bin/asgart.rs:744-747)
@@ -960,7 +964,7 @@ void* oracle_search_trim(const uint8_t* T, int64_t n1, const int64_t* SA, int64_
     for (int64_t i = 0; i < n_chunks; ++i) ch.push_back({usize(chunks[2 * i]), usize(chunks[2 * i + 1])});
     Result* r = new Result();
     r->fams = search_duplications_step(T, usize(n1), SA, ch, st, threads, nullptr, nullptr, nullptr, usize(sa_len));
-    if (post_mask & 1) step_filter_ns(r->fams, T);
+    try { if (post_mask & 1) step_filter_ns(r->fams, T, usize(n1)); } catch (const RefPanic&) { delete r; return nullptr; }
     if (post_mask & 2) step_reorder(r->fams);
     if (post_mask & 4) step_reduce_overlap(r->fams);
     if (post_mask & 16) {
@@ -994,7 +998,7 @@ void* oracle_result_from_arrays(const int64_t* fam_offsets, int64_t n_fam, const
 // returns -1 where the reference panics (ComputeScore on an arm that ends on '$' under -C, or past the strand)
 int oracle_result_post(void* h, const uint8_t* T, int64_t n1, int post_mask) {
     Result* r = static_cast<Result*>(h);
-    if (post_mask & 1) step_filter_ns(r->fams, T);
+    try { if (post_mask & 1) step_filter_ns(r->fams, T, usize(n1)); } catch (const RefPanic&) { return -1; }
     if (post_mask & 2) step_reorder(r->fams);
     if (post_mask & 4) step_reduce_overlap(r->fams);
     if (post_mask & 16) {

@@ -53,6 +53,12 @@ void emul_window(const uint8_t* text, int64_t n1, int mode, uint64_t pos, int k,
     *hi = w.hi; *lo = w.lo;
 }
 
+// lut_literal_kernel (search.cuh), one "thread" per requested pattern: (first, count) of the reference's sa_search
+void emul_literal_bucket(const uint8_t* text, int64_t tsize, const uint8_t* P8, const int64_t* SA, int64_t sa_size, int64_t* first,
+                         int64_t* count) {
+    literal_bucket<int64_t>(text, tsize, P8, SA, sa_size, *first, *count);
+}
+
 int emul_lut(const uint8_t* text, int64_t n1, const int64_t* SA, int64_t* lo, int64_t* hi) {  // lut_build_kernel
     auto P = pack(text, u64(n1), 0);
     for (u32 s = 0; s < kLutSize; ++s) lo[s] = hi[s] = 0;

@@ -23,6 +23,7 @@ def lib():
         L.emul_search.restype = C.c_void_p
         L.emul_search.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(ablib.Settings), C.c_void_p]
         L.emul_lut.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.emul_literal_bucket.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
         L.emul_window.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p]
         for n in ("emul_result_n_families", "emul_result_n_sds"):
             getattr(L, n).restype = C.c_int64

@@ -88,3 +88,38 @@ def test_q6_forced_less_near_strand_end():
         got, ctr = emul_harness.search(strand, sa, [(0, len(text))], sc)
         assert got == _strip(want.families.as_lists())
         assert ctr == want.counters
+
+
+def test_device_literal_bucket_equals_reference_sa_search_on_trimmed_indexes():
+    """literal_bucket (kmer_core.h; what lut_literal_kernel runs per 8-mer) against the reference's own sa_searchb64
+    (oracle/_ref) where present, else the oracle's literal restatement that is pinned to it — on trimmed indexes, where the
+    array is not sorted for the text near the cut and only the exact probe sequence gives the reference's answer (Q9)."""
+    import ctypes as C
+    t = oracle.as_strand(cases.stress_text(17, n=30000, n_dups=12))
+    t = np.concatenate([t, np.frombuffer(b"$", dtype=np.uint8)])
+    L = emul_harness.lib()
+    R = oracle.ref()
+    rng = np.random.default_rng(2)
+    letters = np.frombuffer(b"ATGCN", dtype=np.uint8)
+    checked = nonempty = 0
+    for (a, b) in [(0, len(t) - 1), (1000, 20000), (12345, 12399), (29000, len(t) - 1), (7, 8), (5000, 5009)]:
+        sa = np.ascontiguousarray(oracle.trimmed_suffix_array(t, (a, b)), dtype=np.int64)
+        pats = [bytes(t[i:i + 8]) for i in range(max(a, b - 60), min(b + 9, len(t) - 8))]
+        pats += [bytes(t[i:i + 8]) for i in rng.integers(a, max(a + 1, b - 8), 300)]
+        pats += [bytes(rng.choice(letters, size=8)) for _ in range(1200)]
+        for p in pats:
+            if b"$" in p or len(p) != 8:
+                continue
+            pa = np.frombuffer(p, dtype=np.uint8)
+            first, count = C.c_int64(), C.c_int64()
+            L.emul_literal_bucket(t.ctypes.data, len(t), pa.ctypes.data, sa.ctypes.data, len(sa), C.byref(first), C.byref(count))
+            if R is not None:
+                out = C.c_int64()
+                cnt = R.sa_searchb64(t.ctypes.data, len(t), pa.ctypes.data, 8, sa.ctypes.data, len(sa), C.byref(out), 0, len(sa))
+                want = (out.value, cnt)
+            else:
+                want = oracle.sa_search_literal(t, p, sa)
+            assert (first.value, count.value) == want, (a, b, p)
+            checked += 1
+            nonempty += count.value > 0
+    assert checked > 5000 and nonempty > 500

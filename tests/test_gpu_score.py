@@ -5,6 +5,7 @@ import numpy as np
 import pytest
 
 import asgart_b200 as ab
+from asgart_b200 import _lib
 import oracle
 from tests import cases, kat
 
@@ -92,6 +93,15 @@ def test_score_with_n_and_terminator_symbols():
         with pytest.raises(ab.AsgartB200Error, match="past the strand"):
             ctx.post_steps(ab.families_from_lists([[(3000, 8000, 1000, 1001)]]), ab.POST_COMPUTE_SCORE)
         assert ctx.post_steps(ab.families_from_lists([]), ab.POST_COMPUTE_SCORE).n_families == 0
+        # FilterNs reads the same inclusive ranges (src/structs.rs:455-466): past the strand is the reference's slice panic,
+        # not an out-of-bounds device read — and the context stays usable afterwards
+        for bad in ((3000, 8000, 1000, 1001), (10 ** 15, 8000, 10, 10), (3000, 2 ** 63, 10, 2 ** 63)):
+            with pytest.raises(oracle.RefPanic):
+                oracle.post_steps(_ofam(ab.families_from_lists([[bad]])), strand, oracle.POST_FILTER_NS)
+            with pytest.raises(ab.AsgartB200Error, match="past the strand") as ei:
+                ctx.post_steps(ab.families_from_lists([[bad]]), ab.POST_FILTER_NS)
+            assert ei.value.code == _lib.EPANIC
+        assert ctx.post_steps(fam, ab.POST_FILTER_NS).as_lists() == oracle.post_steps(_ofam(fam), strand, oracle.POST_FILTER_NS).as_lists()
 
 
 @pytest.mark.parametrize("seed", [11, 13])

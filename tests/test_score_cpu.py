@@ -102,3 +102,14 @@ def test_inputs_the_reference_panics_on():
     # and a range past the strand is a slice panic
     with pytest.raises(oracle.RefPanic):
         oracle.post_steps(_fam([(0, n - 8, 8, 9)]), strand, oracle.POST_COMPUTE_SCORE)
+
+
+def test_filter_ns_panics_past_the_strand_like_the_reference():
+    """strand[p ..= p + len] in n_content (src/structs.rs:455-466) is a slice panic when the inclusive range passes '$'."""
+    strand = np.frombuffer(b"ACGTACGTACGTACGTACGT$", dtype=np.uint8)
+    n = len(strand) - 1
+    assert oracle.post_steps(_fam([(0, n - 8, 8, 8)]), strand, oracle.POST_FILTER_NS).as_lists() == [[(0, n - 8, 8, 8, False, False)]]
+    with pytest.raises(oracle.RefPanic):
+        oracle.post_steps(_fam([(0, n - 8, 8, 9)]), strand, oracle.POST_FILTER_NS)
+    with pytest.raises(oracle.RefPanic):
+        oracle.post_steps(_fam([(10 ** 12, 0, 8, 8)]), strand, oracle.POST_FILTER_NS)
