@@ -64,6 +64,8 @@ class Stats(C.Structure):
         + [("ms_sa_scatter_main", C.c_double), ("launches_sa_scatter_main", C.c_uint64), ("bytes_sa_scatter_main", C.c_uint64)]
         + [("ms_score", C.c_double), ("score_cells", C.c_uint64), ("score_pairs", C.c_uint64)]
         + [("ms_ingest", C.c_double), ("ingest_bytes", C.c_uint64), ("ingest_records", C.c_uint64)]
+        + [(n, C.c_double) for n in ("ms_msd_scatter0", "ms_msd_hist", "ms_msd_local")]
+        + [(n, C.c_uint64) for n in ("bytes_msd_scatter0", "bytes_msd_hist", "bytes_msd_local", "launches_msd_local", "msd_levels")]
     )
 
     def as_dict(self):

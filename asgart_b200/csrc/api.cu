@@ -71,7 +71,7 @@ struct asgart_b200_ctx {
     Index32 ix32;
     Index64 ix64;
     asgart_b200_stats st{};
-    FamilyTimer t_sort, t_gather, t_rank, t_probe, t_emit, t_scatter, t_scatter_main;
+    FamilyTimer t_sort, t_gather, t_rank, t_probe, t_emit, t_scatter, t_scatter_main, t_msd0, t_msd_hist, t_msd_local;
     cudaEvent_t ev_a = nullptr, ev_b = nullptr;
     LaunchCounter launches;
     // sharded index build: the group this context is a member of (null: builds alone) and this member's slice of the
@@ -259,6 +259,7 @@ void build_index_t(asgart_b200_ctx* ctx) {
     LutHook<IdxT> hook(ctx);
     SaStats ss;
     ss.sort = &ctx->t_sort; ss.gather = &ctx->t_gather; ss.rank = &ctx->t_rank; ss.scatter = &ctx->t_scatter; ss.scatter_main = &ctx->t_scatter_main;
+    ss.msd.scatter = &ctx->t_scatter_main; ss.msd.scatter0 = &ctx->t_msd0; ss.msd.hist = &ctx->t_msd_hist; ss.msd.local = &ctx->t_msd_local;
     SaGroup* grp = (ctx->group && ctx->group->world > 1) ? ctx->group : nullptr;
     if (!grp) {
         DevBuf<IdxT> rank(ctx->n1, ctx->stream);
@@ -283,6 +284,7 @@ void build_index_t(asgart_b200_ctx* ctx) {
         build_suffix_array<IdxT>(ctx->d_text.p, ctx->n1, ix.sa.p, rv, ctx->stream, &ss, &hook, grp);
     }
     ctx->st.sa_rounds = ss.rounds;
+    ctx->st.msd_levels = ss.used_msd ? u64(ss.msd.levels) : 0;
     tsa.stop();
     tlut.start();
     if (!hook.done) build_lut<IdxT>(ctx);
@@ -304,6 +306,7 @@ void build_index_trim_t(asgart_b200_ctx* ctx, u64 a, u64 b) {
     ix.sa.alloc(m1, s);
     SaStats ss;
     ss.sort = &ctx->t_sort; ss.gather = &ctx->t_gather; ss.rank = &ctx->t_rank; ss.scatter = &ctx->t_scatter; ss.scatter_main = &ctx->t_scatter_main;
+    ss.msd.scatter = &ctx->t_scatter_main; ss.msd.scatter0 = &ctx->t_msd0; ss.msd.hist = &ctx->t_msd_hist; ss.msd.local = &ctx->t_msd_local;
     {
         DevBuf<IdxT> rank(m1, s);
         build_suffix_array<IdxT>(sub.p, m1, ix.sa.p, rank.p, s, &ss, nullptr);
@@ -791,7 +794,11 @@ void shard_range(u64 total, int shard, int n_shards, u64& b, u64& e) {
 
 void fold_family_timers(asgart_b200_ctx* ctx) {
     ctx->t_sort.drain(); ctx->t_gather.drain(); ctx->t_rank.drain(); ctx->t_probe.drain(); ctx->t_emit.drain(); ctx->t_scatter.drain(); ctx->t_scatter_main.drain();
+    ctx->t_msd0.drain(); ctx->t_msd_hist.drain(); ctx->t_msd_local.drain();
     asgart_b200_stats& S = ctx->st;
+    S.ms_msd_scatter0 = ctx->t_msd0.total_ms; S.bytes_msd_scatter0 = ctx->t_msd0.bytes;
+    S.ms_msd_hist = ctx->t_msd_hist.total_ms; S.bytes_msd_hist = ctx->t_msd_hist.bytes;
+    S.ms_msd_local = ctx->t_msd_local.total_ms; S.bytes_msd_local = ctx->t_msd_local.bytes; S.launches_msd_local = ctx->t_msd_local.launches;
     S.ms_sa_sort = ctx->t_sort.total_ms; S.launches_sa_sort = ctx->t_sort.launches; S.bytes_sa_sort = ctx->t_sort.bytes;
     S.ms_sa_gather = ctx->t_gather.total_ms; S.launches_sa_gather = ctx->t_gather.launches; S.bytes_sa_gather = ctx->t_gather.bytes;
     S.ms_sa_rank = ctx->t_rank.total_ms;
@@ -837,6 +844,7 @@ int32_t asgart_b200_ctx_create(int32_t device, asgart_b200_ctx** out) {
         CUDA_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
         ctx->t_sort.init(ctx->stream); ctx->t_gather.init(ctx->stream); ctx->t_rank.init(ctx->stream);
         ctx->t_probe.init(ctx->stream); ctx->t_emit.init(ctx->stream); ctx->t_scatter.init(ctx->stream); ctx->t_scatter_main.init(ctx->stream);
+        ctx->t_msd0.init(ctx->stream); ctx->t_msd_hist.init(ctx->stream); ctx->t_msd_local.init(ctx->stream);
         CUDA_CHECK(cudaEventCreate(&ctx->ev_a)); CUDA_CHECK(cudaEventCreate(&ctx->ev_b));
     } catch (const CudaError& e) {
         int code = e.code;
@@ -856,6 +864,7 @@ void asgart_b200_ctx_destroy(asgart_b200_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     ctx->t_sort.destroy(); ctx->t_gather.destroy(); ctx->t_rank.destroy(); ctx->t_probe.destroy(); ctx->t_emit.destroy(); ctx->t_scatter.destroy(); ctx->t_scatter_main.destroy();
+    ctx->t_msd0.destroy(); ctx->t_msd_hist.destroy(); ctx->t_msd_local.destroy();
     if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
     if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
     if (ctx->group_owned && ctx->group) { delete ctx->group; }
@@ -1576,6 +1585,7 @@ void asgart_b200_ctx_reset_stats(asgart_b200_ctx* ctx) {
     try {
         cudaSetDevice(ctx->device);
         ctx->t_sort.reset(); ctx->t_gather.reset(); ctx->t_rank.reset(); ctx->t_probe.reset(); ctx->t_emit.reset(); ctx->t_scatter.reset(); ctx->t_scatter_main.reset();
+        ctx->t_msd0.reset(); ctx->t_msd_hist.reset(); ctx->t_msd_local.reset();
     } catch (...) {}
     ctx->launches.total = 0;
     ctx->st = asgart_b200_stats{};

@@ -102,7 +102,9 @@ __global__ void automaton_kernel(AutoBuffers B, AutoParams P, u64 n_segments, u3
 // the next flush), and the first match of every event is prefetched together with the batch of 32 event records.
 // Segments whose matches add up to kHeavySegment or more get a whole block of kHeavyWarps warps: warp 0 runs the event loop
 // exactly as in the one-warp case and wakes the helper warps (named barriers 1/2) only for events whose
-// matches x active-arms product is large; phase 1 of such an event is then spread over all warps.
+// matches x active-arms product is large; phase 1 of such an event is then spread over all warps. The named barriers are
+// the non-aligned form (barrier.sync, not bar.sync): warp 0 reaches them from inside its data-dependent event loop, where
+// the compiler need not have reconverged the lanes (compute-sanitizer synccheck flags the aligned form there).
 constexpr int kActCapLight = 128;
 constexpr int kActCapHeavy = 768;
 constexpr int kHeavyWarps = 8;
@@ -166,11 +168,11 @@ __global__ void __launch_bounds__(W * 32) automaton_segment_kernel(AutoBuffers B
 
     if (W > 1 && warp > 0) {  // helper warps
         for (;;) {
-            asm volatile("bar.sync 1, %0;" ::"r"(W * 32));
+            asm volatile("barrier.sync 1, %0;" ::"r"(W * 32) : "memory");
             const AutoCmd cmd = s_cmd;
             if (cmd.op == 0) return;
             classify(cmd.t, cmd.m0, cmd.cnt, cmd.snap, cmd.in_smem != 0, warp, W);
-            asm volatile("bar.sync 2, %0;" ::"r"(W * 32));
+            asm volatile("barrier.sync 2, %0;" ::"r"(W * 32) : "memory");
         }
     }
 
@@ -324,6 +326,7 @@ __global__ void __launch_bounds__(W * 32) automaton_segment_kernel(AutoBuffers B
                     const unsigned m = __ballot_sync(FULL, hit);
                     if (m) { target = i64(base) + (__ffs(m) - 1); break; }
                 }
+                __syncwarp();   // every lane has read its entries before lane 0 rewrites the winner (racecheck: WAR)
                 if (target >= 0) {
                     if (lane == 0) extend(u64(target), i, ms, t);
                     if (t + P.q_ext > max_death) max_death = t + P.q_ext;
@@ -360,9 +363,9 @@ __global__ void __launch_bounds__(W * 32) automaton_segment_kernel(AutoBuffers B
             } else if (W > 1 && u64(cnt) * snap >= kHeavyEvent) {
                 if (lane == 0) { s_cmd.t = t; s_cmd.m0 = m0; s_cmd.snap = snap; s_cmd.cnt = cnt; s_cmd.op = 1; s_cmd.in_smem = in_smem ? 1 : 0; }
                 __syncwarp();
-                asm volatile("bar.sync 1, %0;" ::"r"(W * 32));
+                asm volatile("barrier.sync 1, %0;" ::"r"(W * 32) : "memory");
                 classify(t, m0, cnt, snap, in_smem, 0, W);
-                asm volatile("bar.sync 2, %0;" ::"r"(W * 32));
+                asm volatile("barrier.sync 2, %0;" ::"r"(W * 32) : "memory");
             } else {
                 classify(t, m0, cnt, snap, in_smem, 0, 1);
             }
@@ -414,7 +417,7 @@ __global__ void __launch_bounds__(W * 32) automaton_segment_kernel(AutoBuffers B
     if (W > 1) {  // release the helpers
         if (lane == 0) s_cmd.op = 0;
         __syncwarp();
-        asm volatile("bar.sync 1, %0;" ::"r"(W * 32));
+        asm volatile("barrier.sync 1, %0;" ::"r"(W * 32) : "memory");
     }
 }
 

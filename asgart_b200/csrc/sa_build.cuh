@@ -27,6 +27,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "msd_sort.cuh"
 #include "radix_sort.cuh"
 #include "sa_group.h"
 #include "scan.cuh"
@@ -40,6 +41,8 @@ struct SaStats {
     FamilyTimer* scatter_main = nullptr; // rs_scatter_kernel of the initial sort: every launch moves all n suffixes
     FamilyTimer* gather = nullptr;  // rank[I + h] gathers
     FamilyTimer* rank = nullptr;    // re-rank / compaction scans
+    MsdStats msd;                   // initial sort, MSD form (msd_sort.cuh)
+    bool used_msd = false;
     u64 rounds = 0;
 };
 
@@ -524,18 +527,34 @@ void build_suffix_array(const u8* d_text, u64 n, IdxT* d_sa, const RankView<IdxT
     piece_off[world] = n;
     int pshift = 0;
     u32 pre_lo = 0, pre_hi = 0;
+    // the initial sort runs MSD-first (msd_sort.cuh) for small alphabets and large texts, else as the stable LSD sort
+    bool use_msd = msd_sort_applicable(b, p0, n);
+    DevBuf<IdxT> msd_table0;   // sharded build: histogram of the level-0 digit of the WHOLE text (the range cuts come from it)
     if (grp) {
         const int psym = std::max(1, std::min(p0, std::min(4, 12 / b)));
         const u32 nb = 1u << (b * psym);
         pshift = b * p0 - b * psym;
-        DevBuf<unsigned long long> d_ph(nb, stream);
-        d_ph.zero();
-        const int blocks = int(std::min<u64>(ceil_div(n, 256), u64(kNumSMs) * 8));
-        key_prefix_hist_kernel<<<blocks, 256, nb * sizeof(u32), stream>>>(d_text, n, d_code.p, b, psym, d_ph.p);
-        KERNEL_CHECK();
-        count_launch();
+        if (b * psym != kMsdDigitBits) use_msd = false;   // the members' ranges must be ranges of level-0 bins
         std::vector<unsigned long long> h_ph(nb);
-        sync_read(h_ph.data(), d_ph.p, nb * sizeof(unsigned long long));
+        if (use_msd) {
+            msd_table0.alloc(kMsdBins, stream);
+            msd_table0.zero();
+            const int blocks = int(std::min<u64>(ceil_div(n, u64(kH0Tile)), u64(kNumSMs) * 2));
+            msd_hist_text_kernel<IdxT><<<blocks, kMsdThreads, 0, stream>>>(d_text, n, d_code.p, b, psym, msd_table0.p);
+            KERNEL_CHECK();
+            count_launch();
+            std::vector<IdxT> h_t(nb);
+            sync_read(h_t.data(), msd_table0.p, nb * sizeof(IdxT));
+            for (u32 i = 0; i < nb; ++i) h_ph[i] = (unsigned long long)h_t[i];
+        } else {
+            DevBuf<unsigned long long> d_ph(nb, stream);
+            d_ph.zero();
+            const int blocks = int(std::min<u64>(ceil_div(n, 256), u64(kNumSMs) * 8));
+            key_prefix_hist_kernel<<<blocks, 256, nb * sizeof(u32), stream>>>(d_text, n, d_code.p, b, psym, d_ph.p);
+            KERNEL_CHECK();
+            count_launch();
+            sync_read(h_ph.data(), d_ph.p, nb * sizeof(unsigned long long));
+        }
         // member r starts at the first bin whose preceding bins hold >= r * n / world suffixes (same cut on every member)
         std::vector<u32> cut(world + 1, nb);
         cut[0] = 0;
@@ -563,6 +582,18 @@ void build_suffix_array(const u8* d_text, u64 n, IdxT* d_sa, const RankView<IdxT
         DevBuf<IdxT> valsT(n_loc, stream), valsU(grp ? n_loc : 0, stream);
         u64 *k = keysA.p, *ka = keysB.p;
         IdxT *v, *va;
+        bool sorted = false;
+        if (use_msd) {
+            // MSD-first: keys are built inside the first partition pass; the result lands in (keysA, d_sa / valsT)
+            v = grp ? valsT.p : d_sa; va = grp ? valsU.p : valsT.p;
+            if (st && st->sort) st->sort->begin();
+            sorted = msd_sort_suffixes<IdxT>(d_text, n, d_code.p, b, p0, grp ? pre_lo : 0u, grp ? pre_hi : u32(kMsdBins), n_loc, k, v, ka, va,
+                                             grp ? msd_table0.p : nullptr, stream, st ? &st->msd : nullptr);
+            if (st && st->sort) st->sort->end(0, 0);
+            if (st) st->used_msd = sorted;
+            phase(sorted ? "initial sort (msd)" : "initial sort (msd declined)", n_loc);
+        }
+        if (!sorted) {
         if (!grp) {
             v = (shifts.size() % 2 == 0) ? d_sa : valsT.p; va = (shifts.size() % 2 == 0) ? valsT.p : d_sa;
             init_keys_kernel<IdxT><<<unsigned(ceil_div(n, u64(kInitTile))), kInitThreads, 0, stream>>>(d_text, n, d_code.p, b, p0, k, v);
@@ -589,6 +620,7 @@ void build_suffix_array(const u8* d_text, u64 n, IdxT* d_sa, const RankView<IdxT
         radix_sort_pairs<u64, IdxT>(k, ka, v, va, n_loc, shifts.data(), int(shifts.size()), stream, st ? st->sort : nullptr,
                                     st ? st->scatter_main : nullptr);
         phase("initial sort", shifts.size());
+        }
         nv.next("sa_build/lookup tables");
         if (grp && n_loc) CUDA_CHECK(cudaMemcpyAsync(sa_loc, v, n_loc * sizeof(IdxT), cudaMemcpyDeviceToDevice, stream));
 
@@ -622,6 +654,34 @@ void build_suffix_array(const u8* d_text, u64 n, IdxT* d_sa, const RankView<IdxT
                                                                                 GA.p, IA.p, HSA.p, GS.p, IS.p);
             KERNEL_CHECK();
             count_launch();
+        }
+        if (sorted && US > 1) {
+            // The MSD sort leaves equal keys in arbitrary order, but the run round reads the suffixes of every pure key in
+            // text order (a stretch of consecutive positions = one run): order the short list by (symbol, position).
+            DevBuf<u64> PK(US, stream), PK2(US, stream);
+            DevBuf<IdxT> GT(US, stream);
+            {
+                const IdxT* isp = IS.p;
+                const uint16_t* cd = d_code.p;
+                u64* pk = PK.p;
+                for_each_index(US, [=] __device__(u64 c) { const u64 i = u64(isp[c]); pk[c] = (u64(cd[d_text[i]]) << 58) | i; }, stream);
+            }
+            std::vector<int> sh;
+            for (int s = 0; s < bit_width_u64(n); s += 8) sh.push_back(s);
+            for (int s = 0; s < b; s += 8) sh.push_back(58 + s);
+            u64 *k1 = PK.p, *k2 = PK2.p;
+            IdxT *g1 = GS.p, *g2 = GT.p;
+            radix_sort_pairs<u64, IdxT>(k1, k2, g1, g2, US, sh.data(), int(sh.size()), stream, st ? st->sort : nullptr, st ? st->scatter : nullptr);
+            {
+                IdxT *gsp = GS.p, *isp = IS.p;
+                const u64* kk1 = k1;
+                const IdxT* gg1 = g1;
+                for_each_index(US, [=] __device__(u64 c) {
+                    const IdxT g = gg1[c];
+                    isp[c] = IdxT(kk1[c] & ((u64(1) << 58) - 1));
+                    gsp[c] = g;
+                }, stream);
+            }
         }
         // the sorted keys are dead from here on: both key buffers serve as scratch of the sort-back scatter
         if (!grp) inverse_scatter<IdxT>(d_sa, rpos, n, d_rank.base[0], n, stream, k, ka);

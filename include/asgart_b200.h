@@ -232,6 +232,11 @@ typedef struct asgart_b200_stats {
     /* FASTA ingest: device ms of the scan passes (the file's H2D copy is in ms_h2d / h2d_bytes), file bytes, records */
     double ms_ingest;
     uint64_t ingest_bytes, ingest_records;
+    /* initial sort of the suffix-array build in its MSD form (msd_sort.cuh): partition passes over (key, index) pairs
+     * (ms_sa_scatter_main / launches / bytes above then describe msd_scatter_kernel, levels >= 1), the first pass that
+     * builds the keys from the text, the per-level histograms, the in-shared-memory finishing sort, levels used */
+    double ms_msd_scatter0, ms_msd_hist, ms_msd_local;
+    uint64_t bytes_msd_scatter0, bytes_msd_hist, bytes_msd_local, launches_msd_local, msd_levels;
 } asgart_b200_stats;
 ASGART_B200_API int32_t asgart_b200_ctx_stats(const asgart_b200_ctx *ctx, asgart_b200_stats *out);
 ASGART_B200_API void asgart_b200_ctx_reset_stats(asgart_b200_ctx *ctx);

@@ -522,3 +522,66 @@ def test_sa_sort_back_inverse_scatter(tmp_path):
     env = dict(os.environ, ASGART_B200_PERM_SCATTER_MIN="0")
     r = subprocess.run([sys.executable, "-c", _SORT_BACK_SCRIPT.format(root=root)], env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "sort-back ok" in r.stdout, r.stdout + r.stderr
+
+
+_MSD_SCRIPT = r"""
+import sys
+import numpy as np
+sys.path.insert(0, {root!r})
+import asgart_b200 as ab
+import oracle
+from tests import cases
+rng = np.random.default_rng(9)
+acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+texts = [rng.choice(acgt, size=n) for n in (300, 4095, 4096, 4097, 6143, 6144, 6145, 70001, 1 << 20)]
+texts.append(np.frombuffer(cases.stress_text(31, n=900_000, n_dups=50), dtype=np.uint8))
+g, fr = ab.synth_genome(2, scale_n=3_000_000)
+soft = np.array(ab.Prepared.from_memory(ab.normalise(g, True), fr, "x.fa").strand)
+texts.append(soft)
+texts.append(np.full(50_000, ord("A"), dtype=np.uint8))                       # one symbol: every level keeps one giant bucket
+texts.append(np.tile(np.frombuffer(b"ACGTTGCA", dtype=np.uint8), 40_000))     # period 8: a handful of huge equal-key buckets
+low = rng.choice(acgt, size=400_000); low[50_000:250_000] = np.tile(np.frombuffer(b"AC", dtype=np.uint8), 100_000)
+low[300_000:390_000] = ord("N")
+texts.append(low)
+n_checked = 0
+for t in texts:
+    t = np.concatenate([t, np.frombuffer(b"$", dtype=np.uint8)])
+    want = oracle.best_suffix_array(t)
+    for bits in (32, 64):
+        got = ab.r_divsufsort(t, device=0, index_bits=bits)
+        assert np.array_equal(got, want), (len(t), bits)
+        n_checked += 1
+# the sharded build takes the same path with every member's own range of level-0 bins
+ctxs = [ab.Context(0) for _ in range(3)]
+for c in ctxs:
+    c.load_strand(soft)
+ab.build_index_group(ctxs)
+want = oracle.best_suffix_array(soft)
+for c in ctxs:
+    assert c.stats()["msd_levels"] >= 2
+    assert np.array_equal(c.download_sa(), want)
+    c.close()
+# and a whole search on top of it
+prep = ab.Prepared.from_memory(ab.normalise(g, True), fr, "x.fa")
+with ab.Context(0) as ctx:
+    ctx.load_strand(soft)
+    ctx.build_index()
+    assert ctx.stats()["msd_levels"] >= 2
+    st = ab.RunSettings(reverse=True, complement=True, skip_masked=True)
+    got = ctx.search(prep.chunks, st, ab.POST_ALL)
+    so = oracle.make_settings(reverse=True, complement=True, skip_masked=True)
+    assert got.as_lists() == oracle.search(soft, want, prep.chunks, so, oracle.POST_ALL, threads=4).families.as_lists()
+print("msd ok", n_checked)
+"""
+
+
+def test_sa_msd_initial_sort(tmp_path):
+    """The MSD form of the initial sort (msd_sort.cuh) only engages above 2 M suffixes; ASGART_B200_MSD_MIN=0 forces it for
+    small texts: tile- and window-edge sizes, soft-masked N-runs, one-symbol and periodic texts (giant equal-key buckets on
+    every level, the slow path of the local sort), u32 and u64 indices, a 3-member sharded build and a full search."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, ASGART_B200_MSD_MIN="0")
+    r = subprocess.run([sys.executable, "-c", _MSD_SCRIPT.format(root=root)], env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "msd ok" in r.stdout, r.stdout + r.stderr
