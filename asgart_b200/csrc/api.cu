@@ -80,6 +80,7 @@ struct asgart_b200_ctx {
     bool group_owned = false;
     void* rank_slice = nullptr;
     size_t rank_slice_bytes = 0;
+    MemberScratch scratch;    // exchange buffers of the sharded build that the peers map
     std::vector<void*> retired_slices;
     // GPU-side FASTA ingest: one piece per file between ingest_begin and ingest_finish; pinned staging for ingest_file
     bool ingesting = false;
@@ -221,10 +222,32 @@ struct LutHook : SaKeyHook {
         ix.deep.alloc(M, stream);
         ix.deep.zero();
         ix.deep_depth = depth;
+        // 3-bit codes (DNA): the deep slot is decoded four symbols per lookup through a 4096-entry table
+        DevBuf<uint16_t> tab4;
+        u32 pad4 = 0;
+        if (b == 3 && depth > 0) {
+            std::vector<uint16_t> h_tab(4096);
+            for (u32 g = 0; g < 4096; ++g) {
+                u32 e = 0;
+                for (int q = 0; q < 4; ++q) {
+                    const u8 d = map.d4[(g >> (3 * (3 - q))) & 7u];
+                    if (d == 255) e |= 0x8000u; else e |= u32(d) << (2 * (3 - q));
+                }
+                h_tab[g] = uint16_t(e);
+            }
+            u32 ok_code = 8;
+            for (u32 c = 0; c < 8; ++c) if (map.d4[c] != 255) { ok_code = c; break; }
+            if (ok_code < 8) {
+                pad4 = ok_code | (ok_code << 3) | (ok_code << 6);
+                tab4.alloc(4096, stream);
+                CUDA_CHECK(cudaMemcpyAsync(tab4.p, h_tab.data(), 4096 * sizeof(uint16_t), cudaMemcpyHostToDevice, stream));
+                CUDA_CHECK(cudaStreamSynchronize(stream));   // h_tab goes out of scope
+            }
+        }
         if (n_local) {
             lut_from_keys_kernel<IdxT><<<unsigned(ceil_div(n_local, 256 * 4)), 256, 0, stream>>>(d_keys, n_local, base, b, p0, map.nibbles(map.d5),
-                                                                                                map.nibbles(map.d4), depth, ix.lut_lo.p,
-                                                                                                ix.lut_hi.p, ix.deep.p);
+                                                                                                map.nibbles(map.d4), depth, tab4.p, pad4,
+                                                                                                ix.lut_lo.p, ix.lut_hi.p, ix.deep.p);
             KERNEL_CHECK();
             count_launch();
         }
@@ -232,7 +255,37 @@ struct LutHook : SaKeyHook {
             // every slot was seen by exactly one member (zero elsewhere; slot values are >= 1): the maximum merges the tables
             grp->allreduce_max_dev(ix.lut_lo.p, kLutSize, int(sizeof(IdxT)), stream);
             grp->allreduce_max_dev(ix.lut_hi.p, kLutSize, int(sizeof(IdxT)), stream);
-            if (depth) grp->allreduce_max_dev(ix.deep.p, M, int(sizeof(IdxT)), stream);
+            if (depth && b == 3 && p0 >= 4) {
+                // The members' key ranges are cut where the first four symbols change, so each member's keys fill one
+                // contiguous range of deep slots: exchange those pieces (4 GiB / world each at 3.1 Gbp) instead of
+                // all-reducing the whole table. Member r's piece starts at the slot of its first key's 4-symbol prefix
+                // (slots before it that no key hits belong to nobody and stay 0 everywhere).
+                u64 first_key = 0;
+                if (n_local) {
+                    CUDA_CHECK(cudaMemcpyAsync(&first_key, d_keys, sizeof(u64), cudaMemcpyDeviceToHost, stream));
+                    CUDA_CHECK(cudaStreamSynchronize(stream));
+                }
+                std::vector<u64> lo(size_t(grp->world), 0);
+                if (n_local) {
+                    const u32 bin = u32(first_key >> (3 * (p0 - 4))) & 4095u;
+                    u64 f = 0;   // base-4 value of the smallest all-ACGT 4-mer >= bin's 4 symbols = number of all-ACGT bins below `bin`
+                    for (u32 g2 = 0; g2 < bin; ++g2) {
+                        bool ok = true;
+                        for (int q = 0; q < 4; ++q) ok = ok && map.d4[(g2 >> (3 * q)) & 7u] != 255;
+                        f += ok ? 1 : 0;
+                    }
+                    lo[size_t(grp->rank)] = (f << (2 * (depth - 4))) + 1;   // + 1: 0 = this member has no keys
+                }
+                CUDA_CHECK(cudaStreamSynchronize(stream));
+                grp->allreduce_sum_host(lo.data(), grp->world);
+                std::vector<u64> offs(size_t(grp->world) + 1, 0);
+                offs[size_t(grp->world)] = M - 1;
+                for (int r = grp->world - 1; r >= 0; --r) offs[size_t(r)] = lo[size_t(r)] ? std::min<u64>(lo[size_t(r)] - 1, offs[size_t(r) + 1]) : offs[size_t(r) + 1];
+                offs[0] = 0;
+                grp->share_pieces(ix.deep.p, offs.data(), int(sizeof(IdxT)), stream);
+            } else if (depth) {
+                grp->allreduce_max_dev(ix.deep.p, M, int(sizeof(IdxT)), stream);
+            }
         }
         if (depth) {
             // unseen slots take the start of the next seen one (empty bucket); the last entry closes the table at n1
@@ -278,6 +331,7 @@ void build_index_t(asgart_b200_ctx* ctx) {
             CUDA_CHECK(cudaMalloc(&ctx->rank_slice, need));
             ctx->rank_slice_bytes = need;
         }
+        grp->scratch = &ctx->scratch;
         void* all[kMaxWorld] = {};
         grp->exchange_ptr(ctx->rank_slice, ctx->rank_slice_bytes, all);
         for (int r = 0; r < kMaxWorld; ++r) rv.base[r] = static_cast<IdxT*>(all[r < grp->world ? r : 0]);
@@ -871,6 +925,7 @@ void asgart_b200_ctx_destroy(asgart_b200_ctx* ctx) {
     ctx->group = nullptr;
     if (ctx->rank_slice) cudaFree(ctx->rank_slice);
     for (void* p : ctx->retired_slices) cudaFree(p);
+    ctx->scratch.release();
     ctx->pieces.clear();
     for (int i = 0; i < 2; ++i) {
         if (ctx->stage[i]) cudaFreeHost(ctx->stage[i]);
@@ -901,11 +956,25 @@ int32_t asgart_b200_ctx_load_strand(asgart_b200_ctx* ctx, const uint8_t* T, int6
         EventTimer th(ctx->stream);
         th.start();
         ctx->d_text.alloc(ctx->n1, ctx->stream);
-        CUDA_CHECK(cudaMemcpyAsync(ctx->d_text.p, T, ctx->n1, cudaMemcpyHostToDevice, ctx->stream));
+        u64 copied = ctx->n1;
+        if (ctx->group && ctx->group_owned && ctx->group->world > 1) {
+            // one process per GPU, every rank was handed the same strand: each rank moves 1/world of it over PCIe and the
+            // ranks exchange the pieces over NVLink (N full host copies made the N-GPU end-to-end time worse than N = 1)
+            const int world = ctx->group->world, rank = ctx->group->rank;
+            std::vector<u64> offs(size_t(world) + 1);
+            for (int r = 0; r <= world; ++r) offs[size_t(r)] = (ctx->n1 * u64(r) / u64(world)) & ~u64(15);
+            offs[size_t(world)] = ctx->n1;
+            const u64 o = offs[size_t(rank)];
+            copied = offs[size_t(rank) + 1] - o;
+            if (copied) CUDA_CHECK(cudaMemcpyAsync(ctx->d_text.p + o, T + o, copied, cudaMemcpyHostToDevice, ctx->stream));
+            ctx->group->share_pieces(ctx->d_text.p, offs.data(), 1, ctx->stream);
+        } else {
+            CUDA_CHECK(cudaMemcpyAsync(ctx->d_text.p, T, ctx->n1, cudaMemcpyHostToDevice, ctx->stream));
+        }
         th.stop();
         const int32_t rc = pack_loaded_strand(ctx);
         ctx->st.ms_h2d += th.ms();
-        ctx->st.h2d_bytes += ctx->n1;
+        ctx->st.h2d_bytes += copied;
         return rc;
     });
 }

@@ -160,7 +160,7 @@ struct NcclGroup : SaGroup {
     u64* d_stage = nullptr;   // 64 words: host-value reductions, IPC handles
     u64* h_stage = nullptr;   // pinned
     std::map<std::string, void*> opened;   // IPC handle bytes -> mapped base
-    static constexpr int kStageWords = 64;
+    static constexpr int kStageWords = 256 * kMaxWorld + 64;   // host-value reductions up to one 256-bin table per member
 
     NcclGroup(int r, int w, const ncclUniqueId& id, cudaStream_t st) : stream(st) {
         rank = r; world = w;

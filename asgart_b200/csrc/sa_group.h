@@ -19,8 +19,31 @@ namespace ab200 {
 
 constexpr int kMaxWorld = 16;
 
+// Device blocks of one member that outlive a build (the peers keep them mapped): grow-only, freed with their owner.
+struct MemberScratch {
+    static constexpr int kSlots = 2;
+    void* p[kSlots] = {};
+    size_t bytes[kSlots] = {};
+    void* retired[64] = {};
+    int n_retired = 0;
+    void* get(int slot, size_t need) {
+        if (need <= bytes[slot]) return p[slot];
+        if (p[slot] && n_retired < 64) retired[n_retired++] = p[slot];   // peers may still have it mapped (CUDA IPC)
+        p[slot] = nullptr; bytes[slot] = 0;
+        if (cudaMalloc(&p[slot], need) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        bytes[slot] = need;
+        return p[slot];
+    }
+    void release() {
+        for (int i = 0; i < kSlots; ++i) { if (p[i]) cudaFree(p[i]); p[i] = nullptr; bytes[i] = 0; }
+        for (int i = 0; i < n_retired; ++i) cudaFree(retired[i]);
+        n_retired = 0;
+    }
+};
+
 struct SaGroup {
     int rank = 0, world = 1;
+    MemberScratch* scratch = nullptr;   // set by the member's context before a build
     // Sum of host values over the members. Every member calls it after synchronising its stream, so when it returns all
     // device work issued before it — on every member, including stores into peer memory — is complete and visible.
     virtual void allreduce_sum_host(uint64_t* vals, int n) = 0;
@@ -34,8 +57,10 @@ struct SaGroup {
     virtual ~SaGroup() = default;
 };
 
-// Rank array of the suffix-array build, block-cyclic over the members: block j of 2^blk_shift positions lives on member
-// j % world. world == 1 is the plain array.
+// Rank array of the suffix-array build, one contiguous slice per member: positions [r << blk_shift, (r + 1) << blk_shift)
+// live on member r, 2^blk_shift >= n / world (the last members may own less, or nothing). A power-of-two slice makes the
+// owner of a position a shift, and lets the inverse scatter route (position, rank) pairs to their owners by the leading
+// bits of the position (sharded_inverse_scatter, scatter.cuh). world == 1 is the plain array.
 template <typename IdxT>
 struct RankView {
     IdxT* base[kMaxWorld];
@@ -43,11 +68,7 @@ struct RankView {
     uint32_t blk_shift;
     __host__ __device__ __forceinline__ IdxT* ptr(uint64_t p) const {
         if (world == 1) return base[0] + p;
-        const uint64_t blk = p >> blk_shift;
-        uint64_t q, o;
-        if (blk <= 0xFFFFFFFFull) { q = uint32_t(blk) / world; o = uint32_t(blk) % world; }
-        else { q = blk / world; o = blk % world; }
-        return base[o] + ((q << blk_shift) | (p & ((uint64_t(1) << blk_shift) - 1)));
+        return base[p >> blk_shift] + (p & ((uint64_t(1) << blk_shift) - 1));
     }
     static RankView single(IdxT* p) {
         RankView v;
@@ -56,17 +77,15 @@ struct RankView {
         v.blk_shift = 20;
         return v;
     }
-    // block size: 1 Mi positions, smaller for short texts so that every member owns several blocks
+    // slice size: the smallest power of two that lets `world` slices cover n positions (at least 16)
     static uint32_t pick_shift(uint64_t n, uint32_t world) {
-        uint32_t s = 20;
-        while (s > 4 && (n >> s) < uint64_t(world) * 4) --s;
+        const uint64_t per = (n + world - 1) / world;
+        uint32_t s = 4;
+        while ((uint64_t(1) << s) < per) ++s;
         return s;
     }
     // positions a member must hold
-    static uint64_t slice_len(uint64_t n, uint32_t world, uint32_t blk_shift) {
-        const uint64_t nblk = (n + (uint64_t(1) << blk_shift) - 1) >> blk_shift;
-        return ((nblk + world - 1) / world) << blk_shift;
-    }
+    static uint64_t slice_len(uint64_t, uint32_t, uint32_t blk_shift) { return uint64_t(1) << blk_shift; }
 };
 
 }  // namespace ab200

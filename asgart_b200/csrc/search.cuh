@@ -135,13 +135,40 @@ __device__ __forceinline__ bool key_slot4(u64 key, int b, int p0, int depth, u64
     return (bad & 12u) == 0;   // digits are 0..3
 }
 
+// Base-4 slot of the first `depth` symbols of a key made of 3-bit symbol codes, four symbols per table lookup:
+// tab4[12 bits] = the four 2-bit digits (first symbol in the top pair) | 0x8000 when one of the four codes is not A/C/G/T.
+// `pad` = 9 bits of a valid code repeated: fills a last group of fewer than four symbols (its digits are dropped again).
+// The digit-by-digit decode (key_slot4) made the table kernel ALU-bound: ~90 instructions per bucket border, a third of
+// all keys at 3.1 Gbp with 15-symbol buckets.
+__device__ __forceinline__ bool key_slot4_tab(u64 key, int p0, int depth, const uint16_t* __restrict__ tab4, u32 pad, u32& slot) {
+    u32 s = 0, bad = 0;
+    int sh = 3 * p0, rem = depth;
+    while (rem >= 4) {
+        sh -= 12;
+        const u32 e = __ldg(&tab4[u32(key >> sh) & 4095u]);
+        s = (s << 8) | (e & 255u);
+        bad |= e;
+        rem -= 4;
+    }
+    if (rem) {
+        sh -= 3 * rem;
+        const int fill = 3 * (4 - rem);
+        const u32 grp = ((u32(key >> sh) & ((1u << (3 * rem)) - 1u)) << fill) | (pad & ((1u << fill) - 1u));
+        const u32 e = __ldg(&tab4[grp]);
+        s = (s << (2 * rem)) | ((e & 255u) >> (2 * (4 - rem)));
+        bad |= e;
+    }
+    slot = s;
+    return (bad & 0x8000u) == 0;
+}
+
 // 8-mer LUT (Searcher::new, src/searcher.rs:99-143) and, when depth > 0, the first suffix of every ACGT-only
 // `depth`-mer (0 = not seen; position 0 is always the '$' suffix) from the sorted initial keys. Needs p0 >= 8, depth.
 // Four keys per thread (two 16-byte loads + the predecessor); keys must be 16-byte aligned.
 template <typename IdxT>
 __global__ void __launch_bounds__(256) lut_from_keys_kernel(const u64* __restrict__ keys, u64 n_local, u64 base, int b, int p0,
-                                                            u64 m5, u64 m4, int depth, IdxT* __restrict__ lut_lo,
-                                                            IdxT* __restrict__ lut_hi, IdxT* __restrict__ deep) {
+                                                            u64 m5, u64 m4, int depth, const uint16_t* __restrict__ tab4, u32 pad4,
+                                                            IdxT* __restrict__ lut_lo, IdxT* __restrict__ lut_hi, IdxT* __restrict__ deep) {
     // keys[0 .. n_local) are positions [base, base + n_local) of the sorted keys (sharded build: one member's key range,
     // cut where the first four symbols change, so the first and the last key of the piece are bucket boundaries)
     const u64 i0 = (u64(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
@@ -174,7 +201,8 @@ __global__ void __launch_bounds__(256) lut_from_keys_kernel(const u64* __restric
         }
         if (depth > 0 && (cur >> sd) != (prev >> sd)) {
             u32 cs = 0;
-            if (key_slot4(cur, b, p0, depth, m4, cs)) deep[cs] = IdxT(base + i);
+            const bool ok4 = tab4 ? key_slot4_tab(cur, p0, depth, tab4, pad4, cs) : key_slot4(cur, b, p0, depth, m4, cs);
+            if (ok4) deep[cs] = IdxT(base + i);
         }
     }
 }

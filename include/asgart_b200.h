@@ -109,7 +109,9 @@ ASGART_B200_API void asgart_b200_ctx_destroy(asgart_b200_ctx *ctx);
 ASGART_B200_API const char *asgart_b200_ctx_last_error(const asgart_b200_ctx *ctx);
 
 /* Strand = what prepare_data produces (src/bin/asgart.rs:273-471): bytes in {A,C,G,N,T} followed by one '$'
- * (n_plus_1 bytes, host memory; pinned memory makes the copy asynchronous). Copies to the device and packs it. */
+ * (n_plus_1 bytes, host memory; pinned memory makes the copy asynchronous). Copies to the device and packs it.
+ * In a context that joined a group (asgart_b200_ctx_dist_init) the call is collective: every rank passes the same strand,
+ * copies 1/world of it to its device and the ranks exchange the pieces over NVLink. */
 ASGART_B200_API int32_t asgart_b200_ctx_load_strand(asgart_b200_ctx *ctx, const uint8_t *T, int64_t n_plus_1);
 /* Suffix array (replaces r_divsufsort, :149) + 8-mer LUT (replaces Searcher::new, :151; src/searcher.rs:99-143) */
 ASGART_B200_API int32_t asgart_b200_ctx_build_index(asgart_b200_ctx *ctx);

@@ -44,6 +44,13 @@ def main():
     bad = ctx.check_sa()
     print(f"[rank {rank}] sufcheck violations: {bad}", flush=True)
     ok = bad == 0
+    # the collective load (every rank copies 1/world of the strand, the pieces travel over NVLink) gives the same strand
+    ctx.load_strand(strand)
+    ok = ok and np.array_equal(ctx.download_strand(), strand)
+    ctx.build_index()
+    fam_again = sharded_search(ctx, prep.chunks, st, ab.POST_ALL, dev)
+    ok = ok and fam_again.digest() == fam.digest()
+    print(f"[rank {rank}] families digest {fam.digest()}", flush=True)
     if rank == 0:
         lut = ctx.download_lut()
         with ab.Context(local) as one:
