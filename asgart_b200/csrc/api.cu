@@ -321,8 +321,9 @@ void build_index_t(asgart_b200_ctx* ctx) {
         // this member's slice of the rank array: a cudaMalloc block of its own (its address is what the peers map)
         RankView<IdxT> rv;
         rv.world = u32(grp->world);
-        rv.blk_shift = RankView<IdxT>::pick_shift(ctx->n1, rv.world);
-        const size_t need = RankView<IdxT>::slice_len(ctx->n1, rv.world, rv.blk_shift) * sizeof(IdxT);
+        rv.g = RankView<IdxT>::pick_g(ctx->n1);
+        rv.k = RankView<IdxT>::pick_k(ctx->n1, rv.world, rv.g);
+        const size_t need = rv.slice_len() * sizeof(IdxT);
         if (need > ctx->rank_slice_bytes) {   // same decision on every member: n1 and world are the same everywhere
             // the previous build ended with a collective, so nobody still works on the old slice; peers may still have it
             // mapped (CUDA IPC), so it is only freed with the context

@@ -187,15 +187,21 @@ struct NcclGroup : SaGroup {
         if (count == 0) return;
         NCCL_CHECK(nccl_api().AllReduce(buf, buf, count, elem_bytes == 4 ? ncclUint32 : ncclUint64, ncclMax, comm, st));
     }
+    // Every member pulls the other members' pieces straight out of their copies of the array (CUDA IPC mappings, copy
+    // engines over NVLink). `base` must be the start of a cudaMalloc block. Measured at two GPUs, 6.2 GB per direction:
+    // 26 ms as grouped ncclBroadcasts of the pieces.
     void share_pieces(void* base, const u64* offs, int elem_bytes, cudaStream_t st) override {
-        NCCL_CHECK(nccl_api().GroupStart());
-        for (int r = 0; r < world; ++r) {
+        void* all[kMaxWorld] = {};
+        exchange_ptr(base, 0, all);     // stream-ordered collective inside: the peers' pieces are complete when it returns
+        for (int i = 1; i < world; ++i) {
+            const int r = (rank + i) % world;    // staggered, so that the members do not all read from the same peer at once
             const size_t cnt = size_t(offs[r + 1] - offs[r]);
             if (cnt == 0) continue;
-            char* p = static_cast<char*>(base) + size_t(offs[r]) * elem_bytes;
-            NCCL_CHECK(nccl_api().Broadcast(p, p, cnt * elem_bytes, ncclUint8, r, comm, st));
+            const size_t o = size_t(offs[r]) * elem_bytes;
+            CUDA_CHECK(cudaMemcpyAsync(static_cast<char*>(base) + o, static_cast<const char*>(all[r]) + o, cnt * elem_bytes, cudaMemcpyDefault, st));
         }
-        NCCL_CHECK(nccl_api().GroupEnd());
+        CUDA_CHECK(cudaStreamSynchronize(st));
+        barrier();   // nobody touches its copy again before everyone has read its piece
     }
     void exchange_ptr(void* mine, size_t, void** all) override {
         static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");

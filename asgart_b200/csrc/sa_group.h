@@ -57,35 +57,42 @@ struct SaGroup {
     virtual ~SaGroup() = default;
 };
 
-// Rank array of the suffix-array build, one contiguous slice per member: positions [r << blk_shift, (r + 1) << blk_shift)
-// live on member r, 2^blk_shift >= n / world (the last members may own less, or nothing). A power-of-two slice makes the
-// owner of a position a shift, and lets the inverse scatter route (position, rank) pairs to their owners by the leading
-// bits of the position (sharded_inverse_scatter, scatter.cuh). world == 1 is the plain array.
+// Rank array of the suffix-array build, one contiguous slice per member. Positions come in regions of 2^g (at most 256
+// regions; g >= 16), member r owns regions [r k, (r + 1) k), k = ceil(regions / world): slices are balanced to one region
+// and the inverse scatter can route (position, rank) pairs to their owners by the leading digit of the position
+// (sharded_inverse_scatter, scatter.cuh). world == 1 is the plain array.
 template <typename IdxT>
 struct RankView {
     IdxT* base[kMaxWorld];
     uint32_t world;
-    uint32_t blk_shift;
+    uint32_t g;   // region shift
+    uint32_t k;   // regions per member
     __host__ __device__ __forceinline__ IdxT* ptr(uint64_t p) const {
         if (world == 1) return base[0] + p;
-        return base[p >> blk_shift] + (p & ((uint64_t(1) << blk_shift) - 1));
+        const uint32_t o = uint32_t(p >> g) / k;
+        return base[o] + (p - ((uint64_t(o) * k) << g));
     }
     static RankView single(IdxT* p) {
         RankView v;
         for (int i = 0; i < kMaxWorld; ++i) v.base[i] = p;
         v.world = 1;
-        v.blk_shift = 20;
+        v.g = 16;
+        v.k = 1;
         return v;
     }
-    // slice size: the smallest power of two that lets `world` slices cover n positions (at least 16)
-    static uint32_t pick_shift(uint64_t n, uint32_t world) {
-        const uint64_t per = (n + world - 1) / world;
-        uint32_t s = 4;
-        while ((uint64_t(1) << s) < per) ++s;
-        return s;
+    // region shift: the leading 8-bit digit of a position above 16-bit buckets (what the sort-back scatter partitions by)
+    static uint32_t pick_g(uint64_t n) {
+        int bits = 0;
+        for (uint64_t v = n ? n - 1 : 0; v; v >>= 1) ++bits;
+        return bits <= 16 ? 16u : uint32_t(16 + 8 * ((bits - 17) / 8));
+    }
+    static uint32_t pick_k(uint64_t n, uint32_t world, uint32_t g) {
+        const uint64_t regions = (n + (uint64_t(1) << g) - 1) >> g;
+        const uint64_t k = (regions + world - 1) / world;
+        return uint32_t(k ? k : 1);
     }
     // positions a member must hold
-    static uint64_t slice_len(uint64_t, uint32_t, uint32_t blk_shift) { return uint64_t(1) << blk_shift; }
+    uint64_t slice_len() const { return uint64_t(k) << g; }
 };
 
 }  // namespace ab200

@@ -267,8 +267,8 @@ void inverse_scatter(const IdxT* idx, const IdxT* val, u64 n, IdxT* out, u64 out
 // Every member holds (position, value) pairs for the suffixes of ITS piece of the suffix array; the positions are spread
 // over all members' slices. Plain stores through the view are 4-byte writes over NVLink (measured: 133 ms per member at
 // two GPUs for 1.5 G pairs, against 74 ms for the whole single-GPU scatter). Instead the pairs travel in bulk:
-//   1. each member partitions its pairs by the leading digit of the position (regions of 2^g positions, g <= slice shift:
-//      a region belongs to one owner),
+//   1. each member partitions its pairs by the leading digit of the position (regions of 2^g positions; a member's slice of
+//      rank[] is a whole number of regions, RankView),
 //   2. the members exchange their region counts (one small host all-reduce) — a permutation fills every region exactly,
 //      so each (sender, region) run has a fixed place in the owner's receive buffer,
 //   3. one kernel copies the runs into the owners' buffers (coalesced stores into peer memory, whole lines over NVLink),
@@ -284,17 +284,17 @@ __global__ void pt_bin_starts_kernel(const u32* __restrict__ offs, u64 tiles, u3
 }
 
 __global__ void __launch_bounds__(256) push_pairs_kernel(const u32* __restrict__ ti, const u32* __restrict__ vi, u32 n_loc,
-                                                         const u32* __restrict__ bstart, const u64* __restrict__ pre, int g, int s,
+                                                         const u32* __restrict__ bstart, const u64* __restrict__ pre, int g, u32 k,
                                                          u64 slice, PeerU32 ridx, PeerU32 rval) {
     __shared__ u32 bs[257];
     __shared__ u64 dst0[256];   // where bin b's first pair of this member goes, relative to the owner's buffers
     __shared__ u32 own[256];
     for (u32 i = threadIdx.x; i < 257; i += 256) bs[i] = bstart[i];
     {
-        const u64 b = threadIdx.x;
-        const u64 o = (b << g) >> s;
-        own[b] = u32(o < u64(kMaxWorld) ? o : 0);
-        dst0[b] = ((b << g) - (o << s)) + pre[b];
+        const u32 b = threadIdx.x;
+        const u32 o = b / k;
+        own[b] = o < u32(kMaxWorld) ? o : 0u;
+        dst0[b] = (u64(b - o * k) << g) + pre[b];
     }
     __syncthreads();
     const u64 stride = u64(gridDim.x) * blockDim.x;
@@ -317,12 +317,10 @@ bool sharded_inverse_scatter(const IdxT* idx, const IdxT* val, u64 n_loc, u64 n,
         return false;
     } else {
         const int bits = bit_width_u64(n - 1);
-        if (bits <= kBucketBits || n >= (u64(1) << 32)) return false;
-        const int g = kBucketBits + 8 * ((bits - kBucketBits - 1) / 8);   // leading digit = position >> g, at most 256 regions
-        const int s = int(rv.blk_shift);
-        if (s < g || !grp->scratch) return false;
+        if (bits <= kBucketBits || n >= (u64(1) << 32) || !grp->scratch) return false;
+        const int g = int(rv.g);   // leading digit = position >> g, at most 256 regions (RankView::pick_g)
         const int world = grp->world, rank = grp->rank;
-        const u64 slice = u64(1) << s;
+        const u64 slice = rv.slice_len();
         // 1. my pairs by region
         const u64 half = (n_loc + 3) / 4 * 4;
         DevBuf<u32> pa(2 * (half + 4), stream), hist, offs, d_bs(257, stream);
@@ -359,14 +357,14 @@ bool sharded_inverse_scatter(const IdxT* idx, const IdxT* val, u64 n_loc, u64 n,
         }
         if (n_loc) {
             const unsigned grid = unsigned(std::min<u64>(ceil_div(n_loc, 256), u64(kNumSMs) * 16));
-            push_pairs_kernel<<<grid, 256, 0, stream>>>(pa.p, pa.p + half, u32(n_loc), d_bs.p, d_pre.p, g, s, slice, ridx, rval);
+            push_pairs_kernel<<<grid, 256, 0, stream>>>(pa.p, pa.p + half, u32(n_loc), d_bs.p, d_pre.p, g, rv.k, slice, ridx, rval);
             KERNEL_CHECK();
             count_launch();
         }
         // 4. all runs have landed (and h_pre is no longer read by the copy above)
         CUDA_CHECK(cudaStreamSynchronize(stream));
         grp->barrier();
-        const u64 own0 = u64(rank) << s;
+        const u64 own0 = u64(rank) * slice;
         const u64 n_own = own0 < n ? std::min(slice, n - own0) : 0;
         if (n_own) {
             const u64 ohalf = (n_own + 3) / 4 * 4;
