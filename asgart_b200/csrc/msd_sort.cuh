@@ -345,8 +345,8 @@ __global__ void __launch_bounds__(kMsdThreads) msd_copy_tiles_kernel(const u64* 
 //               batch over all bits that can differ (5-bit digits, private per-thread counters) — ~90 instructions per pair
 //               and pass, independent of the key distribution (measured: 94 ms for 3 G pairs over 30 bits, the fast path
 //               with one thread insertion-sorting each sub-bucket: 166 ms, 41 G warp instructions at half-empty warps).
-constexpr int kLocCounters = kLocCap;  // sub-bucket counters of the fast path (u32)
-constexpr int kLocRankMax = 64;        // longest sub-bucket the fast path finishes by ranking
+constexpr int kLocCounters = 2 * kLocCap;  // sub-bucket counters of the fast path: 16 bits each, two per u32 word
+constexpr int kLocRankMax = 64;            // longest sub-bucket the fast path finishes by ranking
 constexpr int kLocFastItems = kLocCap / kLocThreads;
 
 template <typename IdxT>
@@ -355,7 +355,7 @@ struct MsdLocalSmem {
     static constexpr size_t aux = size_t(kLocDigits) * kLocThreads * sizeof(uint16_t) + 2 * kLocDigits * sizeof(u32) + 768;
     static constexpr size_t bytes = size_t(kLocCap) * (sizeof(u64) + sizeof(IdxT)) + aux;
 };
-static_assert(size_t(kLocCounters + 1) * sizeof(u32) + size_t(kMsdBins) * sizeof(uint16_t) <= MsdLocalSmem<u32>::aux, "fast-path tables must fit");
+static_assert(size_t(kLocCounters / 2 + 1) * sizeof(u32) + size_t(kMsdBins) * sizeof(uint16_t) <= MsdLocalSmem<u32>::aux, "fast-path tables must fit");
 static_assert(kLocItems * kLocThreads >= kLocCap && kLocFastItems * kLocThreads == kLocCap, "local sort shapes");
 
 // first index i in [0, 4096) with arr[i] >= v (4096 when there is none); arr non-decreasing. Every warp runs the same
@@ -441,18 +441,41 @@ __device__ __noinline__ void msd_local_lsd(u64* sk, IdxT* sv, u32 count, int hb,
     }
 }
 
+// 16-bit counters packed two per word: bump counter `sub`, return its previous value (the pair's slot in its sub-bucket).
+// A warp whose lanes all hit one counter takes one atomic.
+__device__ __forceinline__ u32 msd_sub_slot(u32* cnt, u32 sub, bool valid) {
+    const u32 sh = (sub & 1u) * 16u;
+    const u32 s0 = __shfl_sync(0xffffffffu, sub, 0);
+    if (__all_sync(0xffffffffu, valid && sub == s0)) {
+        u32 old = 0;
+        if (lane_id() == 0) old = atomicAdd(&cnt[s0 >> 1], 32u << sh);
+        return ((__shfl_sync(0xffffffffu, old, 0) >> sh) & 0xffffu) + lane_id();
+    }
+    return valid ? ((atomicAdd(&cnt[sub >> 1], 1u << sh) >> sh) & 0xffffu) : 0u;
+}
+__device__ __forceinline__ u32 msd_sub_off(const u32* cnt, u32 sub) { return (cnt[sub >> 1] >> ((sub & 1u) * 16u)) & 0xffffu; }
+
 // Sorts pairs [lo, hi) (hi - lo <= kLocCap; whole children of the row, bins [ba, bb) of its table E) of (src_k, src_v) by
-// the key bits below `shift` inside every child, into (dst_k, dst_v) at the same positions.
+// the key bits below `shift` inside every child, into (dst_k, dst_v) at the same positions. The batch is fetched with
+// cp.async while the child ordinals are worked out from the row's table.
 template <typename IdxT, typename OffT>
 __device__ void msd_local_sort_range(const u64* __restrict__ src_k, const IdxT* __restrict__ src_v, u64* __restrict__ dst_k,
-                                     IdxT* __restrict__ dst_v, u64 lo, u64 hi, const OffT* __restrict__ E, u64 first_start, u32 ba, u32 bb,
+                                     IdxT* __restrict__ dst_v, u64 lo, u32 count, const OffT* __restrict__ E, u32 ba, u32 bb,
                                      int shift, u32 dmask, u64* sk, IdxT* sv, unsigned char* aux, bool allow_fast) {
     __shared__ u32 wsm[32];
     __shared__ u32 s_max;
     const u32 tid = threadIdx.x;
-    const u32 count = u32(hi - lo);
-    u32* cnt = reinterpret_cast<u32*>(aux);                                   // [kLocCounters + 1]
-    uint16_t* ord = reinterpret_cast<uint16_t*>(cnt + kLocCounters + 1);       // [bb - ba] dense ordinal of every non-empty child
+    u32* cnt = reinterpret_cast<u32*>(aux);                                       // [kLocCounters / 2 + 1] packed 16-bit counters
+    uint16_t* ord = reinterpret_cast<uint16_t*>(cnt + kLocCounters / 2 + 1);       // [bb - ba] dense ordinal of every non-empty child
+    // ---- the batch starts to travel: 8 bytes per key, 4 or 8 per value, striped over the threads
+    for (u32 i = tid; i < count; i += kLocThreads) {
+        const u32 dk = u32(__cvta_generic_to_shared(sk + i));
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dk), "l"(src_k + lo + i));
+        const u32 dv = u32(__cvta_generic_to_shared(sv + i));
+        if constexpr (sizeof(IdxT) == 4) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dv), "l"(src_v + lo + i));
+        else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dv), "l"(src_v + lo + i));
+    }
+    asm volatile("cp.async.commit_group;");
     // ---- dense child ordinals over the bins of the range
     const u32 span = bb - ba;
     u32 nchild;
@@ -464,7 +487,7 @@ __device__ void msd_local_sort_range(const u64* __restrict__ src_k, const IdxT* 
             const u32 r = tid * PER + q;
             if (r < span) {
                 const u32 bin = ba + r;
-                const u64 s = r == 0 ? first_start : u64(E[bin - 1]);
+                const u64 s = r == 0 ? lo : u64(E[bin - 1]);
                 if (u64(E[bin]) > s) { flags |= 1u << q; ++c; }
             }
         }
@@ -480,81 +503,110 @@ __device__ void msd_local_sort_range(const u64* __restrict__ src_k, const IdxT* 
     while (w < 12 && w < shift && (u64(nchild) << (w + 1)) <= u64(kLocCounters)) ++w;
     const bool fast = allow_fast && nchild >= 1 && nchild <= u32(kLocCounters) && shift > 0;
     const u32 nsub = fast ? (nchild << w) : 0;
-    for (u32 i = tid; i <= nsub; i += kLocThreads) cnt[i] = 0;
+    for (u32 i = tid; i <= nsub / 2; i += kLocThreads) cnt[i] = 0;
     if (tid == 0) s_max = 0;
+    asm volatile("cp.async.wait_group 0;");
     __syncthreads();
     bool ranked = false;
     if (fast) {
-        // Register budget: 64 per thread (two blocks of 512 per SM). Only the 12 slots / ranks live across the barriers;
-        // keys and values are read again where they are needed (global reads hit L2: the batch is 72 KB).
-        u32 slot[kLocFastItems];
+        // Register budget: 64 per thread (two blocks of 512 per SM): slots / ranks are kept as 16-bit halves
+        u32 slot2[kLocFastItems / 2];
         const int wshift = shift - w;
         const u32 wmask = (1u << w) - 1u;
 #pragma unroll
         for (int j = 0; j < kLocFastItems; ++j) {
             const u32 li = j * kLocThreads + tid;
             const bool ok = li < count;
-            const u64 k = ok ? src_k[lo + li] : 0;
+            const u64 k = ok ? sk[li] : 0;
             const u32 d = (u32(k >> shift) & dmask) - ba;
             const u32 sub = ok ? ((u32(ord[d]) << w) | (u32(k >> wshift) & wmask)) : 0u;
-            slot[j] = msd_bin_slot(cnt, sub, ok);
+            const u32 sl = msd_sub_slot(cnt, sub, ok);
+            if (j & 1) slot2[j >> 1] |= sl << 16; else slot2[j >> 1] = sl;
         }
         __syncthreads();
-        {   // exclusive scan of the sub-bucket counts in place (+ total at cnt[nsub]); longest sub-bucket
-            constexpr int PER = kLocCounters / kLocThreads;   // 12 (read twice rather than kept in registers)
+        {   // exclusive scan of the sub-bucket counts in place (packed; cnt word nsub / 2 also closes the table); longest sub-bucket
+            constexpr int PER = kLocCounters / 2 / kLocThreads;   // 12 words = 24 counters per thread, read twice rather than kept
+            const u32 nw = nsub / 2 + 1;
             u32 sum = 0, mx = 0;
 #pragma unroll
-            for (int q = 0; q < PER; ++q) {
+            for (int q = 0; q < PER + 1; ++q) {
                 const u32 i = tid * PER + q;
-                const u32 c = i < nsub ? cnt[i] : 0;
-                sum += c;
-                mx = max(mx, c);
+                if (q < PER || tid == kLocThreads - 1) {
+                    const u32 v = i < nw ? cnt[i] : 0;
+                    sum += (v & 0xffffu) + (v >> 16);
+                    mx = max(mx, max(v & 0xffffu, v >> 16));
+                }
             }
             u32 total;
             u32 run = block_exclusive_scan(sum, SumOp(), total, wsm);
 #pragma unroll
-            for (int q = 0; q < PER; ++q) {
+            for (int q = 0; q < PER + 1; ++q) {
                 const u32 i = tid * PER + q;
-                if (i < nsub) { const u32 c = cnt[i]; cnt[i] = run; run += c; }
+                if ((q < PER || tid == kLocThreads - 1) && i < nw) {
+                    const u32 v = cnt[i];
+                    const u32 a0 = run, a1 = run + (v & 0xffffu);
+                    cnt[i] = a0 | (a1 << 16);
+                    run = a1 + (v >> 16);
+                }
             }
-            if (tid == 0) cnt[nsub] = total;
 #pragma unroll
             for (int dd = 16; dd; dd >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, dd));
             if ((tid & 31u) == 0) atomicMax(&s_max, mx);
         }
         __syncthreads();
         ranked = s_max <= u32(kLocRankMax);
+        {   // place: the pairs move from their striped places to their sub-buckets (through registers: in place)
+            u64 key[kLocFastItems];
+            IdxT val[kLocFastItems];
 #pragma unroll
-        for (int j = 0; j < kLocFastItems; ++j) {
-            const u32 li = j * kLocThreads + tid;
-            if (li < count) {
-                const u64 k = src_k[lo + li];
-                const u32 d = (u32(k >> shift) & dmask) - ba;
-                const u32 sub = (u32(ord[d]) << w) | (u32(k >> wshift) & wmask);
-                const u32 pos = cnt[sub] + slot[j];
-                sk[pos] = k;
-                sv[pos] = src_v[lo + li];
+            for (int j = 0; j < kLocFastItems; ++j) {
+                const u32 li = j * kLocThreads + tid;
+                if (li < count) { key[j] = sk[li]; val[j] = sv[li]; }
+            }
+            __syncthreads();
+#pragma unroll
+            for (int j = 0; j < kLocFastItems; ++j) {
+                const u32 li = j * kLocThreads + tid;
+                if (li < count) {
+                    const u64 k = key[j];
+                    const u32 d = (u32(k >> shift) & dmask) - ba;
+                    const u32 sub = (u32(ord[d]) << w) | (u32(k >> wshift) & wmask);
+                    const u32 pos = msd_sub_off(cnt, sub) + ((slot2[j >> 1] >> ((j & 1) * 16)) & 0xffffu);
+                    sk[pos] = k;
+                    sv[pos] = val[j];
+                }
             }
         }
         __syncthreads();
         if (ranked) {
-            // every pair: its rank among the keys of its sub-bucket (ties by position) -> final place
+            // every pair: its rank among the keys of its sub-bucket (ties by position) -> final place. Inside a sub-bucket only
+            // the bits below wshift differ: when those fit a word the comparisons run on the low words.
+            const bool low32 = wshift <= 32;
 #pragma unroll
             for (int j = 0; j < kLocFastItems; ++j) {
                 const u32 p = j * kLocThreads + tid;
-                slot[j] = ~0u;
+                u32 r = 0xffffu;
                 if (p < count) {
                     const u64 k = sk[p];
                     const u32 d = (u32(k >> shift) & dmask) - ba;
                     const u32 sub = (u32(ord[d]) << w) | (u32(k >> wshift) & wmask);
-                    const u32 s0 = cnt[sub], s1 = cnt[sub + 1];
-                    u32 r = s0;
-                    for (u32 q = s0; q < s1; ++q) {
-                        const u64 o = sk[q];
-                        r += (o < k || (o == k && q < p)) ? 1u : 0u;
+                    const u32 s0 = msd_sub_off(cnt, sub), s1 = msd_sub_off(cnt, sub + 1);
+                    r = s0;
+                    if (low32) {
+                        const u32 kl = u32(k);
+                        const u32* skl = reinterpret_cast<const u32*>(sk);
+                        for (u32 q = s0; q < s1; ++q) {
+                            const u32 o = skl[2 * q];
+                            r += (o < kl || (o == kl && q < p)) ? 1u : 0u;
+                        }
+                    } else {
+                        for (u32 q = s0; q < s1; ++q) {
+                            const u64 o = sk[q];
+                            r += (o < k || (o == k && q < p)) ? 1u : 0u;
+                        }
                     }
-                    slot[j] = r;
                 }
+                if (j & 1) slot2[j >> 1] |= r << 16; else slot2[j >> 1] = r;
             }
             {   // permute the keys, then the values (one array at a time: half the registers)
                 u64 key[kLocFastItems];
@@ -562,7 +614,7 @@ __device__ void msd_local_sort_range(const u64* __restrict__ src_k, const IdxT* 
                 for (int j = 0; j < kLocFastItems; ++j) { const u32 p = j * kLocThreads + tid; if (p < count) key[j] = sk[p]; }
                 __syncthreads();
 #pragma unroll
-                for (int j = 0; j < kLocFastItems; ++j) if (slot[j] != ~0u) sk[slot[j]] = key[j];
+                for (int j = 0; j < kLocFastItems; ++j) { const u32 p = j * kLocThreads + tid; if (p < count) sk[(slot2[j >> 1] >> ((j & 1) * 16)) & 0xffffu] = key[j]; }
             }
             {
                 IdxT val[kLocFastItems];
@@ -570,13 +622,10 @@ __device__ void msd_local_sort_range(const u64* __restrict__ src_k, const IdxT* 
                 for (int j = 0; j < kLocFastItems; ++j) { const u32 p = j * kLocThreads + tid; if (p < count) val[j] = sv[p]; }
                 __syncthreads();
 #pragma unroll
-                for (int j = 0; j < kLocFastItems; ++j) if (slot[j] != ~0u) sv[slot[j]] = val[j];
+                for (int j = 0; j < kLocFastItems; ++j) { const u32 p = j * kLocThreads + tid; if (p < count) sv[(slot2[j >> 1] >> ((j & 1) * 16)) & 0xffffu] = val[j]; }
             }
             __syncthreads();
         }
-    } else {
-        for (u32 i = tid; i < count; i += kLocThreads) { sk[i] = src_k[lo + i]; sv[i] = src_v[lo + i]; }
-        __syncthreads();
     }
     if (!ranked) {
         // the batch sits in shared memory (in child order, grouped by sub-bucket when the fast path ran): sort it over every
@@ -592,24 +641,24 @@ __device__ void msd_local_sort_range(const u64* __restrict__ src_k, const IdxT* 
     __syncthreads();
 }
 
-// One block per window of kLocWindow positions of a row: the children that START inside the window, except those that
-// went on to the next level (larger than kLocSmall), are sorted by the key bits below the level's digit.
-// `table` holds the children's END offsets (the scatter advanced every cursor from the child's start to its end).
-template <typename IdxT, typename OffT>
-__global__ void __launch_bounds__(kLocThreads, 2)
-msd_local_kernel(const u64* __restrict__ src_k, const IdxT* __restrict__ src_v, u64* __restrict__ dst_k, IdxT* __restrict__ dst_v,
-                 const OffT* __restrict__ table, const MsdDesc* __restrict__ wins, const u32* __restrict__ n_wins, int shift, u32 dmask,
-                 int allow_fast, u32* __restrict__ err) {
-    extern __shared__ __align__(16) unsigned char msd_smem[];
-    u64* sk = reinterpret_cast<u64*>(msd_smem);
-    IdxT* sv = reinterpret_cast<IdxT*>(sk + kLocCap);
-    unsigned char* aux = reinterpret_cast<unsigned char*>(sv + kLocCap);
-    __shared__ u64 big_s[8], big_e[8];
-    __shared__ u32 big_b[8];
-    __shared__ u32 n_big;
+// A batch of the local sort: consecutive small children of one row, at most kLocCap pairs.
+struct MsdBatch {
+    u64 lo;
+    u32 count, row, ba, bb;
+};
 
-    if (blockIdx.x >= *n_wins) return;
-    const MsdDesc wd = wins[blockIdx.x];     // base = first position of the window, count = index of the window inside its row
+// One warp per window of kLocWindow positions of a row: the children that START inside the window, except those that went
+// on to the next level (larger than kLocSmall), become one batch — or several, when large children lie in between.
+// `table` holds the children's END offsets (the scatter advanced every cursor from the child's start to its end).
+// Doing this ahead of the sort takes a chain of eight dependent table reads out of every sorting block, and windows
+// without small children (levels whose children all went on) cost one warp here instead of one block there.
+template <typename OffT>
+__global__ void __launch_bounds__(256) msd_batches_kernel(const OffT* __restrict__ table, const MsdDesc* __restrict__ wins,
+                                                          const u32* __restrict__ n_wins, MsdBatch* __restrict__ batches,
+                                                          u32* __restrict__ n_batches, u32 cap, u32* __restrict__ err) {
+    const u32 win = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31u;
+    if (win >= *n_wins) return;
+    const MsdDesc wd = wins[win];     // base = first position of the window, count = index of the window inside its row
     const OffT* E = table + u64(wd.row) * kMsdBins;
     const u64 seg_hi = u64(E[kMsdBins - 1]);  // the last child ends where the row ends
     const u64 wlo = wd.base, whi = min(wlo + u64(kLocWindow), seg_hi);
@@ -620,39 +669,47 @@ msd_local_kernel(const u64* __restrict__ src_k, const IdxT* __restrict__ src_v, 
     const u64 lo = b0 == 0 ? wlo : u64(E[b0 - 1]);
     const u64 hi = u64(E[b1 - 1]);
     if (lo >= hi) return;
-    if (threadIdx.x == 0) n_big = 0;
-    __syncthreads();
-    for (u32 bq = b0 + threadIdx.x; bq < b1; bq += kLocThreads) {
-        const u64 s = bq == b0 ? lo : u64(E[bq - 1]), e = u64(E[bq]);
-        if (e - s > u64(kLocSmall)) {
-            const u32 i = atomicAdd(&n_big, 1u);
-            if (i < 8) { big_s[i] = s; big_e[i] = e; big_b[i] = bq; }
-        }
-    }
-    __syncthreads();
-    const u32 nb = n_big;
-    if (nb > 8) { if (threadIdx.x == 0) atomicOr(err, 1u); return; }   // cannot happen: large children start > kLocSmall apart
-    if (threadIdx.x == 0) {   // order the few large children by position
-        for (u32 a = 1; a < nb; ++a) {
-            const u64 s = big_s[a], e = big_e[a];
-            const u32 bb = big_b[a];
-            u32 w = a;
-            while (w > 0 && big_s[w - 1] > s) { big_s[w] = big_s[w - 1]; big_e[w] = big_e[w - 1]; big_b[w] = big_b[w - 1]; --w; }
-            big_s[w] = s; big_e[w] = e; big_b[w] = bb;
-        }
-    }
-    __syncthreads();
+    auto emit = [&](u64 from, u64 to, u32 ba, u32 bb) {
+        if (lane != 0) return;
+        if (to - from > u64(kLocCap)) { atomicOr(err, 2u); return; }
+        const u32 i = atomicAdd(n_batches, 1u);
+        if (i >= cap) { atomicOr(err, 4u); return; }
+        MsdBatch bt;
+        bt.lo = from; bt.count = u32(to - from); bt.row = wd.row; bt.ba = ba; bt.bb = bb;
+        batches[i] = bt;
+    };
     u64 cur = lo;
     u32 cur_b = b0;
-    for (u32 i = 0; i <= nb; ++i) {
-        const u64 stop = i < nb ? big_s[i] : hi;
-        const u32 stop_b = i < nb ? big_b[i] : b1;
-        if (stop > cur) {
-            if (stop - cur > u64(kLocCap)) { if (threadIdx.x == 0) atomicOr(err, 2u); return; }
-            msd_local_sort_range<IdxT, OffT>(src_k, src_v, dst_k, dst_v, cur, stop, E, cur, cur_b, stop_b, shift, dmask, sk, sv, aux, allow_fast != 0);
+    for (u32 base = b0; base < b1; base += 32) {
+        const u32 bq = base + lane;
+        u64 s = 0, e = 0;
+        if (bq < b1) { s = bq == b0 ? lo : u64(E[bq - 1]); e = u64(E[bq]); }
+        unsigned big = __ballot_sync(0xffffffffu, bq < b1 && e - s > u64(kLocSmall));
+        while (big) {
+            const int l = __ffs(big) - 1;
+            const u64 bs = __shfl_sync(0xffffffffu, s, l), be = __shfl_sync(0xffffffffu, e, l);
+            if (bs > cur) emit(cur, bs, cur_b, base + l);
+            cur = be;
+            cur_b = base + l + 1;
+            big &= big - 1;
         }
-        if (i < nb) { cur = big_e[i]; cur_b = big_b[i] + 1; }
     }
+    if (hi > cur) emit(cur, hi, cur_b, b1);
+}
+
+template <typename IdxT, typename OffT>
+__global__ void __launch_bounds__(kLocThreads, 2)
+msd_local_kernel(const u64* __restrict__ src_k, const IdxT* __restrict__ src_v, u64* __restrict__ dst_k, IdxT* __restrict__ dst_v,
+                 const OffT* __restrict__ table, const MsdBatch* __restrict__ batches, const u32* __restrict__ n_batches, int shift,
+                 u32 dmask, int allow_fast) {
+    extern __shared__ __align__(16) unsigned char msd_smem[];
+    u64* sk = reinterpret_cast<u64*>(msd_smem);
+    IdxT* sv = reinterpret_cast<IdxT*>(sk + kLocCap);
+    unsigned char* aux = reinterpret_cast<unsigned char*>(sv + kLocCap);
+    if (blockIdx.x >= *n_batches) return;
+    const MsdBatch bt = batches[blockIdx.x];
+    msd_local_sort_range<IdxT, OffT>(src_k, src_v, dst_k, dst_v, bt.lo, bt.count, table + u64(bt.row) * kMsdBins, bt.ba, bt.bb, shift, dmask,
+                                     sk, sv, aux, allow_fast != 0);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -803,10 +860,17 @@ bool msd_sort_suffixes(const u8* d_text, u64 n, const uint16_t* d_code, int b, i
             if (h_ctr[0] > next_cap) throw CudaError(ASGART_B200_ECUDA, "msd sort: more large children than fit the row list");
             if (elems > h_ctr[1]) {
                 if (st && st->local) st->local->begin();
-                msd_local_kernel<IdxT, OffT><<<unsigned(wins_ub), kLocThreads, smem_loc, stream>>>(dst_k, dst_v, keys_a, vals_a, tp, win_desc.p, n_wins,
-                                                                                                  shift, dmask, local_fast ? 1 : 0, d_err.p);
+                // windows -> batches (a window yields one batch, plus one per large child inside it), then one block per batch
+                const u64 cap = wins_ub + h_ctr[0] + 1;
+                DevBuf<MsdBatch> batches(cap, stream);
+                DevBuf<u32> n_batches(1, stream);
+                n_batches.zero();
+                msd_batches_kernel<OffT><<<unsigned(ceil_div(wins_ub, 8)), 256, 0, stream>>>(tp, win_desc.p, n_wins, batches.p, n_batches.p, u32(cap), d_err.p);
                 KERNEL_CHECK();
-                count_launch();
+                msd_local_kernel<IdxT, OffT><<<unsigned(cap), kLocThreads, smem_loc, stream>>>(dst_k, dst_v, keys_a, vals_a, tp, batches.p, n_batches.p,
+                                                                                              shift, dmask, local_fast ? 1 : 0);
+                KERNEL_CHECK();
+                count_launch(2);
                 if (st && st->local) st->local->end(1, (elems - h_ctr[1]) * 2 * (sizeof(u64) + sizeof(IdxT)));
             }
         } else if (!to_a) {
