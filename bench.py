@@ -395,25 +395,67 @@ def run_ours(args):
     stats_e2e = ctx.stats()
     assert fam2.digest() == fam.digest()
     digest = fam.digest()
+    free_b, total_b = torch.cuda.mem_get_info(dev)     # the library's block cache only grows: what is in use now is the peak
+    sa_bad = ctx.check_sa() if args.check_sa else None   # on-device sufcheck of this rank's copy of the index
+    if dist is not None:
+        t = torch.tensor([total_b - free_b, -1 if sa_bad is None else sa_bad], dtype=torch.int64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        peak_dev, sa_bad = int(t[0]), (None if int(t[1]) < 0 else int(t[1]))
+    else:
+        peak_dev = total_b - free_b
     g = golden(args.config) if not args.scale_n else None
     digest_ok = (digest == g["families_sha256"]) if g else None     # None: no full-size golden for this run (scaled workload)
 
     if rank == 0:
         peak, peak_src = peaks()
         K = args.steps
-        # roofline kernel: rs_scatter_kernel, the launches of the initial sort (each moves all n+1 (key, index) pairs)
-        scat_ms = stats["ms_sa_scatter_main"] / max(1, stats["launches_sa_scatter_main"])
-        scat_bytes = stats["bytes_sa_scatter_main"] / max(1, stats["launches_sa_scatter_main"])
-        achieved = scat_bytes / (scat_ms * 1e-3) / 1e9 if scat_ms > 0 else 0.0
+        # kernel families of the step: device ms (CUDA events on the library stream, accumulated over the K steps), launches
+        # and ALGORITHMIC bytes. The roofline block describes the family with the largest share.
+        msd = stats["msd_levels"] > 0
+        fams = {}
+
+        def family(name, what, ms_tot, launches, nbytes):
+            if launches and ms_tot > 0:
+                fams[name] = {"what": what, "ms_per_step": ms_tot / K, "launches_per_step": launches / K, "ms_per_launch": ms_tot / launches,
+                              "bytes_per_launch": nbytes / launches, "alg_GBps": nbytes / ms_tot / 1e6, "frac_of_hbm_peak": nbytes / ms_tot / 1e6 / peak,
+                              "share_of_step": ms_tot / ms if ms else None}
+        if msd:
+            family("msd_local_kernel", "initial sort, finishing sort of the small buckets in shared memory (12 B read + 12 B written per suffix)",
+                   stats["ms_msd_local"], stats["launches_msd_local"], stats["bytes_msd_local"])
+            family("msd_scatter_kernel", "initial sort, 12-bit partition pass over (key, index) pairs, levels >= 1 (24 B per pair)",
+                   stats["ms_sa_scatter_main"], stats["launches_sa_scatter_main"], stats["bytes_sa_scatter_main"])
+            family("msd_scatter_kernel<text>", "initial sort, level 0: keys built from the text and partitioned (1 B read + 12 B written per suffix)",
+                   stats["ms_msd_scatter0"], K, stats["bytes_msd_scatter0"])
+            family("msd_hist_kernel", "initial sort, per-level digit histograms (1 B per suffix from the text, then 8 B per pair)",
+                   stats["ms_msd_hist"], K * max(1, int(stats["msd_levels"])), stats["bytes_msd_hist"])
+        else:
+            family("rs_scatter_kernel", "initial sort (LSD form), stable 8-bit scatter pass (24 B per suffix)",
+                   stats["ms_sa_scatter_main"], stats["launches_sa_scatter_main"], stats["bytes_sa_scatter_main"])
+        family("probe_search_kernel", "k-mer probe search: LUT narrow + lock-step equal range + filters (SURVEY 8d gather bytes)",
+               stats["ms_probe"], stats["launches_probe"], stats["bytes_probe"])
+        family("gather_rank_kernel", "prefix doubling: rank[i + D] gathers (12 B per unsorted suffix and round)",
+               stats["ms_sa_gather"], stats["launches_sa_gather"], stats["bytes_sa_gather"])
+        top = max(fams, key=lambda k: fams[k]["ms_per_step"]) if fams else None
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tpath):
+        if top and os.path.exists(tpath):
             try:
-                tj = json.load(open(tpath))
-                if tj.get("algorithmic_bytes_per_launch") == int(scat_bytes):      # the capture is of this very launch shape
-                    traffic = tj.get("rs_scatter_kernel_dram_bytes_per_launch")
+                tj_all = json.load(open(tpath))
+                tj = tj_all.get("kernels", {}).get(top)
+                # the capture must be of this very workload and launch pattern (same config, same launches per step)
+                if tj and tj_all.get("config") == args.config and tj_all.get("strand_bp") == n1 - 1 and world == 1 \
+                        and abs(tj["launches_per_step"] - fams[top]["launches_per_step"]) < 0.5:
+                    traffic = tj["dram_bytes_per_launch"]
             except Exception:
                 traffic = None
+        roof = {"kernel": None, "bound": "hbm", "achieved": 0.0, "peak": peak, "unit": "GB/s", "frac": None, "traffic": None}
+        if top:
+            f = fams[top]
+            roof = {"kernel": f"{top} ({f['what']})", "bound": "hbm", "achieved": f["alg_GBps"], "peak": peak, "unit": "GB/s",
+                    "frac": f["frac_of_hbm_peak"], "traffic": traffic, "peak_source": peak_src, "bytes_per_launch": f["bytes_per_launch"],
+                    "ms_per_launch": f["ms_per_launch"], "launches_per_step": f["launches_per_step"], "share_of_step": f["share_of_step"],
+                    "note": ("largest share of the step among the kernel families (kernel_families lists all of them); msd_local_kernel works in "
+                             "shared memory and is bound by instruction issue, not by HBM (profiles/r2_ncu_full_msd_v1.summary.txt)")}
         line = {
             "metric": METRIC, "value": bp * K / (ms * 1e-3), "unit": "bp/s", "n_gpus": world, "steps": K, "warmup": args.warmup,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -424,25 +466,14 @@ def run_ours(args):
             "timing": "CUDA events on the library stream around the K-step loop; wall clock agrees within ms_per_step_wall",
             "ms_per_step_wall": wall / K,
             "families_sha256": digest, "families_match_oracle_golden": digest_ok,
+            "device_bytes_peak": peak_dev, "sa_check_violations": sa_bad,
             "clocks": clocks,
             "e2e": {"value": bp * K / (ms_e2e * 1e-3), "unit": "bp/s", "ms_per_step": ms_e2e / K,
                     "h2d_bytes_per_step": stats_e2e["h2d_bytes"] // K, "d2h_bytes_per_step": stats_e2e["d2h_bytes"] // K},
             "gpu_launches": int(stats["launches_total"]),
-            "roofline": {"kernel": "rs_scatter_kernel (radix-sort scatter pass of the SA build; launches of the initial sort, 24 B per suffix)", "bound": "hbm",
-                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
-                         "traffic": traffic, "peak_source": peak_src,
-                         "bytes_per_launch": scat_bytes, "ms_per_launch": scat_ms,
-                         "launches_per_step": stats["launches_sa_scatter_main"] / K,
-                         "share_of_step": stats["ms_sa_scatter_main"] / ms if ms else None,
-                         "all_launches": {"per_step": stats["launches_sa_scatter"] / K, "ms_per_step": stats["ms_sa_scatter"] / K,
-                                          "share_of_step": stats["ms_sa_scatter"] / ms if ms else None,
-                                          "alg_GBps": stats["bytes_sa_scatter"] / max(stats["ms_sa_scatter"], 1e-9) / 1e6}},
-            "kernel_families": {
-                "sa_sort_pass": {"ms_per_step": stats["ms_sa_sort"] / K, "alg_GBps": stats["bytes_sa_sort"] / max(stats["ms_sa_sort"], 1e-9) / 1e6},
-                "sa_gather": {"ms_per_step": stats["ms_sa_gather"] / K, "alg_GBps": stats["bytes_sa_gather"] / max(stats["ms_sa_gather"], 1e-9) / 1e6},
-                "probe_search": {"ms_per_step": stats["ms_probe"] / K, "alg_GBps": stats["bytes_probe"] / max(stats["ms_probe"], 1e-9) / 1e6,
-                                 "probes_per_s": stats["n_probes"] / max(stats["ms_probe"], 1e-9) * 1e3},
-            },
+            "roofline": roof,
+            "kernel_families": fams,
+            "initial_sort": {"form": "msd" if msd else "lsd", "levels": int(stats["msd_levels"]), "ms_per_step": stats["ms_sa_sort"] / K},
             "phases_ms_per_step": {k: stats[k] / K for k in ("ms_sa_build", "ms_lut", "ms_search", "ms_automaton", "ms_post", "ms_d2h")},
             "counters_per_step": {k: stats[k] // K for k in ("n_probes", "n_searched", "n_skipped_n", "n_skipped_card", "n_matches")}
                                  | {"sa_rounds": stats["sa_rounds"], "families": fam.n_families, "duplicons": len(fam.sds)},
@@ -498,6 +529,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--index-bits", type=int, default=0, choices=[0, 32, 64], help="force the suffix-index width (0 = auto)")
+    ap.add_argument("--check-sa", action="store_true", help="run the on-device sufcheck on every rank's index after the timed steps")
     ap.add_argument("--ref-sample-bp", type=int, default=0, help="--impl reference: genome length per step (0 = bounded default)")
     ap.add_argument("--no-ingest", action="store_true", help="skip the FASTA-ingest measurement (N=1 only)")
     args = ap.parse_args()
