@@ -16,6 +16,12 @@ POST_FILTER_NS, POST_REORDER, POST_REDUCE_OVERLAP, POST_SORT, POST_ALL = 1, 2, 4
 POST_COMPUTE_SCORE = 16
 LUT_SIZE = 390625
 SLICE_NO_DIRECT, SLICE_NO_REVERSED, SLICE_NO_UNCOMPLEMENTED, SLICE_NO_COMPLEMENTED, SLICE_NO_INTER, SLICE_NO_INTRA, SLICE_MIN_LENGTH = 1, 2, 4, 8, 16, 32, 64
+SLICE_COLLAPSE, SLICE_NO_INTER_RELAXED, SLICE_REGEXP = 128, 256, 512
+
+
+class SliceOptions(C.Structure):
+    _fields_ = [("flags", C.c_uint32), ("reserved", C.c_uint32), ("min_length", C.c_uint64), ("max_family_members", C.c_int64),
+                ("keep_fragments", C.c_char_p), ("restrict_fragments", C.c_char_p), ("exclude_fragments", C.c_char_p)]
 
 
 class Settings(C.Structure):
@@ -92,7 +98,8 @@ SYMBOLS = [
     "asgart_b200_ctx_ingest_begin", "asgart_b200_ctx_ingest_fasta", "asgart_b200_ctx_ingest_file",
     "asgart_b200_ctx_ingest_finish", "asgart_b200_ctx_download_strand", "asgart_b200_run_files_passes",
     "asgart_b200_ctx_build_index_trim", "asgart_b200_effective_trim", "asgart_b200_slice_families",
-    "asgart_b200_run_files_sliced",
+    "asgart_b200_run_files_sliced", "asgart_b200_run_files_sliced_ex", "asgart_b200_run_result_new", "asgart_b200_run_result_slice",
+    "asgart_b200_run_result_to_json", "asgart_b200_run_result_error", "asgart_b200_run_result_free",
 ]
 
 _lib = None
@@ -169,6 +176,12 @@ def load() -> C.CDLL:
         "asgart_b200_run_files": (vp, [C.c_char_p, PS, i32, C.POINTER(C.c_char_p)]),
         "asgart_b200_run_files_passes": (vp, [C.c_char_p, PS, i32, i32, C.POINTER(C.c_char_p)]),
         "asgart_b200_run_files_sliced": (vp, [C.c_char_p, PS, i32, i32, u32, C.c_uint64, i64, C.POINTER(C.c_char_p)]),
+        "asgart_b200_run_files_sliced_ex": (vp, [C.c_char_p, PS, i32, i32, C.POINTER(SliceOptions), C.POINTER(C.c_char_p)]),
+        "asgart_b200_run_result_new": (vp, [vp, PS, vp, i64, vp]),
+        "asgart_b200_run_result_slice": (i32, [vp, C.POINTER(SliceOptions)]),
+        "asgart_b200_run_result_to_json": (vp, [vp]),
+        "asgart_b200_run_result_error": (C.c_char_p, [vp]),
+        "asgart_b200_run_result_free": (None, [vp]),
         "asgart_b200_synth_length": (i64, [i32, i32, i64]),
         "asgart_b200_synth_fill": (i64, [i32, i32, i64, C.c_uint64, i64, i32, vp, i64, i32]),
         "asgart_b200_synth_fragments": (i64, [i32, i32, i64, vp, i64, vp, vp, i64]),

@@ -462,6 +462,38 @@ class Prepared:
             raise AsgartB200Error(rc, "slice_families failed")
         return _take_result(self.L, rh)
 
+    def slice_json(self, settings: RunSettings, fam: Families, collapse=False, no_direct=False, no_reversed=False,
+                   no_uncomplemented=False, no_complemented=False, no_inter=False, no_inter_relaxed=False, no_intra=False,
+                   min_length: Optional[int] = None, max_family_members: Optional[int] = None,
+                   keep_fragments: Optional[Sequence[str]] = None, restrict_fragments: Optional[Sequence[str]] = None,
+                   exclude_fragments: Optional[Sequence[str]] = None, regexp=False) -> str:
+        """`asgart-slice` on the result of a run (src/bin/asgart-slice.rs:126-191), options applied in its order -> the JSON
+        it would write. Host code only."""
+        flags = (_lib.SLICE_COLLAPSE * bool(collapse) | _lib.SLICE_NO_DIRECT * bool(no_direct) | _lib.SLICE_NO_REVERSED * bool(no_reversed)
+                 | _lib.SLICE_NO_UNCOMPLEMENTED * bool(no_uncomplemented) | _lib.SLICE_NO_COMPLEMENTED * bool(no_complemented)
+                 | _lib.SLICE_NO_INTER * bool(no_inter) | _lib.SLICE_NO_INTER_RELAXED * bool(no_inter_relaxed)
+                 | _lib.SLICE_NO_INTRA * bool(no_intra) | _lib.SLICE_MIN_LENGTH * (min_length is not None) | _lib.SLICE_REGEXP * bool(regexp))
+        enc = lambda l: None if l is None else "\n".join(l).encode()   # noqa: E731
+        op = _lib.SliceOptions(flags, 0, int(min_length or 0), -1 if max_family_members is None else int(max_family_members),
+                               enc(keep_fragments), enc(restrict_fragments), enc(exclude_fragments))
+        st = settings.to_c()
+        off = np.ascontiguousarray(fam.fam_offsets, dtype=np.uint64)
+        sds = np.ascontiguousarray(fam.sds, dtype=PROTOSD_DTYPE)
+        rr = self.L.asgart_b200_run_result_new(self.h, C.byref(st), _ptr(off), len(off) - 1, _ptr(sds) if len(sds) else None)
+        if not rr:
+            raise AsgartB200Error(_lib.EINVAL, "run_result_new failed")
+        try:
+            rc = self.L.asgart_b200_run_result_slice(rr, C.byref(op))
+            if rc != 0:
+                raise AsgartB200Error(rc, self.L.asgart_b200_run_result_error(rr).decode())
+            p = self.L.asgart_b200_run_result_to_json(rr)
+            try:
+                return C.string_at(p).decode()
+            finally:
+                self.L.asgart_b200_free_string(p)
+        finally:
+            self.L.asgart_b200_run_result_free(rr)
+
     def to_json(self, settings: RunSettings, fam: Families) -> str:
         st = settings.to_c()
         off = np.ascontiguousarray(fam.fam_offsets, dtype=np.uint64)

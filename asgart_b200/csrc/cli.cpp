@@ -25,6 +25,9 @@ static void usage() {
             "      --no-direct --no-reversed --no-uncomplemented --no-complemented --no-inter --no-intra\n"
             "      --slice-min-length <N> --max-family-members <N>\n"
             "                              asgart-slice's duplicon filters, applied before the file is written\n"
+            "      --collapse --no-inter-relaxed\n"
+            "      --keep-fragments <A,B,..> --restrict-fragments <A,B,..> --exclude-fragments <A,B,..> [--regexp]\n"
+            "                              asgart-slice's fragment options (they rewrite the fragment map)\n"
             "      --device <N>            CUDA device [default: 0]\n"
             "      --with-direct           (with -R/-C) also run the direct pass on the same index and write both, combined as\n"
             "                              `asgart-slice` combines the two runs' files\n"
@@ -43,6 +46,9 @@ int main(int argc, char** argv) {
     uint64_t slice_min = 0;
     long long slice_max = -1;
     bool slice = false;
+    std::string keep_f, restrict_f, exclude_f;
+    bool have_keep = false, have_restrict = false, have_exclude = false;
+    auto commas = [](std::string v) { for (char& c : v) if (c == ',') c = '\n'; return v; };
     auto need = [&](int& i) -> const char* { if (i + 1 >= argc) { usage(); exit(2); } return argv[++i]; };
     for (int i = 1; i < argc; ++i) {
         std::string a = argv[i];
@@ -64,6 +70,12 @@ int main(int argc, char** argv) {
         else if (a == "--no-intra") { slice = true; slice_flags |= ASGART_B200_SLICE_NO_INTRA; }
         else if (a == "--slice-min-length") { slice = true; slice_flags |= ASGART_B200_SLICE_MIN_LENGTH; slice_min = strtoull(need(i), nullptr, 10); }
         else if (a == "--max-family-members") { slice = true; slice_max = atoll(need(i)); }
+        else if (a == "--collapse") { slice = true; slice_flags |= ASGART_B200_SLICE_COLLAPSE; }
+        else if (a == "--no-inter-relaxed") { slice = true; slice_flags |= ASGART_B200_SLICE_NO_INTER_RELAXED; }
+        else if (a == "--regexp") { slice_flags |= ASGART_B200_SLICE_REGEXP; }
+        else if (a == "--keep-fragments") { slice = true; have_keep = true; keep_f = commas(need(i)); }
+        else if (a == "--restrict-fragments") { slice = true; have_restrict = true; restrict_f = commas(need(i)); }
+        else if (a == "--exclude-fragments") { slice = true; have_exclude = true; exclude_f = commas(need(i)); }
         else if (a == "--trim") { st.has_trim = 1; st.trim_a = strtoull(need(i), nullptr, 10); st.trim_b = strtoull(need(i), nullptr, 10); }
         else if (a == "-h" || a == "--help") { usage(); return 0; }
         else if (a == "--reverse") st.reverse = 1;
@@ -86,7 +98,12 @@ int main(int argc, char** argv) {
     asgart_b200_settings passes[2] = {st, st};
     passes[1].reverse = passes[1].complement = 0;
     const int n_passes = (with_direct && (st.reverse || st.complement)) ? 2 : 1;
-    char* js = slice ? asgart_b200_run_files_sliced(joined.c_str(), passes, n_passes, device, slice_flags, slice_min, slice_max, &err)
+    asgart_b200_slice_options op{};
+    op.flags = slice_flags; op.min_length = slice_min; op.max_family_members = slice_max;
+    op.keep_fragments = have_keep ? keep_f.c_str() : nullptr;
+    op.restrict_fragments = have_restrict ? restrict_f.c_str() : nullptr;
+    op.exclude_fragments = have_exclude ? exclude_f.c_str() : nullptr;
+    char* js = slice ? asgart_b200_run_files_sliced_ex(joined.c_str(), passes, n_passes, device, &op, &err)
                      : asgart_b200_run_files_passes(joined.c_str(), passes, n_passes, device, &err);
     if (!js) { fprintf(stderr, "asgart-b200: %s\n", err ? err : "failed"); return 1; }
     char* name = asgart_b200_out_filename(joined.c_str(), prefix.c_str(), out.empty() ? nullptr : out.c_str(), &st);

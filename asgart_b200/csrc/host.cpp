@@ -12,6 +12,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <functional>
+#include <map>
+#include <regex>
 #include <sstream>
 #include <string>
 #include <thread>
@@ -484,29 +487,88 @@ const char* asgart_b200_prepared_fragment(const asgart_b200_prepared* p, int64_t
 }
 void asgart_b200_prepared_free(asgart_b200_prepared* p) { delete p; }
 
-char* asgart_b200_to_json(const asgart_b200_prepared* p, const asgart_b200_settings* st, const uint64_t* fam_off, int64_t n_fam,
-                          const asgart_b200_protosd* sds) {
+// ------------------------------------------------------------------------------------------------ RunResult
+// The SD-level result of a run (RunResult / StrandResult / SD, src/structs.rs:60-97, 471-493): what JSONExporter writes
+// and what asgart-slice reads back, edits and writes again.
+extern "C++" {
+namespace {
+struct SDRec {
+    std::string chr_left, chr_right;
+    uint64_t global_left, global_right, chr_left_position, chr_right_position, left_length, right_length;
+    float identity;
+    bool reversed, complemented;
+};
+}  // namespace
+
+struct asgart_b200_run_result {
+    std::string strand_name;
+    uint64_t strand_length = 0;
+    std::vector<Fragment> map;
+    asgart_b200_settings settings{};
+    std::vector<std::vector<SDRec>> families;
+    std::string error;
+};
+
+namespace {
+const char* const kCollapsedName = "ASGART_COLLAPSED";   // src/structs.rs:9
+
+const Fragment* find_chr(const std::vector<Fragment>& map, const std::string& name) {   // StrandResult::find_chr, :77-79
+    for (const Fragment& c : map) if (c.name == name) return &c;
+    return nullptr;
+}
+
+// ProtoSD -> SD (src/bin/asgart.rs:776-821): fragment by position, "unknown" outside every fragment
+void fill_run_result(asgart_b200_run_result& rr, const asgart_b200_prepared* p, const asgart_b200_settings* st, const uint64_t* fam_off,
+                     int64_t n_fam, const asgart_b200_protosd* sds) {
+    rr.strand_name = p->file_names;
+    rr.strand_length = 0;
+    for (const Fragment& f : p->map) rr.strand_length += f.length;   // bin/asgart.rs:772
+    rr.map = p->map;
+    rr.settings = *st;
+    rr.families.assign(size_t(n_fam), {});
+    for (int64_t f = 0; f < n_fam; ++f) {
+        for (uint64_t j = fam_off[f]; j < fam_off[f + 1]; ++j) {
+            const asgart_b200_protosd& sd = sds[j];
+            const Fragment* cl = chr_by_pos(p->map, sd.left);
+            const Fragment* cr = chr_by_pos(p->map, sd.right);
+            SDRec r;
+            r.chr_left = cl ? cl->name : "unknown";
+            r.chr_right = cr ? cr->name : "unknown";
+            r.global_left = sd.left; r.global_right = sd.right;
+            r.chr_left_position = sd.left - (cl ? cl->position : 0);
+            r.chr_right_position = sd.right - (cr ? cr->position : 0);
+            r.left_length = sd.left_length; r.right_length = sd.right_length;
+            r.identity = sd.identity;
+            r.reversed = sd.reversed != 0; r.complemented = sd.complemented != 0;
+            rr.families[size_t(f)].push_back(std::move(r));
+        }
+    }
+}
+
+// JSONExporter::save (src/exporters.rs:12-25): serde_json pretty layout, field order = declaration order
+std::string run_result_json(const asgart_b200_run_result& rr) {
     std::string o;
-    o.reserve(4096 + size_t(n_fam ? fam_off[n_fam] : 0) * 420);
+    size_t n_sds = 0;
+    for (const auto& f : rr.families) n_sds += f.size();
+    o.reserve(4096 + n_sds * 420);
     Ind in{o};
     auto key = [&](int level, const char* k) { in.nl(level); o += '"'; o += k; o += "\": "; };
     auto num = [&](uint64_t v) { o += std::to_string(v); };
-    uint64_t total = 0;
-    for (const Fragment& f : p->map) total += f.length;  // bin/asgart.rs:772
+    const asgart_b200_settings* st = &rr.settings;
     o += '{';
     key(1, "strand"); o += '{';
-    key(2, "name"); jstr(o, p->file_names); o += ',';
-    key(2, "length"); num(total); o += ',';
+    key(2, "name"); jstr(o, rr.strand_name); o += ',';
+    key(2, "length"); num(rr.strand_length); o += ',';
     key(2, "map"); o += '[';
-    for (size_t i = 0; i < p->map.size(); ++i) {
+    for (size_t i = 0; i < rr.map.size(); ++i) {
         if (i) o += ',';
         in.nl(3); o += '{';
-        key(4, "name"); jstr(o, p->map[i].name); o += ',';
-        key(4, "position"); num(p->map[i].position); o += ',';
-        key(4, "length"); num(p->map[i].length);
+        key(4, "name"); jstr(o, rr.map[i].name); o += ',';
+        key(4, "position"); num(rr.map[i].position); o += ',';
+        key(4, "length"); num(rr.map[i].length);
         in.nl(3); o += '}';
     }
-    if (!p->map.empty()) in.nl(2);
+    if (!rr.map.empty()) in.nl(2);
     o += ']';
     in.nl(1); o += "},";
     key(1, "settings"); o += '{';
@@ -521,21 +583,19 @@ char* asgart_b200_to_json(const asgart_b200_prepared* p, const asgart_b200_setti
     key(2, "skip_masked"); o += st->skip_masked ? "true" : "false";
     in.nl(1); o += "},";
     key(1, "families"); o += '[';
-    for (int64_t f = 0; f < n_fam; ++f) {
+    for (size_t f = 0; f < rr.families.size(); ++f) {
         if (f) o += ',';
         in.nl(2); o += '[';
-        for (uint64_t j = fam_off[f]; j < fam_off[f + 1]; ++j) {
-            const asgart_b200_protosd& sd = sds[j];
-            const Fragment* cl = chr_by_pos(p->map, sd.left);    // bin/asgart.rs:785-806
-            const Fragment* cr = chr_by_pos(p->map, sd.right);
-            if (j > fam_off[f]) o += ',';
+        for (size_t j = 0; j < rr.families[f].size(); ++j) {
+            const SDRec& sd = rr.families[f][j];
+            if (j) o += ',';
             in.nl(3); o += '{';
-            key(4, "chr_left"); jstr(o, cl ? cl->name : "unknown"); o += ',';
-            key(4, "chr_right"); jstr(o, cr ? cr->name : "unknown"); o += ',';
-            key(4, "global_left_position"); num(sd.left); o += ',';
-            key(4, "global_right_position"); num(sd.right); o += ',';
-            key(4, "chr_left_position"); num(sd.left - (cl ? cl->position : 0)); o += ',';
-            key(4, "chr_right_position"); num(sd.right - (cr ? cr->position : 0)); o += ',';
+            key(4, "chr_left"); jstr(o, sd.chr_left); o += ',';
+            key(4, "chr_right"); jstr(o, sd.chr_right); o += ',';
+            key(4, "global_left_position"); num(sd.global_left); o += ',';
+            key(4, "global_right_position"); num(sd.global_right); o += ',';
+            key(4, "chr_left_position"); num(sd.chr_left_position); o += ',';
+            key(4, "chr_right_position"); num(sd.chr_right_position); o += ',';
             key(4, "left_length"); num(sd.left_length); o += ',';
             key(4, "right_length"); num(sd.right_length); o += ',';
             key(4, "left_seq"); o += "null,";
@@ -545,15 +605,156 @@ char* asgart_b200_to_json(const asgart_b200_prepared* p, const asgart_b200_setti
             key(4, "complemented"); o += sd.complemented ? "true" : "false";
             in.nl(3); o += '}';
         }
-        if (fam_off[f + 1] > fam_off[f]) in.nl(2);
+        if (!rr.families[f].empty()) in.nl(2);
         o += ']';
     }
-    if (n_fam > 0) in.nl(1);
+    if (!rr.families.empty()) in.nl(1);
     o += ']';
     in.nl(0); o += "}\n";  // exporters.rs:15-17: writeln!
+    return o;
+}
+
+char* dup_string(const std::string& o) {
     char* out = static_cast<char*>(malloc(o.size() + 1));
     if (out) memcpy(out, o.c_str(), o.size() + 1);
     return out;
+}
+
+void drop_empty(asgart_b200_run_result& rr) {   // families.retain(|f| !f.is_empty())
+    rr.families.erase(std::remove_if(rr.families.begin(), rr.families.end(), [](const std::vector<SDRec>& f) { return f.empty(); }),
+                      rr.families.end());
+}
+template <typename Pred>
+void retain_sds(asgart_b200_run_result& rr, Pred keep) {
+    for (auto& f : rr.families) f.erase(std::remove_if(f.begin(), f.end(), [&](const SDRec& sd) { return !keep(sd); }), f.end());
+}
+bool in_list(const std::vector<std::string>& l, const std::string& n) { return std::find(l.begin(), l.end(), n) != l.end(); }
+
+// RunResult::flatten (src/structs.rs:350-416, `--collapse`): fragments no longer than mean + one standard deviation whose
+// name is longer than two bytes become one pseudo-fragment. As in the reference: its Start sits at (kept length + 1),
+// strand.length and the duplicons' global positions are left alone.
+void rr_flatten(asgart_b200_run_result& rr) {
+    if (rr.map.size() < 2) return;
+    const double n = double(rr.map.size());
+    double sum = 0;
+    for (const Fragment& c : rr.map) sum += double(c.length);
+    const double avg = sum / n;
+    double ss = 0;
+    for (const Fragment& c : rr.map) ss += std::pow(double(c.length) - avg, 2.0);
+    const double sd = std::sqrt(1.0 / (n - 1.0) * ss);
+    std::vector<Fragment> to_flatten, to_keep;
+    for (const Fragment& c : rr.map) if (double(c.length) <= avg + sd && c.name.size() > 2) to_flatten.push_back(c);
+    uint64_t to_flatten_len = 0, to_keep_len = 0;
+    for (const Fragment& c : to_flatten) to_flatten_len += c.length;
+    for (const Fragment& c : rr.map) {
+        bool fl = false;
+        for (const Fragment& r : to_flatten) fl = fl || r.name == c.name;
+        if (!fl) to_keep.push_back(c);
+    }
+    for (const Fragment& c : to_keep) to_keep_len += c.length;
+    uint64_t i = 0;
+    for (Fragment& c : to_keep) { c.position = i; i += c.length; }
+    for (Fragment& c : to_flatten) { c.position = i; i += c.length; }
+    std::map<std::string, uint64_t> pos;   // HashMap from (name, position): a repeated name keeps its last position
+    for (const Fragment& c : to_flatten) pos[c.name] = c.position;
+    rr.map = to_keep;
+    rr.map.push_back(Fragment{kCollapsedName, to_keep_len + 1, to_flatten_len});
+    for (auto& f : rr.families)
+        for (SDRec& s2 : f) {
+            const bool lm = pos.count(s2.chr_left) != 0, rm = pos.count(s2.chr_right) != 0;
+            if (lm) { s2.chr_left_position += pos[s2.chr_left]; s2.chr_left = kCollapsedName; }
+            if (rm) { s2.chr_right_position += pos[s2.chr_right]; s2.chr_right = kCollapsedName; }
+        }
+}
+
+// the common tail of keep/restrict (consolidate_families, src/structs.rs:204-230) and of exclude (:277-298, which unwraps)
+bool rr_relayout(asgart_b200_run_result& rr, const std::function<bool(const std::string&)>& keep_fragment, bool unwrap) {
+    drop_empty(rr);
+    rr.map.erase(std::remove_if(rr.map.begin(), rr.map.end(), [&](const Fragment& c) { return !keep_fragment(c.name); }), rr.map.end());
+    rr.strand_length = 0;
+    for (const Fragment& c : rr.map) rr.strand_length += c.length;
+    uint64_t i = 0;
+    for (Fragment& c : rr.map) { c.position = i; i += c.length; }
+    for (auto& f : rr.families)
+        for (SDRec& sd : f) {
+            const Fragment* l = find_chr(rr.map, sd.chr_left);
+            const Fragment* r = find_chr(rr.map, sd.chr_right);
+            if (unwrap && (!l || !r)) { rr.error = "exclude-fragments: a duplicon stands on a fragment that is not in the map; the reference panics here (Option::unwrap, src/structs.rs:291-294)"; return false; }
+            sd.global_left = l ? l->position + sd.chr_left_position : 0;
+            sd.global_right = r ? r->position + sd.chr_right_position : 0;
+        }
+    return true;
+}
+}  // namespace
+}  // extern "C++"
+
+char* asgart_b200_to_json(const asgart_b200_prepared* p, const asgart_b200_settings* st, const uint64_t* fam_off, int64_t n_fam,
+                          const asgart_b200_protosd* sds) {
+    asgart_b200_run_result rr;
+    fill_run_result(rr, p, st, fam_off, n_fam, sds);
+    return dup_string(run_result_json(rr));
+}
+
+asgart_b200_run_result* asgart_b200_run_result_new(const asgart_b200_prepared* p, const asgart_b200_settings* st, const uint64_t* fam_off,
+                                                   int64_t n_fam, const asgart_b200_protosd* sds) {
+    if (!p || !st || !fam_off || n_fam < 0 || (fam_off[n_fam] && !sds)) return nullptr;
+    auto* rr = new (std::nothrow) asgart_b200_run_result();
+    if (rr) fill_run_result(*rr, p, st, fam_off, n_fam, sds);
+    return rr;
+}
+void asgart_b200_run_result_free(asgart_b200_run_result* rr) { delete rr; }
+char* asgart_b200_run_result_to_json(const asgart_b200_run_result* rr) { return rr ? dup_string(run_result_json(*rr)) : nullptr; }
+const char* asgart_b200_run_result_error(const asgart_b200_run_result* rr) { return rr ? rr->error.c_str() : ""; }
+
+// asgart-slice's options in ITS order (src/bin/asgart-slice.rs:126-191)
+int32_t asgart_b200_run_result_slice(asgart_b200_run_result* rr, const asgart_b200_slice_options* op) {
+    if (!rr || !op) return ASGART_B200_EINVAL;
+    const uint32_t fl = op->flags;
+    if (fl & ASGART_B200_SLICE_COLLAPSE) rr_flatten(*rr);
+    auto filter = [&](auto keep) { retain_sds(*rr, keep); drop_empty(*rr); };
+    if (fl & ASGART_B200_SLICE_NO_DIRECT) filter([](const SDRec& sd) { return sd.reversed; });
+    if (fl & ASGART_B200_SLICE_NO_REVERSED) filter([](const SDRec& sd) { return !sd.reversed; });
+    if (fl & ASGART_B200_SLICE_NO_UNCOMPLEMENTED) filter([](const SDRec& sd) { return sd.complemented; });
+    if (fl & ASGART_B200_SLICE_NO_COMPLEMENTED) filter([](const SDRec& sd) { return !sd.complemented; });
+    if (fl & ASGART_B200_SLICE_NO_INTER) filter([](const SDRec& sd) { return sd.chr_left == sd.chr_right; });
+    if (fl & ASGART_B200_SLICE_NO_INTER_RELAXED)
+        filter([](const SDRec& sd) { return sd.chr_left == sd.chr_right || sd.chr_left == kCollapsedName || sd.chr_right == kCollapsedName; });
+    if (fl & ASGART_B200_SLICE_NO_INTRA) filter([](const SDRec& sd) { return sd.chr_left != sd.chr_right; });
+    if (fl & ASGART_B200_SLICE_MIN_LENGTH) { const uint64_t m = op->min_length; filter([m](const SDRec& sd) { return std::min(sd.left_length, sd.right_length) >= m; }); }
+    if (op->max_family_members >= 0) {
+        const size_t m = size_t(op->max_family_members);
+        rr->families.erase(std::remove_if(rr->families.begin(), rr->families.end(), [m](const std::vector<SDRec>& f) { return f.size() > m; }),
+                           rr->families.end());
+    }
+    const bool re_mode = (fl & ASGART_B200_SLICE_REGEXP) != 0;
+    // 0 keep (a leg on a listed fragment), 1 restrict (both legs), 2 exclude (neither leg)
+    auto select = [&](const char* arg, int mode) -> int32_t {
+        if (!arg) return ASGART_B200_OK;
+        const std::vector<std::string> items = split_lines(arg);
+        if (re_mode) {
+            for (const std::string& pat : items) {   // one call of the *_regexp method per pattern, like the reference's loop
+                std::regex re;
+                try { re.assign(pat, std::regex::ECMAScript); }
+                catch (const std::regex_error& e) { rr->error = "Error while compiling `" + pat + "`: " + e.what(); return ASGART_B200_EINVAL; }
+                auto m = [&](const std::string& n) { return std::regex_search(n, re); };
+                if (mode == 0) retain_sds(*rr, [&](const SDRec& sd) { return m(sd.chr_left) || m(sd.chr_right); });
+                else if (mode == 1) retain_sds(*rr, [&](const SDRec& sd) { return m(sd.chr_left) && m(sd.chr_right); });
+                else retain_sds(*rr, [&](const SDRec& sd) { return !m(sd.chr_left) && !m(sd.chr_right); });
+                if (!rr_relayout(*rr, [&](const std::string& n) { return mode == 2 ? !m(n) : m(n); }, mode == 2)) return ASGART_B200_EPANIC;
+            }
+        } else {
+            auto m = [&](const std::string& n) { return in_list(items, n); };
+            if (mode == 0) retain_sds(*rr, [&](const SDRec& sd) { return m(sd.chr_left) || m(sd.chr_right); });
+            else if (mode == 1) retain_sds(*rr, [&](const SDRec& sd) { return m(sd.chr_left) && m(sd.chr_right); });
+            else retain_sds(*rr, [&](const SDRec& sd) { return !m(sd.chr_left) && !m(sd.chr_right); });
+            if (!rr_relayout(*rr, [&](const std::string& n) { return mode == 2 ? !m(n) : m(n); }, mode == 2)) return ASGART_B200_EPANIC;
+        }
+        return ASGART_B200_OK;
+    };
+    int32_t rc = select(op->keep_fragments, 0);
+    if (!rc) rc = select(op->restrict_fragments, 1);
+    if (!rc) rc = select(op->exclude_fragments, 2);
+    return rc;
 }
 
 void asgart_b200_free_string(char* s) { free(s); }
@@ -634,7 +835,7 @@ char* asgart_b200_out_filename(const char* files, const char* prefix, const char
 // bytes go to HBM as they are read. Several passes combine as RunResult::from_files does for their JSON files
 // (structs.rs:114-141): strand and settings of the first, families concatenated in pass order.
 static char* run_files_impl(const char* files, const asgart_b200_settings* passes, int32_t n_passes, int32_t device,
-                            uint32_t slice_flags, uint64_t slice_min_length, int64_t slice_max_members, bool slice, const char** err) {
+                            const asgart_b200_slice_options* slice, const char** err) {
     static thread_local std::string msg;
     if (err) *err = nullptr;
     auto failf = [&](const std::string& m) -> char* { msg = m; if (err) *err = msg.c_str(); return nullptr; };
@@ -684,12 +885,11 @@ static char* run_files_impl(const char* files, const asgart_b200_settings* passe
         if (rc) failf(std::string("device pipeline failed: ") + asgart_b200_ctx_last_error(ctx));
         else if (!slice) js = asgart_b200_to_json(p, &passes[0], fam_off.data(), int64_t(fam_off.size()) - 1, sds.data());
         else {
-            asgart_b200_result* sl = nullptr;
-            rc = asgart_b200_slice_families(p, fam_off.data(), int64_t(fam_off.size()) - 1, sds.data(), slice_flags, slice_min_length,
-                                            slice_max_members, &sl);
-            if (rc) failf("slice_families failed");
-            else js = asgart_b200_to_json(p, &passes[0], sl->fam_off.data(), int64_t(sl->fam_off.size()) - 1, sl->sds.data());
-            delete sl;
+            asgart_b200_run_result* rr = asgart_b200_run_result_new(p, &passes[0], fam_off.data(), int64_t(fam_off.size()) - 1, sds.data());
+            if (!rr) failf("out of memory");
+            else if (asgart_b200_run_result_slice(rr, slice) != ASGART_B200_OK) failf(std::string("asgart-slice options: ") + asgart_b200_run_result_error(rr));
+            else js = asgart_b200_run_result_to_json(rr);
+            asgart_b200_run_result_free(rr);
         }
     }
     asgart_b200_ctx_destroy(ctx);
@@ -699,12 +899,19 @@ static char* run_files_impl(const char* files, const asgart_b200_settings* passe
 
 char* asgart_b200_run_files_passes(const char* files, const asgart_b200_settings* passes, int32_t n_passes, int32_t device,
                                    const char** err) {
-    return run_files_impl(files, passes, n_passes, device, 0, 0, -1, false, err);
+    return run_files_impl(files, passes, n_passes, device, nullptr, err);
 }
 
 char* asgart_b200_run_files_sliced(const char* files, const asgart_b200_settings* passes, int32_t n_passes, int32_t device,
                                    uint32_t slice_flags, uint64_t min_length, int64_t max_family_members, const char** err) {
-    return run_files_impl(files, passes, n_passes, device, slice_flags, min_length, max_family_members, true, err);
+    asgart_b200_slice_options op{};
+    op.flags = slice_flags; op.min_length = min_length; op.max_family_members = max_family_members;
+    return run_files_impl(files, passes, n_passes, device, &op, err);
+}
+
+char* asgart_b200_run_files_sliced_ex(const char* files, const asgart_b200_settings* passes, int32_t n_passes, int32_t device,
+                                      const asgart_b200_slice_options* options, const char** err) {
+    return run_files_impl(files, passes, n_passes, device, options, err);
 }
 
 char* asgart_b200_run_files(const char* files, const asgart_b200_settings* st, int32_t device, const char** err) {

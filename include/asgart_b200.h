@@ -292,8 +292,8 @@ ASGART_B200_API char *asgart_b200_run_files_sliced(const char *files, const asga
  * "unknown" for a position outside every fragment), --min-length (min(left_length, right_length) >= it), every one followed
  * by dropping the empty families (so families that were already empty stay when no such filter is given, as in the
  * reference), then --max-family-members (families with more duplicons are dropped, :196-198). min_length counts only with
- * ASGART_B200_SLICE_MIN_LENGTH (`--min-length 0` still drops empty families); max_family_members < 0 = not given. Not restated: --collapse, --no-inter-relaxed and the
- * fragment selection (--keep/--restrict/--exclude-fragments), which rewrite the fragment map. */
+ * ASGART_B200_SLICE_MIN_LENGTH (`--min-length 0` still drops empty families); max_family_members < 0 = not given. --collapse, --no-inter-relaxed and the
+ * fragment selection (--keep/--restrict/--exclude-fragments) rewrite the fragment map: asgart_b200_run_result_slice below. */
 #define ASGART_B200_SLICE_NO_DIRECT          1u
 #define ASGART_B200_SLICE_NO_REVERSED        2u
 #define ASGART_B200_SLICE_NO_UNCOMPLEMENTED  4u
@@ -301,10 +301,51 @@ ASGART_B200_API char *asgart_b200_run_files_sliced(const char *files, const asga
 #define ASGART_B200_SLICE_NO_INTER          16u
 #define ASGART_B200_SLICE_NO_INTRA          32u
 #define ASGART_B200_SLICE_MIN_LENGTH        64u
+#define ASGART_B200_SLICE_COLLAPSE         128u   /* asgart_b200_run_result_slice only */
+#define ASGART_B200_SLICE_NO_INTER_RELAXED 256u   /* asgart_b200_run_result_slice only */
+#define ASGART_B200_SLICE_REGEXP           512u   /* asgart_b200_run_result_slice only: fragment lists are patterns */
 ASGART_B200_API int32_t asgart_b200_slice_families(const asgart_b200_prepared *p, const uint64_t *family_offsets,
                                                    int64_t n_families, const asgart_b200_protosd *sds, uint32_t flags,
                                                    uint64_t min_length, int64_t max_family_members,
                                                    asgart_b200_result **out);
+
+/* ---- the whole of asgart-slice on the SD-level result (rest of row N3; host code, no device needed) ----------------
+ * RunResult as asgart writes it and asgart-slice reads it (src/structs.rs:92-97): strand name / length / fragment map,
+ * settings, families of SD records (fragment names and in-fragment positions, src/bin/asgart.rs:776-821).
+ * asgart_b200_run_result_slice applies asgart-slice's options in ITS order (src/bin/asgart-slice.rs:126-191):
+ *   --collapse            RunResult::flatten (src/structs.rs:350-416): fragments no longer than mean + 1 sd of the fragment
+ *                         lengths (f64, n-1 in the variance) whose name is longer than 2 bytes merge into ASGART_COLLAPSED;
+ *                         like the reference, its map entry sits at kept_length + 1 and strand.length / global positions
+ *                         are left as they were
+ *   --no-direct ... --no-inter, --no-inter-relaxed (:178-187: inter-fragment duplicons survive when a leg is collapsed),
+ *   --no-intra, --min-length, --max-family-members                          as asgart_b200_slice_families above
+ *   --keep-fragments / --restrict-fragments / --exclude-fragments (:232-348): a duplicon stays when a leg / both legs /
+ *                         no leg stands on a listed fragment; then empty families go, the map keeps (drops) the listed
+ *                         fragments, positions are re-laid end to end and every duplicon's global positions recomputed
+ *                         (0 for a fragment no longer in the map; --exclude unwraps instead: ASGART_B200_EPANIC).
+ *                         Lists are '\n'-separated names, NULL = option absent. With ASGART_B200_SLICE_REGEXP every entry
+ *                         is a pattern, applied one after the other like the reference's loop (unanchored search; the
+ *                         reference uses the Rust `regex` crate, this library std::regex ECMAScript — character classes,
+ *                         alternation, anchors and quantifiers agree, Rust-only syntax such as (?i) does not exist here).
+ * Errors: ASGART_B200_EINVAL (bad pattern) / ASGART_B200_EPANIC with asgart_b200_run_result_error() saying why. */
+typedef struct asgart_b200_run_result asgart_b200_run_result;
+typedef struct asgart_b200_slice_options {
+    uint32_t flags;               /* ASGART_B200_SLICE_* */
+    uint32_t reserved;
+    uint64_t min_length;          /* with ASGART_B200_SLICE_MIN_LENGTH */
+    int64_t max_family_members;   /* < 0: not given */
+    const char *keep_fragments, *restrict_fragments, *exclude_fragments;
+} asgart_b200_slice_options;
+ASGART_B200_API asgart_b200_run_result *asgart_b200_run_result_new(const asgart_b200_prepared *p, const asgart_b200_settings *settings,
+                                                                   const uint64_t *family_offsets, int64_t n_families,
+                                                                   const asgart_b200_protosd *sds);
+ASGART_B200_API int32_t asgart_b200_run_result_slice(asgart_b200_run_result *rr, const asgart_b200_slice_options *options);
+ASGART_B200_API char *asgart_b200_run_result_to_json(const asgart_b200_run_result *rr);   /* asgart_b200_free_string */
+ASGART_B200_API const char *asgart_b200_run_result_error(const asgart_b200_run_result *rr);
+ASGART_B200_API void asgart_b200_run_result_free(asgart_b200_run_result *rr);
+/* asgart_b200_run_files_passes followed by asgart_b200_run_result_slice before the JSON is written */
+ASGART_B200_API char *asgart_b200_run_files_sliced_ex(const char *files, const asgart_b200_settings *passes, int32_t n_passes,
+                                                      int32_t device, const asgart_b200_slice_options *options, const char **err);
 
 /* ---- GPU-side FASTA ingest ----------------------------------------------------------------
  * read_fasta + find_chunks_to_process of prepare_data (src/bin/asgart.rs:278-366) on the device, for the raw bytes of
