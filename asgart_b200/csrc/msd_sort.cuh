@@ -126,31 +126,91 @@ __device__ __forceinline__ void msd_load_codes(const u8* __restrict__ text, u64 
 constexpr int kH0Items = 16;
 constexpr int kH0Tile = kMsdThreads * kH0Items;
 
+// TMA (1-D bulk copy) + mbarrier helpers: one thread arms the barrier with the byte count and starts the copy; the bytes
+// land in shared memory without passing through registers and every waiting thread is released when they are all there.
+__device__ __forceinline__ void msd_mbar_init(u64* bar, u32 count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(u32(__cvta_generic_to_shared(bar))), "r"(count));
+}
+__device__ __forceinline__ void msd_bulk_load(void* smem_dst, const void* gmem_src, u32 bytes, u64* bar) {
+    const u32 b = u32(__cvta_generic_to_shared(bar));
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     u32(__cvta_generic_to_shared(smem_dst))),
+                 "l"(gmem_src), "r"(bytes), "r"(b)
+                 : "memory");
+}
+__device__ __forceinline__ void msd_mbar_wait(u64* bar, u32 parity) {
+    const u32 b = u32(__cvta_generic_to_shared(bar));
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "MSD_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra MSD_DONE_%=;\n"
+        "bra MSD_WAIT_%=;\n"
+        "MSD_DONE_%=:\n"
+        "}\n" ::"r"(b),
+        "r"(parity)
+        : "memory");
+}
+
+// Persistent blocks; the text tile of the NEXT iteration is fetched by a bulk copy (TMA) into the other half of a
+// two-stage buffer while the current one is histogrammed, so the tile's DRAM latency is off the block's critical path.
 template <typename OffT>
 __global__ void __launch_bounds__(kMsdThreads) msd_hist_text_kernel(const u8* __restrict__ text, u64 n, const uint16_t* __restrict__ code, int b,
                                                                     int msym, OffT* __restrict__ table) {
+    constexpr u32 kNeed = kH0Tile + kMsdHalo;
     __shared__ u32 h[kMsdBins];
-    __shared__ __align__(16) u8 sc[kH0Tile + kMsdHalo];
+    __shared__ __align__(128) u8 raw[2][kNeed];
+    __shared__ __align__(8) u64 bar[2];
     __shared__ u8 scode[256];
     for (u32 i = threadIdx.x; i < kMsdBins; i += kMsdThreads) h[i] = 0;
     if (threadIdx.x < 256) scode[threadIdx.x] = u8(code[threadIdx.x]);
-    const u32 wmask = (1u << (b * msym)) - 1u;
-    const u64 tiles = (n + kH0Tile - 1) / kH0Tile;
-    for (u64 tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-        __syncthreads();   // scode / h ready; previous tile's sc consumed
-        const u64 base = tile * kH0Tile;
-        msd_load_codes(text, n, base, kH0Tile + kMsdHalo, scode, sc);
-        __syncthreads();
-        const u32 q0 = threadIdx.x * kH0Items;
-        u32 w = 0;
-        for (int j = 0; j < msym - 1; ++j) w = (w << b) | sc[q0 + j];
-#pragma unroll
-        for (int j = 0; j < kH0Items; ++j) {
-            w = ((w << b) | sc[q0 + j + msym - 1]) & wmask;
-            msd_bin_slot(h, w, base + q0 + j < n);
-        }
+    const bool aligned = (reinterpret_cast<uintptr_t>(text) & 15) == 0;
+    if (threadIdx.x == 0) {
+        msd_mbar_init(&bar[0], 1);
+        msd_mbar_init(&bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    const u32 wmask = (1u << (b * msym)) - 1u;
+    const u64 tiles = (n + kH0Tile - 1) / kH0Tile;
+    // bytes of tile t that the bulk copy brings (a multiple of 16 inside the text); the rest is filled by plain loads
+    auto bulk_bytes = [&](u64 t) -> u32 {
+        const u64 base = t * kH0Tile;
+        const u64 avail = n - base;
+        return aligned ? u32((avail < u64(kNeed) ? avail : u64(kNeed)) & ~u64(15)) : 0u;
+    };
+    if (threadIdx.x == 0 && u64(blockIdx.x) < tiles) {
+        const u32 nb = bulk_bytes(blockIdx.x);
+        if (nb) msd_bulk_load(raw[0], text + u64(blockIdx.x) * kH0Tile, nb, &bar[0]);
+    }
+    u32 it = 0;
+    for (u64 tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+        const u32 buf = it & 1u;
+        const u64 base = tile * kH0Tile;
+        const u64 next = tile + gridDim.x;
+        if (threadIdx.x == 0 && next < tiles) {   // the other stage was released by the barrier that ended the last iteration
+            const u32 nb = bulk_bytes(next);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            if (nb) msd_bulk_load(raw[buf ^ 1u], text + next * kH0Tile, nb, &bar[buf ^ 1u]);
+        }
+        const u32 got = bulk_bytes(tile);
+        for (u32 i = got + threadIdx.x; i < kNeed; i += kMsdThreads) raw[buf][i] = (base + i < n) ? text[base + i] : u8(0);
+        if (got) msd_mbar_wait(&bar[buf], (it >> 1) & 1u);
+        __syncthreads();
+        const u8* rb = raw[buf];
+        const u32 q0 = threadIdx.x * kH0Items;
+        u32 w = 0;
+        for (int j = 0; j < msym - 1; ++j) w = (w << b) | (base + q0 + j < n ? u32(scode[rb[q0 + j]]) : 0u);
+#pragma unroll
+        for (int j = 0; j < kH0Items; ++j) {
+            const u32 pos = q0 + j + msym - 1;
+            w = ((w << b) | (base + pos < n ? u32(scode[rb[pos]]) : 0u)) & wmask;
+            msd_bin_slot(h, w, base + q0 + j < n);
+        }
+        __syncthreads();   // everyone is done with this stage (and, in the first iteration, h / scode were ready before use)
+    }
     for (u32 i = threadIdx.x; i < kMsdBins; i += kMsdThreads)
         if (h[i]) msd_atomic_add(&table[i], OffT(h[i]));
 }
@@ -247,12 +307,20 @@ msd_scatter_kernel(const u8* __restrict__ text, u64 n, const uint16_t* __restric
         const MsdDesc td = tiles[blockIdx.x];
         row = td.row; base = td.base; count = td.count;
     }
-    for (u32 i = tid; i < kMsdBins; i += kMsdThreads) cnt[i] = 0;
-
     u64 keys[kMsdItems];
     IdxT vals[kMsdItems];
     u32 slot[kMsdItems];
     bool ok[kMsdItems];
+    if (!FROM_TEXT) {   // the tile's loads are in flight while the counters are cleared
+#pragma unroll
+        for (int j = 0; j < kMsdItems; ++j) {
+            const u32 li = j * kMsdThreads + tid;
+            ok[j] = li < count;
+            keys[j] = ok[j] ? kin[base + li] : 0;
+            vals[j] = ok[j] ? vin[base + li] : IdxT(0);
+        }
+    }
+    for (u32 i = tid; i < kMsdBins; i += kMsdThreads) cnt[i] = 0;
     if (FROM_TEXT) {
         if (tid < 256) scode[tid] = u8(code[tid]);
         __syncthreads();
@@ -271,32 +339,31 @@ msd_scatter_kernel(const u8* __restrict__ text, u64 n, const uint16_t* __restric
             key = ((key << b) & kmask) | sc[q0 + j + p0];
         }
     } else {
-#pragma unroll
-        for (int j = 0; j < kMsdItems; ++j) {
-            const u32 li = j * kMsdThreads + tid;
-            ok[j] = li < count;
-            keys[j] = ok[j] ? kin[base + li] : 0;
-            vals[j] = ok[j] ? vin[base + li] : IdxT(0);
-        }
         __syncthreads();
     }
 #pragma unroll
     for (int j = 0; j < kMsdItems; ++j) slot[j] = msd_bin_slot(cnt, u32(keys[j] >> shift) & dmask, ok[j]);
     __syncthreads();
 
-    // this thread's 8 bins: exclusive offsets inside the tile, and the place their runs go to (one global atomic per non-empty bin)
+    // this thread's 8 bins: exclusive offsets inside the tile, and the place their runs go to (one global atomic per non-empty
+    // bin, issued before the block scan so that its round trip hides behind the scan's barriers)
     u32 placed;
     {
         u32 c[kMsdItems], sum = 0;
-#pragma unroll
-        for (int j = 0; j < kMsdItems; ++j) { c[j] = cnt[tid * kMsdItems + j]; sum += c[j]; }
-        u32 run = block_exclusive_scan(sum, SumOp(), placed, wsm);
+        OffT gbase[kMsdItems];
         OffT* trow = table + u64(row) * kMsdBins;
+#pragma unroll
+        for (int j = 0; j < kMsdItems; ++j) {
+            c[j] = cnt[tid * kMsdItems + j];
+            sum += c[j];
+            gbase[j] = c[j] ? msd_atomic_add(&trow[tid * kMsdItems + j], OffT(c[j])) : OffT(0);
+        }
+        u32 run = block_exclusive_scan(sum, SumOp(), placed, wsm);
 #pragma unroll
         for (int j = 0; j < kMsdItems; ++j) {
             const u32 bin = tid * kMsdItems + j;
             cnt[bin] = run;
-            if (c[j]) delta[bin] = msd_atomic_add(&trow[bin], OffT(c[j])) - OffT(run);
+            if (c[j]) delta[bin] = gbase[j] - OffT(run);
             run += c[j];
         }
     }
