@@ -158,7 +158,9 @@ __device__ __forceinline__ void msd_mbar_wait(u64* bar, u32 parity) {
 // two-stage buffer while the current one is histogrammed, so the tile's DRAM latency is off the block's critical path.
 template <typename OffT>
 __global__ void __launch_bounds__(kMsdThreads) msd_hist_text_kernel(const u8* __restrict__ text, u64 n, const uint16_t* __restrict__ code, int b,
-                                                                    int msym, OffT* __restrict__ table) {
+                                                                    int msym, OffT* __restrict__ table, u64 tile_begin, u64 tile_end) {
+    // positions of the tiles [tile_begin, tile_end) are counted (a sharded build splits the text between the members);
+    // the symbols a position looks ahead to are read wherever they lie
     constexpr u32 kNeed = kH0Tile + kMsdHalo;
     __shared__ u32 h[kMsdBins];
     __shared__ __align__(128) u8 raw[2][kNeed];
@@ -174,19 +176,19 @@ __global__ void __launch_bounds__(kMsdThreads) msd_hist_text_kernel(const u8* __
     }
     __syncthreads();
     const u32 wmask = (1u << (b * msym)) - 1u;
-    const u64 tiles = (n + kH0Tile - 1) / kH0Tile;
+    const u64 tiles = min((n + kH0Tile - 1) / kH0Tile, tile_end);
     // bytes of tile t that the bulk copy brings (a multiple of 16 inside the text); the rest is filled by plain loads
     auto bulk_bytes = [&](u64 t) -> u32 {
         const u64 base = t * kH0Tile;
         const u64 avail = n - base;
         return aligned ? u32((avail < u64(kNeed) ? avail : u64(kNeed)) & ~u64(15)) : 0u;
     };
-    if (threadIdx.x == 0 && u64(blockIdx.x) < tiles) {
-        const u32 nb = bulk_bytes(blockIdx.x);
-        if (nb) msd_bulk_load(raw[0], text + u64(blockIdx.x) * kH0Tile, nb, &bar[0]);
+    if (threadIdx.x == 0 && tile_begin + blockIdx.x < tiles) {
+        const u32 nb = bulk_bytes(tile_begin + blockIdx.x);
+        if (nb) msd_bulk_load(raw[0], text + (tile_begin + blockIdx.x) * kH0Tile, nb, &bar[0]);
     }
     u32 it = 0;
-    for (u64 tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+    for (u64 tile = tile_begin + blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
         const u32 buf = it & 1u;
         const u64 base = tile * kH0Tile;
         const u64 next = tile + gridDim.x;
@@ -889,7 +891,7 @@ bool msd_sort_suffixes(const u8* d_text, u64 n, const uint16_t* d_code, int b, i
             if (st && st->hist) st->hist->begin();
             if (lv == 0) {
                 const int blocks = int(std::min<u64>(ceil_div(n, u64(kH0Tile)), u64(kNumSMs) * 2));
-                msd_hist_text_kernel<OffT><<<blocks, kMsdThreads, 0, stream>>>(d_text, n, d_code, b, L.width[0] / b, tp);
+                msd_hist_text_kernel<OffT><<<blocks, kMsdThreads, 0, stream>>>(d_text, n, d_code, b, L.width[0] / b, tp, 0, ~u64(0));
             } else {
                 msd_hist_kernel<OffT><<<unsigned(tiles_ub), kMsdThreads, 0, stream>>>(src_k, tile_desc.p, n_tiles, shift, dmask, tp);
             }

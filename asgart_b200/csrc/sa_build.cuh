@@ -394,15 +394,16 @@ __device__ __forceinline__ u64 last_le(const IdxT* __restrict__ arr, u64 len, u6
     return lo;
 }
 
+// one thread per slot of the large-group buffer (not per list entry: large groups are rare, the list is not — a pass
+// over all 281 M entries of round 1 at 3.1 Gbp cost 6.3 ms to move a handful of groups)
 template <typename IdxT>
-__global__ void large_copy_out_kernel(const IdxT* __restrict__ hs, const IdxT* __restrict__ large_sz, const IdxT* __restrict__ loff,
-                                      u64 n_groups, u64 U, const IdxT* __restrict__ K2,
-                                      const IdxT* __restrict__ I, int kb, typename CompKey<IdxT>::type* __restrict__ Lk, IdxT* __restrict__ Li) {
-    const u64 c = u64(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (c >= U) return;
-    const u64 j = last_le(hs, n_groups, c);
-    if (large_sz[j] == 0) return;
-    const u64 q = u64(loff[j]) + (c - u64(hs[j]));
+__global__ void large_copy_out_kernel(const IdxT* __restrict__ hs, const IdxT* __restrict__ loff, u64 n_groups, u64 UL,
+                                      const IdxT* __restrict__ K2, const IdxT* __restrict__ I, int kb,
+                                      typename CompKey<IdxT>::type* __restrict__ Lk, IdxT* __restrict__ Li) {
+    const u64 q = u64(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (q >= UL) return;
+    const u64 j = last_le(loff, n_groups, q);  // the large group that owns slot q (last index of the plateau)
+    const u64 c = u64(hs[j]) + (q - u64(loff[j]));
     // keyed on the group's ordinal in the list, not its head index: the list is grouped but not globally ordered by head
     // (ordinary groups first, then the run groups), and the sorted elements are copied back in list order
     Lk[q] = CompKey<IdxT>::make(IdxT(j), K2[c], kb);
@@ -537,15 +538,25 @@ void build_suffix_array(const u8* d_text, u64 n, IdxT* d_sa, const RankView<IdxT
         if (b * psym != kMsdDigitBits) use_msd = false;   // the members' ranges must be ranges of level-0 bins
         std::vector<unsigned long long> h_ph(nb);
         if (use_msd) {
+            // every member counts the level-0 bins of 1/world of the text; the sums go round as host values
             msd_table0.alloc(kMsdBins, stream);
             msd_table0.zero();
-            const int blocks = int(std::min<u64>(ceil_div(n, u64(kH0Tile)), u64(kNumSMs) * 2));
-            msd_hist_text_kernel<IdxT><<<blocks, kMsdThreads, 0, stream>>>(d_text, n, d_code.p, b, psym, msd_table0.p);
-            KERNEL_CHECK();
-            count_launch();
+            const u64 tiles = ceil_div(n, u64(kH0Tile));
+            const u64 t0 = tiles * u64(grp->rank) / u64(world), t1 = tiles * u64(grp->rank + 1) / u64(world);
+            if (t1 > t0) {
+                const int blocks = int(std::min<u64>(t1 - t0, u64(kNumSMs) * 2));
+                msd_hist_text_kernel<IdxT><<<blocks, kMsdThreads, 0, stream>>>(d_text, n, d_code.p, b, psym, msd_table0.p, t0, t1);
+                KERNEL_CHECK();
+                count_launch();
+            }
             std::vector<IdxT> h_t(nb);
             sync_read(h_t.data(), msd_table0.p, nb * sizeof(IdxT));
-            for (u32 i = 0; i < nb; ++i) h_ph[i] = (unsigned long long)h_t[i];
+            std::vector<u64> sums(nb);
+            for (u32 i = 0; i < nb; ++i) sums[i] = u64(h_t[i]);
+            grp->allreduce_sum_host(sums.data(), int(nb));
+            for (u32 i = 0; i < nb; ++i) { h_ph[i] = (unsigned long long)sums[i]; h_t[i] = IdxT(sums[i]); }
+            CUDA_CHECK(cudaMemcpyAsync(msd_table0.p, h_t.data(), nb * sizeof(IdxT), cudaMemcpyHostToDevice, stream));
+            CUDA_CHECK(cudaStreamSynchronize(stream));   // h_t leaves scope
         } else {
             DevBuf<unsigned long long> d_ph(nb, stream);
             d_ph.zero();
@@ -844,8 +855,7 @@ void build_suffix_array(const u8* d_text, u64 n, IdxT* d_sa, const RankView<IdxT
         if (UL > 0) {
             DevBuf<KeyT> LA(UL, stream), LB(UL, stream);
             DevBuf<IdxT> LIA(UL, stream), LIB(UL, stream);
-            large_copy_out_kernel<IdxT><<<unsigned(ceil_div(U, 256)), 256, 0, stream>>>(HSw.p, large_sz.p, loff.p, NG, U, K2.p, Iw.p, kb, LA.p,
-                                                                                        LIA.p);
+            large_copy_out_kernel<IdxT><<<unsigned(ceil_div(UL, 256)), 256, 0, stream>>>(HSw.p, loff.p, NG, UL, K2.p, Iw.p, kb, LA.p, LIA.p);
             KERNEL_CHECK();
             const int jb = std::max(1, bit_width_u64(NG - 1));  // group ordinal in [0, NG)
             std::vector<int> shifts;
