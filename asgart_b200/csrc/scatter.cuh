@@ -119,21 +119,23 @@ __global__ void __launch_bounds__(kPtThreads) pt_hist_kernel(const u32* __restri
     if (threadIdx.x < 256) hist[pt_row(blockIdx.x, threadIdx.x, rt)] = h[threadIdx.x];
 }
 
-__global__ void __launch_bounds__(kPtThreads) pt_scatter_kernel(const u32* __restrict__ idx, const u32* __restrict__ val, u64 n, int shift,
-                                                               const u32* __restrict__ offs, u64 rt, u32* __restrict__ oidx,
-                                                               u32* __restrict__ oval) {
+// Three blocks per SM (42 registers): the kernel is a chain of short phases between barriers and runs at the speed at
+// which other blocks fill the waits (profiles/r2_launches_c4_v1.summary.txt: 18 ms per pass over 3.09 G pairs at two).
+__global__ void __launch_bounds__(kPtThreads, 3) pt_scatter_kernel(const u32* __restrict__ idx, const u32* __restrict__ val, u64 n, int shift,
+                                                                  const u32* __restrict__ offs, u64 rt, u32* __restrict__ oidx,
+                                                                  u32* __restrict__ oval) {
     __shared__ u32 cnt_d[256], tile_off[256], delta[256];
     __shared__ __align__(16) u32 si[kPtTile], sv[kPtTile];
     const u32 tid = threadIdx.x, lane = tid & 31u;
     const u64 base = u64(blockIdx.x) * kPtTile;
     const u32 cnt = u32(min(u64(kPtTile), n - base));
-    if (tid < 256) cnt_d[tid] = 0;
-    u32 k[kPtItems], v[kPtItems], slot[kPtItems];
+    u32 k[kPtItems], slot[kPtItems];
 #pragma unroll
-    for (int j = 0; j < kPtItems; ++j) {
+    for (int j = 0; j < kPtItems; ++j) {   // the tile's loads are in flight while the counters are cleared
         const u32 li = j * kPtThreads + tid;
-        if (li < cnt) { k[j] = idx[base + li]; v[j] = val[base + li]; }
+        k[j] = li < cnt ? idx[base + li] : 0u;
     }
+    if (tid < 256) cnt_d[tid] = 0;
     __syncthreads();
 #pragma unroll
     for (int j = 0; j < kPtItems; ++j) {
@@ -164,7 +166,7 @@ __global__ void __launch_bounds__(kPtThreads) pt_scatter_kernel(const u32* __res
         if (li < cnt) {
             const u32 lp = tile_off[(k[j] >> shift) & 255u] + slot[j];
             si[lp] = k[j];
-            sv[lp] = v[j];
+            sv[lp] = val[base + li];   // read here, not kept through the ranking: registers for a third block
         }
     }
     __syncthreads();
