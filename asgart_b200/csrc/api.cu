@@ -195,7 +195,14 @@ struct LutHook : SaKeyHook {
     asgart_b200_ctx* ctx;
     bool done = false;
     double ms = 0;
+    u64 m4 = 0, m5 = 0;
     explicit LutHook(asgart_b200_ctx* c) : ctx(c) {}
+    bool lookup_tables(SaLookupTables& t) override {
+        if (!done) return false;
+        auto& ix = IxOf<IdxT>::get(ctx);
+        t.deep = ix.deep.p; t.depth = ix.deep_depth; t.lut_lo = ix.lut_lo.p; t.lut_hi = ix.lut_hi.p; t.m4 = m4; t.m5 = m5;
+        return ix.deep.p != nullptr;
+    }
     void on_sorted_keys(const u64* d_keys, u64 n_local, u64 base, u64 n, int b, int p0, const uint16_t* h_code, cudaStream_t stream,
                         SaGroup* grp) override {
         if (p0 < 8 || n != ctx->n1) return;
@@ -208,6 +215,7 @@ struct LutHook : SaKeyHook {
         const char* s4 = "ACGT";
         for (int d = 0; d < 5; ++d) if (h_code[u8(s5[d])] && h_code[u8(s5[d])] < 16) map.d5[h_code[u8(s5[d])]] = u8(d);
         for (int d = 0; d < 4; ++d) if (h_code[u8(s4[d])] && h_code[u8(s4[d])] < 16) map.d4[h_code[u8(s4[d])]] = u8(d);
+        m4 = map.nibbles(map.d4); m5 = map.nibbles(map.d5);
         // depth: buckets of a few suffixes (4^depth <= n), at most 15 symbols (4 GiB of u32 starts: buckets of ~3 suffixes
         // for a 3.1 Gbp strand, which one round of parallel loads compares, instead of a bisection), inside the initial key
         static const int depth_cap = std::min(15, getenv("ASGART_B200_DEEP_MAX") ? atoi(getenv("ASGART_B200_DEEP_MAX")) : 15);

@@ -32,6 +32,7 @@
 #include "sa_group.h"
 #include "scan.cuh"
 #include "scatter.cuh"
+#include "search.cuh"
 
 namespace ab200 {
 
@@ -233,7 +234,9 @@ __global__ void __launch_bounds__(kHpThreads) hp_emit_kernel(const u64* __restri
         if ((t.head >> j) & 1u) head1 = t.i0 + j + 1;
         hd[j] = b0 + IdxT(head1 - 1);
     }
-    if (t.valid == (1u << kHpItems) - 1u) {
+    if (rpos == nullptr) {
+        // lazy ranks: no rank-by-sorted-position array is written
+    } else if (t.valid == (1u << kHpItems) - 1u) {
         if constexpr (sizeof(IdxT) == 4) {
             uint4* o = reinterpret_cast<uint4*>(rpos + t.i0);
             o[0] = make_uint4(u32(hd[0]), u32(hd[1]), u32(hd[2]), u32(hd[3]));
@@ -355,13 +358,65 @@ template <> struct CompKey<u64> {
 constexpr int kSmallGroup = 32;  // groups up to this size are sorted in place by one thread; larger ones go through radix passes
 
 // key2 = rank of the suffix D symbols further on (+1; 0 = past the end): the random gather of prefix doubling
+// ---- lazy ranks (single-device build) ---------------------------------------------------------------------------
+// rank[j] = sorted position of the head of j's group. Right after the initial sort that is lower_bound(sorted keys,
+// key(j)) for EVERY position j, and only 9 % of the suffixes (the unsorted ones) ever ask for a rank — of positions further
+// on in the text. So the inverse permutation rank[SA[i]] = head(i) is never materialised (3.09 G pairs through two
+// partition passes and a bucket scatter: 55 ms at 3.1 Gbp): rank[] starts as all-ones = "still the initial head", the
+// re-ranking stores explicit values for suffixes that leave the first sub-group of their group (a first sub-group keeps its
+// head, so the sentinel stays true), and a gather that meets the sentinel computes the initial head from the text: key of
+// the suffix -> bucket of its first `depth` symbols in the deep table (~3 sorted keys) -> position of its key among them.
 template <typename IdxT>
+struct RankLookup {
+    const u64* keys = nullptr;   // sorted initial keys (all n of them)
+    const u8* text = nullptr;
+    const uint16_t* code = nullptr;
+    u64 n = 0;
+    int b = 0, p0 = 0, depth = 0;
+    const IdxT* deep = nullptr;
+    const IdxT* lut_lo = nullptr;
+    const IdxT* lut_hi = nullptr;
+    u64 m4 = 0, m5 = 0;
+};
+
+template <typename IdxT>
+__device__ __forceinline__ IdxT initial_rank(const RankLookup<IdxT>& L, u64 j) {
+    u64 key = 0;
+    for (int t = 0; t < L.p0; ++t) {
+        const u64 p = j + u64(t);
+        key = (key << L.b) | (p < L.n ? u64(__ldg(&L.code[L.text[p]])) : 0);
+    }
+    u64 lo = 0, hi = L.n;
+    u32 slot = 0;
+    if (L.depth > 0 && key_slot4(key, L.b, L.p0, L.depth, L.m4, slot)) { lo = u64(L.deep[slot]); hi = u64(L.deep[slot + 1]); }
+    else if (L.p0 >= 8 && key_slot5(key, L.b, L.p0, L.m5, slot)) { lo = u64(L.lut_lo[slot]); hi = u64(L.lut_hi[slot]); }
+    while (hi - lo > 4) {   // first entry >= key (the suffix's own key is in there)
+        const u64 mid = (lo + hi) >> 1;
+        if (L.keys[mid] < key) lo = mid + 1; else hi = mid;
+    }
+    while (lo < hi && L.keys[lo] < key) ++lo;
+    return IdxT(lo);
+}
+
+template <typename IdxT, bool LAZY>
 __global__ void gather_rank_kernel(const IdxT* __restrict__ I, const IdxT* __restrict__ D, const RankView<IdxT> rank, u64 U, u64 n,
-                                   IdxT* __restrict__ K2) {
+                                   IdxT* __restrict__ K2, const RankLookup<IdxT> L) {
     const u64 stride = u64(gridDim.x) * blockDim.x;
     for (u64 c = u64(blockIdx.x) * blockDim.x + threadIdx.x; c < U; c += stride) {
         const u64 p = u64(I[c]) + u64(D[c]);
-        K2[c] = p < n ? IdxT(*rank.ptr(p) + 1) : IdxT(0);
+        IdxT v = IdxT(0);
+        if (p < n) {
+            IdxT* rp = rank.ptr(p);
+            v = *rp;
+            // never re-ranked: still the head its initial key gives. Written back: positions inside long repeats are asked for
+            // again in later rounds (i + D for several (i, D)); measured at 3.1 Gbp: 45 ms of gathers with the store, 55 without
+            if (LAZY && v == ~IdxT(0)) {
+                v = initial_rank<IdxT>(L, p);
+                *rp = v;
+            }
+            v = IdxT(v + 1);
+        }
+        K2[c] = v;
     }
 }
 
@@ -445,9 +500,19 @@ __global__ void run_key_kernel(const u8* __restrict__ text, const uint16_t* __re
 // Sharded build: d_keys holds this member's n_local keys, which are positions [base, base + n_local) of the n_total sorted
 // keys; ranges are cut where the first >= 4 symbols change (or the first symbol, for alphabets over 16 symbols), so a
 // bucket of 4 or more symbols never spans two members. Every member calls the hook at the same point (collectives allowed).
+// Tables the hook may have built from the sorted keys (device pointers of the build's index type): the deep table (start
+// of every ACGT `depth`-mer's bucket, closed by one more entry) and the 8-mer LUT, plus the nibble maps dense code -> digit.
+struct SaLookupTables {
+    const void* deep = nullptr;
+    int depth = 0;
+    const void* lut_lo = nullptr;
+    const void* lut_hi = nullptr;
+    u64 m4 = 0, m5 = 0;
+};
 struct SaKeyHook {
     virtual void on_sorted_keys(const u64* d_keys, u64 n_local, u64 base, u64 n_total, int b, int p0, const uint16_t* h_code,
                                 cudaStream_t stream, SaGroup* grp) = 0;
+    virtual bool lookup_tables(SaLookupTables&) { return false; }
     virtual ~SaKeyHook() = default;
 };
 
@@ -584,12 +649,16 @@ void build_suffix_array(const u8* d_text, u64 n, IdxT* d_sa, const RankView<IdxT
     phase("alphabet+ranges", n_loc);
     nv.next("sa_build/init keys");
 
+    // the sorted initial keys outlive the first phase when ranks are looked up lazily (single-device build with lookup tables)
+    DevBuf<u64> keysA, keysB;
+    RankLookup<IdxT> rl;
+    bool lazy = false;
     {
         std::vector<int> shifts;
         for (int s = 0; s < b * p0; s += 8) shifts.push_back(s);
         // the sorted suffix indices must end up in d_sa itself: with an even number of passes they start there
         // (sharded: the piece d_sa + base is not 16-byte aligned, the sort runs in its own buffers and is copied over)
-        DevBuf<u64> keysA(n_loc + 2, stream), keysB(n_loc + 2, stream);   // + 2: reused as pair buffers by the inverse scatter
+        keysA.alloc(n_loc + 4, stream); keysB.alloc(n_loc + 4, stream);   // + 4: reused as pair buffers by the inverse scatter
         DevBuf<IdxT> valsT(n_loc, stream), valsU(grp ? n_loc : 0, stream);
         u64 *k = keysA.p, *ka = keysB.p;
         IdxT *v, *va;
@@ -637,6 +706,17 @@ void build_suffix_array(const u8* d_text, u64 n, IdxT* d_sa, const RankView<IdxT
 
         if (hook) hook->on_sorted_keys(k, n_loc, base, n, b, p0, h_code, stream, grp);
         phase("lookup tables");
+        {
+            static const bool lazy_off = getenv("ASGART_B200_LAZY_RANK") && getenv("ASGART_B200_LAZY_RANK")[0] == '0';   // developer knob
+            SaLookupTables lt;
+            if (!grp && !lazy_off && hook && hook->lookup_tables(lt) && lt.depth > 0 && p0 >= 8) {
+                lazy = true;
+                rl.keys = k; rl.text = d_text; rl.code = d_code.p; rl.n = n; rl.b = b; rl.p0 = p0; rl.depth = lt.depth;
+                rl.deep = static_cast<const IdxT*>(lt.deep);
+                rl.lut_lo = static_cast<const IdxT*>(lt.lut_lo); rl.lut_hi = static_cast<const IdxT*>(lt.lut_hi);
+                rl.m4 = lt.m4; rl.m5 = lt.m5;
+            }
+        }
         nv.next("sa_build/heads+rank scatter");
         const u64* kk = k;
         const IdxT* vv = sa_loc;
@@ -659,7 +739,7 @@ void build_suffix_array(const u8* d_text, u64 n, IdxT* d_sa, const RankView<IdxT
         GA.alloc(UA, stream); IA.alloc(UA, stream); HSA.alloc(NGA, stream);
         GS.alloc(US, stream); IS.alloc(US, stream);
         // rank by sorted position goes to the dead half of the value ping-pong, then to text order by the sliced scatter
-        IdxT* rpos = va;
+        IdxT* rpos = lazy ? nullptr : va;
         if (n_loc) {
             hp_emit_kernel<IdxT><<<unsigned(hp_tiles), kHpThreads, 0, stream>>>(kk, vv, n_loc, rep_unit, sym_mask, hp_pre.p, IdxT(base), rpos,
                                                                                 GA.p, IA.p, HSA.p, GS.p, IS.p);
@@ -695,7 +775,8 @@ void build_suffix_array(const u8* d_text, u64 n, IdxT* d_sa, const RankView<IdxT
             }
         }
         // the sorted keys are dead from here on: both key buffers serve as scratch of the sort-back scatter
-        if (!grp) inverse_scatter<IdxT>(d_sa, rpos, n, d_rank.base[0], n, stream, k, ka);
+        if (lazy) CUDA_CHECK(cudaMemsetAsync(d_rank.base[0], 0xFF, n * sizeof(IdxT), stream));   // all-ones: "the initial head"
+        else if (!grp) inverse_scatter<IdxT>(d_sa, rpos, n, d_rank.base[0], n, stream, k, ka);
         else if (!sharded_inverse_scatter<IdxT>(sa_loc, rpos, n_loc, n, d_rank, grp, stream) && n_loc) {
             const unsigned grid = unsigned(std::min<u64>(ceil_div(n_loc, 256), u64(kNumSMs) * 16));
             scatter_view_kernel<IdxT><<<grid, 256, 0, stream>>>(sa_loc, rpos, n_loc, d_rank);
@@ -704,6 +785,9 @@ void build_suffix_array(const u8* d_text, u64 n, IdxT* d_sa, const RankView<IdxT
         }
         if (st && st->rank) st->rank->end(4, 0);
         phase("heads+rank scatter", UA + US);
+        // the unsorted half of the key ping-pong goes now; the sorted keys stay while ranks are looked up in them
+        if (k == keysA.p) keysB.release(); else keysA.release();
+        if (!lazy) { keysA.release(); keysB.release(); }
     }
     nv.next("sa_build/run round");
 
@@ -832,7 +916,8 @@ void build_suffix_array(const u8* d_text, u64 n, IdxT* d_sa, const RankView<IdxT
         {
             if (st && st->gather) st->gather->begin();
             int blocks = int(std::min<u64>(ceil_div(U, 256), u64(kNumSMs) * 16));
-            gather_rank_kernel<IdxT><<<blocks, 256, 0, stream>>>(Iw.p, Dw.p, d_rank, U, n, K2.p);
+            if (lazy) gather_rank_kernel<IdxT, true><<<blocks, 256, 0, stream>>>(Iw.p, Dw.p, d_rank, U, n, K2.p, rl);
+            else gather_rank_kernel<IdxT, false><<<blocks, 256, 0, stream>>>(Iw.p, Dw.p, d_rank, U, n, K2.p, rl);
             KERNEL_CHECK();
             count_launch();
             if (st && st->gather) st->gather->end(1, U * 3 * sizeof(IdxT));
@@ -913,6 +998,7 @@ void build_suffix_array(const u8* d_text, u64 n, IdxT* d_sa, const RankView<IdxT
         U = U2; NG = NG2;
         H <<= 1;
     }
+    keysA.release(); keysB.release();
     phase("doubling rounds", st ? st->rounds : 0);
     nv.next("sa_build/share SA pieces");
     if (grp) grp->share_pieces(d_sa, piece_off.data(), int(sizeof(IdxT)), stream);
