@@ -368,7 +368,9 @@ constexpr int kSmallGroup = 32;  // groups up to this size are sorted in place b
 // the suffix -> bucket of its first `depth` symbols in the deep table (~3 sorted keys) -> position of its key among them.
 template <typename IdxT>
 struct RankLookup {
-    const u64* keys = nullptr;   // sorted initial keys (all n of them)
+    const u64* keys[kMaxWorld] = {};   // sorted initial keys: member r holds sorted positions [piece[r], piece[r + 1])
+    u64 piece[kMaxWorld + 1] = {};
+    u32 world = 1;
     const u8* text = nullptr;
     const uint16_t* code = nullptr;
     u64 n = 0;
@@ -377,6 +379,11 @@ struct RankLookup {
     const IdxT* lut_lo = nullptr;
     const IdxT* lut_hi = nullptr;
     u64 m4 = 0, m5 = 0;
+    __device__ __forceinline__ u32 owner(u64 p) const {
+        u32 r = 0;
+        while (r + 1 < world && p >= piece[r + 1]) ++r;
+        return r;
+    }
 };
 
 template <typename IdxT>
@@ -388,13 +395,25 @@ __device__ __forceinline__ IdxT initial_rank(const RankLookup<IdxT>& L, u64 j) {
     }
     u64 lo = 0, hi = L.n;
     u32 slot = 0;
-    if (L.depth > 0 && key_slot4(key, L.b, L.p0, L.depth, L.m4, slot)) { lo = u64(L.deep[slot]); hi = u64(L.deep[slot + 1]); }
-    else if (L.p0 >= 8 && key_slot5(key, L.b, L.p0, L.m5, slot)) { lo = u64(L.lut_lo[slot]); hi = u64(L.lut_hi[slot]); }
-    while (hi - lo > 4) {   // first entry >= key (the suffix's own key is in there)
-        const u64 mid = (lo + hi) >> 1;
-        if (L.keys[mid] < key) lo = mid + 1; else hi = mid;
+    bool one_owner = L.world == 1;
+    if (L.depth > 0 && key_slot4(key, L.b, L.p0, L.depth, L.m4, slot)) { lo = u64(L.deep[slot]); hi = u64(L.deep[slot + 1]); one_owner = true; }
+    else if (L.p0 >= 8 && key_slot5(key, L.b, L.p0, L.m5, slot)) { lo = u64(L.lut_lo[slot]); hi = u64(L.lut_hi[slot]); one_owner = true; }
+    if (one_owner) {
+        // a bucket of >= 4 leading symbols lies inside one member's piece (the pieces are cut where the first four symbols change)
+        const u32 r = L.owner(lo);
+        const u64* __restrict__ kk = L.keys[r] - L.piece[r];
+        while (hi - lo > 4) {   // first entry >= key (the suffix's own key is in there)
+            const u64 mid = (lo + hi) >> 1;
+            if (kk[mid] < key) lo = mid + 1; else hi = mid;
+        }
+        while (lo < hi && kk[lo] < key) ++lo;
+    } else {
+        while (lo < hi) {       // the few suffixes that reach past the end of the text: the whole array, whoever holds it
+            const u64 mid = (lo + hi) >> 1;
+            const u32 r = L.owner(mid);
+            if (L.keys[r][mid - L.piece[r]] < key) lo = mid + 1; else hi = mid;
+        }
     }
-    while (lo < hi && L.keys[lo] < key) ++lo;
     return IdxT(lo);
 }
 
@@ -709,9 +728,21 @@ void build_suffix_array(const u8* d_text, u64 n, IdxT* d_sa, const RankView<IdxT
         {
             static const bool lazy_off = getenv("ASGART_B200_LAZY_RANK") && getenv("ASGART_B200_LAZY_RANK")[0] == '0';   // developer knob
             SaLookupTables lt;
-            if (!grp && !lazy_off && hook && hook->lookup_tables(lt) && lt.depth > 0 && p0 >= 8) {
+            // (every member of a group takes the same decision: it depends on n, the alphabet and the key length only)
+            if (!lazy_off && hook && hook->lookup_tables(lt) && lt.depth > 0 && p0 >= 8 && (!grp || b * std::min(p0, 4) >= 8)) {
                 lazy = true;
-                rl.keys = k; rl.text = d_text; rl.code = d_code.p; rl.n = n; rl.b = b; rl.p0 = p0; rl.depth = lt.depth;
+                rl.world = u32(world);
+                if (grp) {
+                    // the members read each other's sorted keys through peer pointers (k is the start of its block)
+                    void* all[kMaxWorld] = {};
+                    CUDA_CHECK(cudaStreamSynchronize(stream));
+                    grp->exchange_ptr(k, (n_loc + 4) * sizeof(u64), all);
+                    for (int r = 0; r < world; ++r) { rl.keys[r] = static_cast<const u64*>(all[r]); rl.piece[r] = piece_off[r]; }
+                    rl.piece[world] = piece_off[world];
+                } else {
+                    rl.keys[0] = k; rl.piece[0] = 0; rl.piece[1] = n;
+                }
+                rl.text = d_text; rl.code = d_code.p; rl.n = n; rl.b = b; rl.p0 = p0; rl.depth = lt.depth;
                 rl.deep = static_cast<const IdxT*>(lt.deep);
                 rl.lut_lo = static_cast<const IdxT*>(lt.lut_lo); rl.lut_hi = static_cast<const IdxT*>(lt.lut_hi);
                 rl.m4 = lt.m4; rl.m5 = lt.m5;
@@ -775,7 +806,14 @@ void build_suffix_array(const u8* d_text, u64 n, IdxT* d_sa, const RankView<IdxT
             }
         }
         // the sorted keys are dead from here on: both key buffers serve as scratch of the sort-back scatter
-        if (lazy) CUDA_CHECK(cudaMemsetAsync(d_rank.base[0], 0xFF, n * sizeof(IdxT), stream));   // all-ones: "the initial head"
+        if (lazy) {   // all-ones: "the initial head"
+            if (!grp) CUDA_CHECK(cudaMemsetAsync(d_rank.base[0], 0xFF, n * sizeof(IdxT), stream));
+            else {
+                CUDA_CHECK(cudaMemsetAsync(d_rank.base[grp->rank], 0xFF, d_rank.slice_len() * sizeof(IdxT), stream));
+                CUDA_CHECK(cudaStreamSynchronize(stream));
+                grp->barrier();   // nobody stores a refined rank into a slice that is still being cleared
+            }
+        }
         else if (!grp) inverse_scatter<IdxT>(d_sa, rpos, n, d_rank.base[0], n, stream, k, ka);
         else if (!sharded_inverse_scatter<IdxT>(sa_loc, rpos, n_loc, n, d_rank, grp, stream) && n_loc) {
             const unsigned grid = unsigned(std::min<u64>(ceil_div(n_loc, 256), u64(kNumSMs) * 16));
@@ -998,6 +1036,7 @@ void build_suffix_array(const u8* d_text, u64 n, IdxT* d_sa, const RankView<IdxT
         U = U2; NG = NG2;
         H <<= 1;
     }
+    if (grp && lazy) { CUDA_CHECK(cudaStreamSynchronize(stream)); grp->barrier(); }   // the peers are done reading these keys
     keysA.release(); keysB.release();
     phase("doubling rounds", st ? st->rounds : 0);
     nv.next("sa_build/share SA pieces");
