@@ -164,6 +164,33 @@ void ingest_piece(asgart_b200_ctx* ctx, const u8* d_file, u64 n, bool skip_maske
     ctx->st.ingest_records += piece.rec_off.size();
 }
 
+// Record ids (header up to the first white space) straight from the file bytes, after the bio reader's end-of-records rule
+// (fasta_core.h). fetch(at, buf, cap) -> number of bytes copied from file offset `at` (0 at the end of the file).
+template <class Fetch>
+void ingest_record_ids(IngestPiece& piece, u64 n, Fetch fetch) {
+    auto header = [&](u64 off, bool whole_line, std::string* id) {   // whole_line: is the header blank; else: collect the id
+        char buf[256];
+        for (u64 at = off + 1; at < n;) {
+            const size_t r = fetch(at, buf, sizeof buf);
+            if (!r) break;
+            for (size_t i = 0; i < r; ++i) {
+                const u8 c = u8(buf[i]);
+                if (c == '\n') return true;
+                if (!fa_space(c)) { if (whole_line) return false; id->push_back(char(c)); }
+                else if (!whole_line) return true;
+            }
+            at += r;
+        }
+        return true;
+    };
+    stop_at_empty_record(piece.rec_off, piece.rec_pos, piece.kept, [&](size_t r) { return header(piece.rec_off[r], true, nullptr); });
+    for (u64 off : piece.rec_off) {
+        std::string id;
+        header(off, false, &id);
+        piece.names.push_back(std::move(id));
+    }
+}
+
 template <typename IdxT> struct IxOf;
 template <> struct IxOf<u32> { static Index32& get(asgart_b200_ctx* c) { return c->ix32; } };
 template <> struct IxOf<u64> { static Index64& get(asgart_b200_ctx* c) { return c->ix64; } };
@@ -1004,9 +1031,7 @@ int32_t asgart_b200_ctx_ingest_fasta(asgart_b200_ctx* ctx, const uint8_t* bytes,
         if (!ctx->ingesting) return fail(ctx, ASGART_B200_ESTATE, "ingest_fasta before ingest_begin");
         if ((!bytes && n_bytes > 0) || n_bytes < 0) return fail(ctx, ASGART_B200_EINVAL, "null bytes or negative size");
         const u64 n = u64(n_bytes);
-        u64 h = 0;
-        while (h < n && bytes[h] == '\n') ++h;
-        if (h < n && bytes[h] != '>') return fail(ctx, ASGART_B200_EINVAL, "Unable to parse FASTA: the first non-empty line is not a header");
+        if (!first_byte_ok(n, n ? bytes[0] : 0)) return fail(ctx, ASGART_B200_EINVAL, "Unable to parse FASTA: expected > at record start");
         DevBuf<u8> d_file(n, ctx->stream);
         EventTimer th(ctx->stream);
         th.start();
@@ -1015,11 +1040,11 @@ int32_t asgart_b200_ctx_ingest_fasta(asgart_b200_ctx* ctx, const uint8_t* bytes,
         ctx->pieces.emplace_back();
         IngestPiece& piece = ctx->pieces.back();
         ingest_piece(ctx, d_file.p, n, skip_masked != 0, piece);
-        for (u64 off : piece.rec_off) {
-            u64 e = off + 1;
-            while (e < n && !fa_space(bytes[e])) ++e;
-            piece.names.emplace_back(reinterpret_cast<const char*>(bytes) + off + 1, size_t(e - off - 1));
-        }
+        ingest_record_ids(piece, n, [&](u64 at, char* buf, size_t cap) {
+            const size_t r = size_t(std::min<u64>(cap, n - at));
+            memcpy(buf, bytes + at, r);
+            return r;
+        });
         ctx->st.ms_h2d += th.ms();
         ctx->st.h2d_bytes += n;
         return ASGART_B200_OK;
@@ -1045,7 +1070,7 @@ int32_t asgart_b200_ctx_ingest_file(asgart_b200_ctx* ctx, const char* path, int3
         DevBuf<u8> d_file(n, ctx->stream);
         EventTimer th(ctx->stream);
         th.start();
-        bool seen_first = false, bad_first = false;
+        bool bad_first = false;
         u64 done = 0;
         for (int slot = 0; done < n; slot ^= 1) {
             CUDA_CHECK(cudaEventSynchronize(ctx->stage_ev[slot]));   // the copy that last used this buffer has finished
@@ -1074,9 +1099,7 @@ int32_t asgart_b200_ctx_ingest_file(asgart_b200_ctx* ctx, const char* path, int3
             for (int r = 0; r < kReaders; ++r) { readers[r].join(); all = all && ok[r]; }
             if (!all) { ctx->err = std::string("Unable to read FASTA file `") + path + "`"; return ASGART_B200_EINVAL; }
             const size_t got = want;
-            for (size_t i = 0; i < got && !seen_first; ++i)
-                if (ctx->stage[slot][i] != '\n') { seen_first = true; bad_first = ctx->stage[slot][i] != '>'; }
-            if (bad_first) break;
+            if (done == 0 && !first_byte_ok(n, ctx->stage[slot][0])) { bad_first = true; break; }
             CUDA_CHECK(cudaMemcpyAsync(d_file.p + done, ctx->stage[slot], got, cudaMemcpyHostToDevice, ctx->stream));
             CUDA_CHECK(cudaEventRecord(ctx->stage_ev[slot], ctx->stream));
             done += got;
@@ -1090,21 +1113,10 @@ int32_t asgart_b200_ctx_ingest_file(asgart_b200_ctx* ctx, const char* path, int3
         ctx->pieces.emplace_back();
         IngestPiece& piece = ctx->pieces.back();
         ingest_piece(ctx, d_file.p, n, skip_masked != 0, piece);
-        for (u64 off : piece.rec_off) {     // record ids: the few bytes after each '>' straight from the file
-            std::string name;
-            char buf[256];
-            bool end = false;
-            for (u64 at = off + 1; !end && at < n;) {
-                const ssize_t r = pread(f.fd, buf, sizeof buf, off_t(at));
-                if (r <= 0) break;
-                for (ssize_t i = 0; i < r; ++i) {
-                    if (fa_space(u8(buf[i]))) { end = true; break; }
-                    name.push_back(buf[i]);
-                }
-                at += u64(r);
-            }
-            piece.names.push_back(std::move(name));
-        }
+        ingest_record_ids(piece, n, [&](u64 at, char* buf, size_t cap) {   // the few bytes after each '>' straight from the file
+            const ssize_t r = pread(f.fd, buf, cap, off_t(at));
+            return r > 0 ? size_t(r) : size_t(0);
+        });
         ctx->st.ms_h2d += th.ms();
         ctx->st.h2d_bytes += n;
         return ASGART_B200_OK;

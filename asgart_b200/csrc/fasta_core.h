@@ -176,4 +176,31 @@ inline void chunks_from_runs(const std::vector<uint64_t>& rec_pos, uint64_t kept
     }
 }
 
+// What the bio FASTA reader (crate `bio`, io/fasta.rs; the reference's Cargo.toml takes any version and ships no lock file)
+// does besides splitting records, as seen by `for record in reader.records()` at src/bin/asgart.rs:286:
+//  * Reader::read returns "Expected > at record start." unless the FIRST byte of a non-empty file is '>' — a leading blank
+//    line is a parse error (first_byte_ok);
+//  * Records::next ends the iteration at the first EMPTY record — no id, no description, no sequence (Record::is_empty) — and
+//    never looks at the rest of the file (stop_at_empty_record). Such a record is a header line with nothing but white space
+//    after the '>' whose sequence lines, if any, are all blank.
+inline bool first_byte_ok(uint64_t n, uint8_t first) { return n == 0 || first == '>'; }
+
+// blank_header(r): only white space between record r's '>' and the end of that line. Cuts rec_off / rec_pos / kept at the
+// first empty record and returns how many records remain.
+template <class BlankHeader>
+inline size_t stop_at_empty_record(std::vector<uint64_t>& rec_off, std::vector<uint64_t>& rec_pos, uint64_t& kept,
+                                   BlankHeader blank_header) {
+    const size_t R = rec_pos.size();
+    for (size_t r = 0; r < R; ++r) {
+        const uint64_t end = r + 1 < R ? rec_pos[r + 1] : kept;
+        if (end == rec_pos[r] && blank_header(r)) {
+            kept = rec_pos[r];
+            rec_off.resize(r);
+            rec_pos.resize(r);
+            return r;
+        }
+    }
+    return R;
+}
+
 }  // namespace ab200

@@ -96,27 +96,31 @@ bool read_fasta(const std::string& path, bool skip_masked, uint64_t offset, asga
     std::ifstream in(path, std::ios::binary);
     if (!in) { g_err = "Unable to read FASTA file `" + path + "`"; return false; }
     std::string line, name;
-    bool have = false, any = false;
+    bool have = false, blank_header = false;
     size_t rec_start = p->data.size();
+    // false: the record is empty (no id, no description, no sequence) — the bio reader's iterator ends there and the rest
+    // of the file is never looked at (bio io/fasta.rs Records::next / Record::is_empty)
     auto close_record = [&]() {
         const size_t len = p->data.size() - rec_start;
+        if (blank_header && len == 0) return false;
         normalise(p->data.data() + rec_start, len, skip_masked);
         p->map.push_back(Fragment{name, uint64_t(rec_start), uint64_t(len)});
         find_chunks(p->data.data() + rec_start, len, rec_start, p->chunks);
+        return true;
     };
     (void)offset;
     while (std::getline(in, line)) {
-        if (!any && line.empty()) continue;
         if (!line.empty() && line[0] == '>') {
-            if (have) close_record();
+            if (have && !close_record()) return true;
             const size_t e = rtrim_len(line);
             size_t sp = 1;
             while (sp < e && !isspace((unsigned char)line[sp])) ++sp;
             name = line.substr(1, sp - 1);
+            blank_header = e <= 1;
             rec_start = p->data.size();
-            have = any = true;
+            have = true;
         } else {
-            if (!have) { g_err = "Unable to parse `" + path + "`"; return false; }
+            if (!have) { g_err = "Unable to parse `" + path + "`"; return false; }   // "Expected > at record start."
             const size_t e = rtrim_len(line);
             p->data.insert(p->data.end(), line.begin(), line.begin() + e);
         }

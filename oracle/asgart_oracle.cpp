@@ -622,17 +622,24 @@ std::string rtrim(const std::string& s) {
     return s.substr(0, e);
 }
 
-// :278-313 with the `bio` FASTA reader's record semantics
+// :278-313 with the record semantics of the `bio` crate's FASTA reader (io/fasta.rs; Cargo.toml asks for "*" and the
+// reference ships no lock file, so this follows the published Reader::read / Records::next):
+//  * a record starts at a line whose first byte is '>'; the first line of a non-empty file must be one ("Expected > at
+//    record start." -> "Unable to parse", also for a leading blank line);
+//  * id = header up to the first white space, the rest is the description; sequence lines are joined after trim_end;
+//  * the iterator ENDS at the first empty record (no id, no description, no sequence: Record::is_empty) and the rest of
+//    the file is never read.
 bool read_fasta(const std::string& filename, bool skip_masked, std::vector<Start>& map, std::vector<uint8_t>& r,
                 std::string& err) {
     std::ifstream in(filename, std::ios::binary);
     if (!in) { err = "Unable to read FASTA file `" + filename + "`"; return false; }
     std::string line;
     usize counter = 0;
-    bool have = false;
+    bool have = false, no_id_no_desc = false;
     std::string name;
     std::vector<uint8_t> seq;
     auto flush = [&]() {
+        if (no_id_no_desc && seq.empty()) return false;   // Records::next: `Ok(()) if record.is_empty() => None`
         if (!skip_masked)  // :291-293
             for (auto& c : seq) if (c >= 'a' && c <= 'z') c = uint8_t(c - 'a' + 'A');
         for (auto& c : seq) {  // :294-301
@@ -643,18 +650,17 @@ bool read_fasta(const std::string& filename, bool skip_masked, std::vector<Start
         counter += seq.size();
         r.insert(r.end(), seq.begin(), seq.end());
         seq.clear();
+        return true;
     };
-    bool first = true;
     while (std::getline(in, line)) {
-        if (first && line.empty()) continue;
         if (!line.empty() && line[0] == '>') {
-            if (have) flush();
+            if (have && !flush()) return true;
             std::string h = rtrim(line.substr(1));
             usize sp = 0;
             while (sp < h.size() && !isspace((unsigned char)h[sp])) ++sp;
             name = h.substr(0, sp);  // record.id(): header up to the first whitespace
+            no_id_no_desc = h.empty();
             have = true;
-            first = false;
         } else {
             if (!have) { err = "Unable to parse `" + filename + "`"; return false; }
             std::string t = rtrim(line);

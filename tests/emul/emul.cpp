@@ -244,8 +244,14 @@ extern "C" int64_t emul_ingest(const uint8_t* file, int64_t n_, int skip_masked,
         if (upto) after_last = outpos + upto;
         outpos = at;
     }
-    const u64 kept = outpos;
+    u64 kept = outpos;
     if (kept - after_last > kLongNRun) { run_start.push_back(after_last); run_len.push_back(kept - after_last); }
+    if (!first_byte_ok(n, n ? file[0] : 0)) return -3;
+    stop_at_empty_record(roff, rpos, kept, [&](size_t r) {
+        for (u64 at = roff[r] + 1; at < n && file[at] != '\n'; ++at)
+            if (!fa_space(file[at])) return false;
+        return true;
+    });
     if (i64(roff.size()) > rec_cap) return -1;
     for (size_t r = 0; r < roff.size(); ++r) { rec_off[r] = roff[r]; rec_pos[r] = rpos[r]; }
     *n_rec = i64(roff.size());

@@ -69,6 +69,8 @@ def ingest(blob: bytes, skip_masked: bool):
     kept = L.emul_ingest(b.ctypes.data if len(b) else None, len(b), int(skip_masked), strand.ctypes.data, cap, rec_off.ctypes.data,
                          rec_pos.ctypes.data, cap, C.byref(n_rec), chunks.ctypes.data, len(chunks), C.byref(n_chunks),
                          frag.ctypes.data, cap, C.byref(n_frag))
+    if kept == -3:
+        raise IOError("Unable to parse: expected > at record start")
     assert kept >= 0, kept
     names = []
     for r in range(n_rec.value):       # record ids: header up to the first white space (what api.cu reads out of the file)

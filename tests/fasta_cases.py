@@ -27,18 +27,34 @@ def line_and_record_blobs():
         fasta([("chr1\tdesc", a), ("chr2", b)], eol="\r\n"),
         fasta([("x", a), ("y", b)], final_eol=False),
         fasta([("x", a)], width=10 ** 9),
-        b"\n\n>lead empty lines\nACGT\nAC GT  \t\nGG\r\n\n\nTT \n>e1\n>e2 d\n\n>last\nNNNN>AC\n ACGT\nA",
+        b">interior empty lines\nACGT\nAC GT  \t\nGG\r\n\n\nTT \n>e1\n>e2 d\n\n>last\nNNNN>AC\n ACGT\nA",
         b">only header",
         b">only header\n",
         b">\nACGT\n",
         b"",
-        b"\n\n",
         b">a\n   \n \t \n>b\n\x0b\x0cAC\x0b\x0c\n",
+    ]
+    # the bio reader's iterator ends at the first EMPTY record (no id, no description, no sequence); records that have any
+    # of the three go on
+    blobs += [
+        b">a\nAC\n>\n>b\nGG\n",                         # only `a`
+        b">\n>b\nGG\n",                                 # nothing at all
+        b">a\nACGT\n>  \t\r\n\n  \n \t\n>b\nGG",          # blank header, blank lines: still empty -> only `a`
+        b">a\nAC\n> d\n>b\nGG\n",                       # a description is enough: a, "", b
+        b">a\nAC\n>\nT\n>b\nGG\n",                      # a sequence is enough
+        b">a\nAC\n>",                                   # empty record at the very end
+        b">a\n>b\n>\n>c\nAC\n",                         # empty NAMED records stay: a, b
+        b">" + b"N" * 6000 + b"\nAC\n>\n>b\n" + b"N" * 7000 + b"\n",
     ]
     blobs.append(b">bin\n" + rng.integers(0, 256, size=20000, dtype=np.uint8).tobytes().replace(b"\n>", b"\n?"))   # ids must stay UTF-8
     blobs.append(b">runs\n" + b"".join(bytes([v]) * 37 for v in range(256)) + b"\n" + bytes(range(256)) * 3)
     blobs.append(b">ws\n" + rng.choice(np.frombuffer(b"AC \t\r\n\x0b\x0c>", dtype=np.uint8), size=30000).tobytes())
     return blobs
+
+
+def unparsable_blobs():
+    """Files the bio reader refuses ("Expected > at record start."): anything but '>' as the first byte."""
+    return [b"\n\n>lead empty lines\nACGT\n", b"\n\n", b"\n", b" >x\nAC\n", b"\r\n>x\nAC\n", b"ACGT\n>late header\nACGT\n", b"A"]
 
 
 def n_run_records():

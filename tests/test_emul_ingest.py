@@ -5,9 +5,10 @@ is covered by tests/test_gpu_ingest.py on the same inputs."""
 import numpy as np
 import pytest
 
+import asgart_b200 as ab
 import oracle
 from tests import emul_harness
-from tests.fasta_cases import fasta, line_and_record_blobs, n_run_records, rand_seq
+from tests.fasta_cases import fasta, line_and_record_blobs, n_run_records, rand_seq, unparsable_blobs
 
 
 def _check(tmp_path, blob, skip_masked, tag):
@@ -25,6 +26,45 @@ def _check(tmp_path, blob, skip_masked, tag):
 def test_emul_ingest_line_and_record_shapes(tmp_path, skip_masked):
     for i, blob in enumerate(line_and_record_blobs()):
         _check(tmp_path, blob, skip_masked, f"s{i}")
+
+
+def test_emul_ingest_unparsable_files(tmp_path):
+    for i, blob in enumerate(unparsable_blobs()):
+        p = tmp_path / f"u{i}.fa"
+        p.write_bytes(blob)
+        with pytest.raises(IOError, match="Unable to parse"):
+            oracle.Prepared.from_files([str(p)])
+        with pytest.raises(IOError, match="Unable to parse"):
+            emul_harness.ingest(blob, False)
+
+
+def test_emul_ingest_empty_record_ends_the_file(tmp_path):
+    want = _check(tmp_path, b">a\nAC\n>\n>b\nGG\n", False, "e0")
+    assert want.map == [("a", 0, 2)] and want.strand.tobytes() == b"AC$"
+    want = _check(tmp_path, b">a\nAC\n> d\n>b\nGG\n", False, "e1")
+    assert want.map == [("a", 0, 2), ("", 2, 0), ("b", 2, 2)]
+    want = _check(tmp_path, b">\n>b\nGG\n", False, "e2")
+    assert want.map == [] and want.strand.tobytes() == b"$"
+
+
+@pytest.mark.parametrize("skip_masked", [False, True])
+def test_host_prepare_files_equals_oracle(tmp_path, skip_masked):
+    """asgart_b200_prepare_files (host.cpp: the host-side read_fasta + find_chunks_to_process, no GPU involved) on the same
+    files, several at once included, and the same refusals."""
+    paths = []
+    for i, blob in enumerate(line_and_record_blobs() + [fasta(n_run_records())]):
+        p = tmp_path / f"h{i}.fa"
+        p.write_bytes(blob)
+        paths.append(str(p))
+    for files in [[f] for f in paths] + [paths[:4], paths]:
+        want = oracle.Prepared.from_files(files, skip_masked)
+        got = ab.Prepared.from_files(files, skip_masked)
+        assert np.array_equal(got.strand, want.strand) and got.map == want.map and got.chunks == want.chunks, files
+    for i, blob in enumerate(unparsable_blobs()):
+        p = tmp_path / f"hu{i}.fa"
+        p.write_bytes(blob)
+        with pytest.raises(IOError, match="Unable to parse"):
+            ab.Prepared.from_files([paths[0], str(p)], skip_masked)
 
 
 def test_emul_ingest_n_runs_and_chunks(tmp_path):

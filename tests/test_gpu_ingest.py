@@ -14,7 +14,7 @@ from tests.test_gpu_parity import _osettings
 pytestmark = pytest.mark.gpu
 
 
-from tests.fasta_cases import fasta as _fasta, line_and_record_blobs, n_run_records, rand_seq as _rand_seq  # noqa: E402
+from tests.fasta_cases import fasta as _fasta, line_and_record_blobs, n_run_records, rand_seq as _rand_seq, unparsable_blobs  # noqa: E402
 
 
 def _check(tmp_path, blobs, skip_masked, tag="f"):
@@ -68,6 +68,15 @@ def test_ingest_errors(tmp_path):
             ctx.ingest([str(bad)])
         with pytest.raises(ab.AsgartB200Error, match="Unable to parse"):
             ctx.ingest([b"\r\n>x\nAC\n"])
+        for i, blob in enumerate(unparsable_blobs()):     # anything but '>' as the first byte, a leading blank line included
+            u = tmp_path / f"u{i}.fa"
+            u.write_bytes(blob)
+            with pytest.raises(ab.AsgartB200Error, match="Unable to parse"):
+                ctx.ingest([str(u)])
+            with pytest.raises(ab.AsgartB200Error, match="Unable to parse"):
+                ctx.ingest([blob])
+            with pytest.raises(IOError, match="Unable to parse"):
+                oracle.Prepared.from_files([str(u)])
         with pytest.raises(ab.AsgartB200Error, match="Unable to read FASTA file"):
             ctx.ingest([str(tmp_path / "missing.fa")])
         with pytest.raises(ab.AsgartB200Error):
@@ -77,6 +86,13 @@ def test_ingest_errors(tmp_path):
         ok = ctx.ingest([b">x\nACGTACGTAC\n"])
         assert ok.map == [("x", 0, 10)] and ok.chunks == [(0, 10)]
         assert ctx.download_strand().tobytes() == b"ACGTACGTAC$"
+
+
+def test_ingest_empty_record_ends_the_file(tmp_path):
+    """The bio reader's iterator stops at the first record without id, description and sequence (fasta_core.h)."""
+    big = b">" + b"N" * 6000 + b"\nAC\n>\n>b\n" + b"N" * 7000 + b"\n"
+    want = _check(tmp_path, [b">a\nAC\n>\n>b\nGG\n", big, b">\n>x\nAC\n", b">c\nGG\n"], False, tag="er")
+    assert [m[0] for m in want.map] == ["a", "N" * 6000, "c"] and want.strand.tobytes() == b"ACACGG$"
 
 
 def test_ingest_then_search_equals_host_prepared_path(tmp_path):
