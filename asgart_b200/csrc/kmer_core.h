@@ -41,6 +41,89 @@ AB_HD uint32_t complement_code(uint32_t c) {
     }
 }
 
+// The same two maps without branches, for the packing kernel (a switch per byte diverges five ways inside a warp and made
+// packing 3.1 Gbp cost 8 ms, ten times its memory time). A byte picks one of 16 slots, slot(c) = bits 3..1 of c, plus 8 when
+// bit 6 is clear: the six strand bytes land in six different slots ('A' 0, 'C' 1, 'T' 2, 'G' 3, 'N' 7, '$' 10). A slot
+// holds the byte it expects (0xFF elsewhere — slot(0xFF) = 7 expects 'N', so no byte matches an unused slot) and a nibble
+// of kCodeTab holds its code, of kCodeTabComp the code of its complement.
+AB_HD constexpr uint32_t code_slot(uint32_t c) { return ((c >> 1) & 7u) | ((((c >> 6) & 1u) ^ 1u) << 3); }
+constexpr uint64_t code_tab_build(int what, bool upper) {   // what 0: expected bytes (8 slots per word), 1: codes, 2: complement codes
+    const uint8_t by[6] = {'$', 'A', 'C', 'G', 'N', 'T'};
+    const uint32_t cd[6] = {CODE_END, CODE_A, CODE_C, CODE_G, CODE_N, CODE_T};
+    const uint32_t cc[6] = {CODE_END, CODE_T, CODE_G, CODE_C, CODE_N, CODE_A};
+    uint64_t r = what == 0 ? ~uint64_t(0) : 0;
+    for (int i = 0; i < 6; ++i) {
+        const uint32_t s = code_slot(by[i]);
+        if (what == 0) {
+            if ((s >= 8) == upper) r = (r & ~(uint64_t(0xFF) << ((s & 7u) * 8))) | (uint64_t(by[i]) << ((s & 7u) * 8));
+        } else {
+            r |= uint64_t(what == 1 ? cd[i] : cc[i]) << (s * 4);
+        }
+    }
+    return r;
+}
+constexpr uint64_t kByteTabLo = code_tab_build(0, false), kByteTabHi = code_tab_build(0, true);
+constexpr uint64_t kCodeTab = code_tab_build(1, false), kCodeTabComp = code_tab_build(2, false);
+// code of strand byte c under `tab` (kCodeTab / kCodeTabComp), CODE_BAD for any other byte
+AB_HD uint32_t code_of_byte_tab(uint32_t c, uint64_t tab) {
+    const uint32_t s = code_slot(c);
+    const uint32_t expect = uint32_t(((s & 8u) ? kByteTabHi : kByteTabLo) >> ((s & 7u) * 8)) & 0xFFu;
+    return expect == c ? uint32_t(tab >> (s * 4)) & 15u : uint32_t(CODE_BAD);
+}
+
+// ---- four bytes per instruction: the packing kernel's fast path -------------------------------------------------------
+// PRMT (byte permute) is a 8-entry byte table look-up for four bytes at once. slot3(c) = bits 3..1 of c tells A, C, T, G, N
+// apart (0, 1, 2, 3, 7); one PRMT fetches the byte each slot expects, one the code; when the four expected bytes equal the
+// four input bytes they are all in {A,C,G,N,T}. Anything else in a thread's 16 bytes — '$', a byte to reject, the ragged end
+// of the text — sends that thread down the byte-by-byte path above, so the fast path never has to decide what is an error.
+AB_HD uint32_t ab_prmt(uint32_t x, uint32_t y, uint32_t sel) {   // selectors 0..7 only (no sign-replicate mode)
+#if defined(__CUDA_ARCH__)
+    return __byte_perm(x, y, sel);
+#else
+    const uint64_t t = (uint64_t(y) << 32) | x;
+    uint32_t r = 0;
+    for (int i = 0; i < 4; ++i) r |= uint32_t((t >> (8 * ((sel >> (4 * i)) & 7u))) & 0xFFu) << (8 * i);
+    return r;
+#endif
+}
+AB_HD uint32_t ab_funnel_r(uint32_t lo, uint32_t hi, uint32_t shift) {   // low word of (hi:lo) >> (shift & 31)
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_r(lo, hi, shift);
+#else
+    return uint32_t(((uint64_t(hi) << 32) | lo) >> (shift & 31u));
+#endif
+}
+constexpr uint32_t kSlotByteLo = 0x47544341u, kSlotByteHi = 0x4EFFFFFFu;   // slot 0 'A', 1 'C', 2 'T', 3 'G', 7 'N'; 0xFF has slot 7
+constexpr uint32_t kSlotCodeLo = CODE_A | CODE_C << 8 | CODE_T << 16 | CODE_G << 24, kSlotCodeHi = CODE_N << 24;
+constexpr uint32_t kSlotCompLo = CODE_T | CODE_G << 8 | CODE_A << 16 | CODE_C << 24;
+// x: four symbols, the FIRST in the most significant byte. false: not all of them in {A,C,G,N,T}; else out16 = their four
+// codes (complemented if comp), first symbol in the top nibble.
+AB_HD bool pack4_fast(uint32_t x, bool comp, uint32_t& out16) {
+    const uint32_t slots = (x >> 1) & 0x07070707u;
+    const uint32_t sel = ab_prmt(slots | (slots >> 4), 0u, 0x4420u);          // nibble i = slot of byte i
+    const uint32_t codes = ab_prmt(comp ? kSlotCompLo : kSlotCodeLo, kSlotCodeHi, sel);
+    out16 = ab_prmt(codes | (codes >> 4), 0u, 0x4420u);                        // byte i -> nibble i
+    return ab_prmt(kSlotByteLo, kSlotByteHi, sel) == x;
+}
+// One thread's 16 symbols. W[0..4]: the five aligned 32-bit words (little endian, as loaded) that contain its 16 source
+// bytes, the lowest of which sits at byte m (0..3) of W[0]. Forwards the image follows the bytes, reversed it runs from the
+// last byte down. false: take the byte-by-byte path.
+AB_HD bool pack16_fast(const uint32_t* W, uint32_t m, bool reversed, bool comp, uint64_t& word) {
+    uint32_t q[4];
+    bool ok = true;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int g = 0; g < 4; ++g) {
+        const int mg = reversed ? 3 - g : g;                                   // memory group that holds image symbols 4g .. 4g+3
+        uint32_t x = ab_funnel_r(W[mg], W[mg + 1], 8u * m);
+        if (!reversed) x = ab_prmt(x, 0u, 0x0123u);                            // first symbol to the top byte
+        ok = pack4_fast(x, comp, q[g]) && ok;
+    }
+    word = (uint64_t(q[0]) << 48) | (uint64_t(q[1]) << 32) | (uint64_t(q[2]) << 16) | uint64_t(q[3]);
+    return ok;
+}
+
 struct Win {
     uint64_t hi, lo;  // 32 symbols, first symbol in the top nibble of hi
 };

@@ -590,6 +590,15 @@ void build_suffix_array(const u8* d_text, u64 n, IdxT* d_sa, const RankView<IdxT
     int p0 = int(std::ceil((std::log2(double(n)) + 6.0) / std::max(entropy, 0.25)));
     p0 = std::min(p0_cap, std::max(p0, 1));
     p0 = std::min(p0_cap, (ceil_div_i(i64(b) * p0, 8) * 8) / b);
+    // That rule prices an LSD sort, where every 8 key bits are a pass over all pairs. The MSD sort moves a pair once per level
+    // only while its bucket is still large, so longer keys cost it next to nothing — and every chance collision they remove is
+    // a suffix the doubling rounds never see (3.1 Gbp of DNA: 18 symbols leave 4.4 % of the suffixes with a random twin, 21
+    // leave 0.07 %). So: as many symbols as 63 bits hold (all-ones stays free for padding keys). ASGART_B200_P0=formula
+    // keeps the LSD rule for A/B runs.
+    {
+        static const char* p0_knob = getenv("ASGART_B200_P0");
+        if (msd_sort_applicable(b, p0, n) && !(p0_knob && p0_knob[0] == 'f')) p0 = std::max(p0, std::min(63 / b, 32));
+    }
     DevBuf<uint16_t> d_code(256, stream);
     CUDA_CHECK(cudaMemcpyAsync(d_code.p, h_code, sizeof h_code, cudaMemcpyHostToDevice, stream));
     u64 rep_unit = 0;  // sum of 2^(b*j): a key whose p0 symbols are all equal to c is c * rep_unit

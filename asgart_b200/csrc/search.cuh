@@ -40,20 +40,32 @@ __global__ void __launch_bounds__(256) pack_text_kernel(const u8* __restrict__ t
     __syncthreads();
     const u64 w = w0 + threadIdx.x;
     if (w >= n_words) return;
+    const u64 pw = w * 16;
+    const u32 valid = pw >= limit ? 0u : (limit - pw >= 16 ? 16u : u32(limit - pw));
+    // stage offset of image position pw + j: forwards s0 + j, reversed s0 - j
+    const int s0 = (mode & 2) ? int(n - 1 - pw - a0) : int(pw - a0);
     u64 word = 0;
-    bool bad = false;
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-        const u64 p = w * 16 + j;
-        u32 c = CODE_PAD;
-        if (p < limit) {
-            const u64 src = (mode & 2) ? (n - 1 - p) : p;
-            c = code_of_byte(stage[src - a0]);
-            if (c == CODE_BAD) bad = true;
-            if ((c == CODE_END) != (src == n)) bad = true;
-            if (mode & 1) c = complement_code(c);
+    if (valid == 16) {   // four bytes per instruction when all 16 are bases (kmer_core.h); '$', bytes to reject, ragged ends: below
+        const int low = (mode & 2) ? s0 - 15 : s0;
+        const u32* sw = reinterpret_cast<const u32*>(stage) + (low >> 2);
+        const u32 W[5] = {sw[0], sw[1], sw[2], sw[3], sw[4]};
+        if (pack16_fast(W, u32(low) & 3u, (mode & 2) != 0, (mode & 1) != 0, word)) {
+            packed[w] = word;
+            return;
         }
-        word |= u64(c & 15u) << (60 - 4 * j);
+        word = 0;
+    }
+    u32 bad = 0;
+    const u64 tab = (mode & 1) ? kCodeTabComp : kCodeTab;
+    const int step = (mode & 2) ? -1 : 1;
+    const i64 s_end = i64(n) - i64(a0);                      // stage offset of the '$' (only the direct mode reaches it)
+#pragma unroll 1
+    for (u32 j = 0; j < valid; ++j) {
+        const int so = s0 + step * int(j);
+        const u32 byte = stage[so];
+        const u32 c = code_of_byte_tab(byte, tab);
+        bad |= u32(c == CODE_BAD) | u32((byte == u32('$')) != (i64(so) == s_end));
+        word |= u64(c) << (60 - 4 * int(j));
     }
     packed[w] = word;
     if (bad) atomicOr(err, 1u);

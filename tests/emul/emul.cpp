@@ -21,22 +21,51 @@ using i64 = int64_t;
 namespace {
 struct Chunk { u64 c0, len, n_probes, probe_base, needle_start; };
 
-std::vector<u64> pack(const uint8_t* text, u64 n1, int mode) {  // pack_text_kernel, one word per iteration
+u64 g_pack_fast_words = 0, g_pack_fast_mismatches = 0, g_pack_tab_mismatches = 0;
+
+std::vector<u64> pack(const uint8_t* text, u64 n1, int mode) {  // pack_text_kernel, one word ("thread") per iteration
     const u64 n = n1 - 1, words = (n1 + 15) / 16 + 4, limit = mode == 0 ? n1 : n;
     std::vector<u64> P(words, 0);
     for (u64 w = 0; w < words; ++w) {
         u64 word = 0;
-        for (int j = 0; j < 16; ++j) {
+        for (int j = 0; j < 16; ++j) {            // the definition: byte by byte, plain switches
             const u64 p = w * 16 + j;
             u32 c = CODE_PAD;
             if (p < limit) {
                 const u64 src = (mode & 2) ? (n - 1 - p) : p;
                 c = code_of_byte(text[src]);
                 if (mode & 1) c = complement_code(c);
+                if (code_of_byte_tab(text[src], (mode & 1) ? kCodeTabComp : kCodeTab) != c) ++g_pack_tab_mismatches;   // the kernel's slow path
             }
             word |= u64(c & 15u) << (60 - 4 * j);
         }
         P[w] = word;
+        // the kernel's fast path on the same 16 bytes: the five aligned words around them as the kernel loads them from its stage
+        const u64 pw = w * 16;
+        if (pw < limit && limit - pw >= 16) {
+            const u64 low = (mode & 2) ? n - 1 - pw - 15 : pw;
+            u32 W[5];
+            for (int k = 0; k < 5; ++k) {
+                u32 x = 0;
+                for (int r = 0; r < 4; ++r) {
+                    const u64 at = (low & ~u64(3)) + 4 * k + r;
+                    x |= u32(at < n1 ? text[at] : uint8_t(0xAA)) << (8 * r);   // past the text: whatever the stage held
+                }
+                W[k] = x;
+            }
+            u64 fast = 0;
+            if (pack16_fast(W, u32(low & 3), (mode & 2) != 0, (mode & 1) != 0, fast)) {
+                ++g_pack_fast_words;
+                if (fast != word) ++g_pack_fast_mismatches;
+            } else {
+                bool all_bases = true;                                         // the fast path may only decline what is not 16 bases
+                for (int j = 0; j < 16; ++j) {
+                    const uint8_t c = text[(mode & 2) ? (n - 1 - pw - j) : pw + j];
+                    all_bases = all_bases && (c == 'A' || c == 'C' || c == 'G' || c == 'N' || c == 'T');
+                }
+                if (all_bases) ++g_pack_fast_mismatches;
+            }
+        }
     }
     return P;
 }
@@ -45,6 +74,25 @@ struct Result { std::vector<int64_t> fam_off{0}; std::vector<u64> fields; };
 }  // namespace
 
 extern "C" {
+
+// pack_text_kernel's two paths on an arbitrary byte string (any bytes: the error flag is not modelled, the codes are), all four
+// modes: out[0] = words the fast path produced, out[1] = fast-path words differing from the byte-by-byte definition or
+// declined although all 16 bytes were bases, out[2] = table-path codes differing from the switches
+void emul_pack_check(const uint8_t* text, int64_t n1, uint64_t* out) {
+    g_pack_fast_words = g_pack_fast_mismatches = g_pack_tab_mismatches = 0;
+    for (int mode = 0; mode < 4; ++mode) pack(text, u64(n1), mode);
+    out[0] = g_pack_fast_words; out[1] = g_pack_fast_mismatches; out[2] = g_pack_tab_mismatches;
+}
+
+// the branch-free byte -> code maps of the packing kernel against the plain switches, all 256 bytes: number of mismatches
+int emul_code_tab_mismatches() {
+    int bad = 0;
+    for (u32 c = 0; c < 256; ++c) {
+        bad += code_of_byte_tab(c, kCodeTab) != code_of_byte(uint8_t(c));
+        bad += code_of_byte_tab(c, kCodeTabComp) != complement_code(code_of_byte(uint8_t(c)));
+    }
+    return bad;
+}
 
 // windows / comparator unit hooks
 void emul_window(const uint8_t* text, int64_t n1, int mode, uint64_t pos, int k, uint64_t* hi, uint64_t* lo) {

@@ -24,6 +24,8 @@ def lib():
         L.emul_search.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(ablib.Settings), C.c_void_p]
         L.emul_lut.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
         L.emul_literal_bucket.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+        L.emul_code_tab_mismatches.restype = C.c_int
+        L.emul_pack_check.argtypes = [C.c_void_p, C.c_int64, C.c_void_p]
         L.emul_window.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p]
         for n in ("emul_result_n_families", "emul_result_n_sds"):
             getattr(L, n).restype = C.c_int64
@@ -35,6 +37,14 @@ def lib():
                                   C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
         _L = L
     return _L
+
+
+def pack_check(text: np.ndarray):
+    """(fast-path words, fast-path mismatches, table-path mismatches) of the packing kernel's logic on `text`, all four modes"""
+    t = np.ascontiguousarray(text, dtype=np.uint8)
+    out = np.zeros(3, dtype=np.uint64)
+    lib().emul_pack_check(t.ctypes.data, len(t), out.ctypes.data)
+    return tuple(int(x) for x in out)
 
 
 def search(strand, sa, chunks, settings_c):

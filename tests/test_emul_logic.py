@@ -47,6 +47,35 @@ def test_emul_stress(seed, label, kw):
     assert ctr["matches"] > 0
 
 
+def test_branch_free_byte_codes_equal_the_switches():
+    """pack_text_kernel's table-driven byte -> 4-bit code map (kmer_core.h code_of_byte_tab), direct and complemented, on all
+    256 byte values; the packing emulation below also runs it next to the plain switch on every byte it packs."""
+    assert emul_harness.lib().emul_code_tab_mismatches() == 0
+
+
+def test_packing_fast_path_equals_the_byte_by_byte_definition():
+    """pack_text_kernel (search.cuh) packs 16 bases with byte permutes, four per instruction (kmer_core.h pack16_fast), and
+    falls back to one byte at a time for anything else. Both against the plain definition: every length 17..96 (all the
+    alignments of the reversed modes and ragged ends), N-runs, '$' and foreign bytes in every position of a word."""
+    rng = np.random.default_rng(31)
+    fast_total = 0
+    for n in list(range(17, 97)) + [1000, 4096, 4097, 4111, 8192 + 5, 70001]:
+        t = rng.choice(np.frombuffer(b"ACGTN", dtype=np.uint8), size=n, p=[0.24, 0.24, 0.24, 0.24, 0.04])
+        t[-1] = ord("$")
+        fast, bad_fast, bad_tab = emul_harness.pack_check(t)
+        assert bad_fast == 0 and bad_tab == 0, n
+        fast_total += fast
+    assert fast_total > 10000
+    base = rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=161)
+    base[-1] = ord("$")
+    for pos in range(0, 160):
+        for byte in (ord("$"), ord("a"), 0, 0xFF, ord("B"), ord("U"), 0x4F, 0x40, ord("N")):
+            t = base.copy()
+            t[pos] = byte
+            fast, bad_fast, bad_tab = emul_harness.pack_check(t)
+            assert bad_fast == 0 and bad_tab == 0, (pos, byte)
+
+
 def test_emul_lut_matches_oracle():
     text = cases.stress_text(5, n=30000)
     strand = np.concatenate([text, np.frombuffer(b"$", dtype=np.uint8)])
