@@ -327,6 +327,19 @@ struct LutHook : SaKeyHook {
             IdxT* dp = ix.deep.p;
             const IdxT n1v = IdxT(n);
             CUDA_CHECK(cudaMemcpyAsync(dp + (M - 1), &n1v, sizeof(IdxT), cudaMemcpyHostToDevice, stream));
+            // short empty runs (the rule in a genome-sized table) in one pass; a run past the look-ahead leaves the rest to the scan
+            static const bool fill_scan_only = getenv("ASGART_B200_DEEP_FILL") && getenv("ASGART_B200_DEEP_FILL")[0] == 's';   // developer knob: "scan"
+            u32 h_over = 1;
+            if (!fill_scan_only) {
+                DevBuf<u32> d_over(1, stream);
+                d_over.zero();
+                deep_fill_kernel<IdxT><<<kNumSMs * 16, 256, 0, stream>>>(dp, M, d_over.p);
+                KERNEL_CHECK();
+                count_launch();
+                CUDA_CHECK(cudaMemcpyAsync(&h_over, d_over.p, sizeof h_over, cudaMemcpyDeviceToHost, stream));
+                CUDA_CHECK(cudaStreamSynchronize(stream));
+            }
+            if (h_over)
             device_scan<IdxT, MaxOp>([dp, M, n1v] __device__(u64 kx) { const IdxT v = dp[M - 1 - kx]; return v ? IdxT(n1v + 1 - v) : IdxT(0); },
                                      [dp, M, n1v] __device__(u64 kx, IdxT, IdxT inc) { dp[M - 1 - kx] = inc ? IdxT(n1v + 1 - inc) : n1v; }, M,
                                      (IdxT*)nullptr, stream);

@@ -236,6 +236,51 @@ __global__ void __launch_bounds__(256) lut_from_keys_kernel(const u64* __restric
     }
 }
 
+// Deep table, empty buckets: a slot no key hit (0) takes the start of the next slot that was hit; deep[M - 1] = n1 closes the
+// table. In a genome-sized table few slots are empty and the runs are short (3.1 Gbp in 4^15 slots: 5 %, mostly single), so
+// one pass does it: four slots per thread, a thread whose group ends on an empty slot looks ahead, at most kDeepLook slots.
+// It may read a slot its owner is filling at that moment — either 0 or the final value, and a filled value is exactly what
+// the look-ahead is after. A longer empty run sets *overflow and the caller runs the general scan over what is left (filled
+// slots then count as hit ones: same answer). deep must be 16-byte aligned.
+constexpr u32 kDeepLook = 256;
+template <typename IdxT>
+__global__ void __launch_bounds__(256) deep_fill_kernel(IdxT* __restrict__ deep_, u64 M, u32* __restrict__ overflow) {
+    volatile IdxT* deep = deep_;                    // the look-ahead reads slots other threads write
+    const u64 groups = (M + 3) / 4;
+    const u64 stride = u64(gridDim.x) * blockDim.x;
+    for (u64 g = u64(blockIdx.x) * blockDim.x + threadIdx.x; g < groups; g += stride) {
+        const u64 s0 = g * 4;
+        IdxT v[4];
+        if (s0 + 4 <= M) {                          // its own four slots (nobody else writes them): vector loads
+            if constexpr (sizeof(IdxT) == 4) {
+                const uint4 x = *reinterpret_cast<const uint4*>(deep_ + s0);
+                v[0] = IdxT(x.x); v[1] = IdxT(x.y); v[2] = IdxT(x.z); v[3] = IdxT(x.w);
+            } else {
+                const ulonglong2 x = *reinterpret_cast<const ulonglong2*>(deep_ + s0), y = *reinterpret_cast<const ulonglong2*>(deep_ + s0 + 2);
+                v[0] = IdxT(x.x); v[1] = IdxT(x.y); v[2] = IdxT(y.x); v[3] = IdxT(y.y);
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) v[q] = s0 + q < M ? deep[s0 + q] : IdxT(1);
+        }
+        if (v[0] != 0 && v[1] != 0 && v[2] != 0 && v[3] != 0) continue;
+        IdxT nxt = v[3];
+        if (nxt == 0) {
+            u64 t = s0 + 4;
+            for (u32 look = 0; look < kDeepLook && t < M; ++look, ++t) {
+                nxt = deep[t];
+                if (nxt != 0) break;
+            }
+            if (nxt == 0) { atomicOr(overflow, 1u); continue; }
+        }
+#pragma unroll
+        for (int q = 3; q >= 0; --q) {
+            if (v[q] == 0) { if (s0 + q < M) deep[s0 + q] = nxt; }
+            else nxt = v[q];
+        }
+    }
+}
+
 // slots of the 8-mer LUT whose bucket holds one of the last k-1 suffixes: there the reference's comparator is forced
 // to Less (src/searcher.rs:165-166, quirk Q6) and only its literal bisection reproduces its answer
 __global__ void q6_mark_kernel(const u64* __restrict__ PT, u64 n1, u32 k, u32* __restrict__ q6_bits) {
