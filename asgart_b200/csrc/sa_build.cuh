@@ -5,20 +5,27 @@
 // (checked against the reference's own library in tests/). Algorithm (Larsson–Sadakane doubling with discarding,
 // laid out for a GPU):
 //   0. byte histogram -> dense symbol codes 1..sigma (0 = "past the end", which orders a suffix that is a prefix of
-//      another one first, as divsufsort does); b bits per symbol, p0 = floor(64 / b) symbols per 64-bit key
-//      (DNA + '$': sigma = 6, b = 3, p0 = 21).
-//   1. key[i] = first p0 symbols of suffix i; one LSD radix sort of (key, i) over b*p0 bits.
-//   2. group heads by key change -> rank[] (= SA index of the group head) and SA[] for all; suffixes in groups of
-//      size > 1 are compacted into the work list (G = group head index, I = suffix).
-//   3. doubling rounds h = p0, 2p0, ...: key2 = rank[I + h] + 1 (0 past the end)  [random gather],
-//      radix sort of the work list by (G, key2), re-rank, write SA for suffixes that became unique, drop them,
+//      another one first, as divsufsort does); b bits per symbol.
+//   1. initial sort of (key, i), key[i] = first p0 symbols of suffix i. Genome-sized texts over small alphabets: the MSD
+//      sort of msd_sort.cuh (12-bit partition levels while a bucket is large, then one sort in shared memory) with as many
+//      symbols as 63 bits hold (DNA + '$': sigma = 6, b = 3, p0 = 21). Short texts, wide alphabets, or when the MSD sort
+//      declines: key generation + stable LSD radix passes over b*p0 bits, p0 sized so that random text is almost resolved.
+//   2. group heads by key change (hp_reduce / hp_emit) -> SA[] for all; suffixes in groups of size > 1 are compacted into
+//      the work list (G = group head index, I = suffix), those whose p0 symbols are all equal into the run round's list.
+//      rank[] (= SA index of the group head) is NOT materialised after the MSD sort: it starts as a sentinel and a gather
+//      that meets the sentinel looks the initial rank up in the sorted keys (initial_rank below: "lazy ranks"); the LSD
+//      path and ASGART_B200_LAZY_RANK=0 write rank[SA[i]] = head(i) for every i (scatter.cuh).
+//   3. run round: runs of >= p0 equal symbols (N-runs) ordered by (symbol after the run, run length) in one sort.
+//   4. doubling rounds h = p0, 2p0, ...: key2 = rank[I + h] + 1 (0 past the end)  [random gather],
+//      segmented sort of the work list by (G, key2), re-rank, write SA for suffixes that became unique, drop them,
 //      until the work list is empty.
-// Sharded form (SaGroup, sa_group.h; world > 1): every member scans the whole text (1 byte per position), keeps the
-// suffixes whose key prefix falls into its range (ranges cut from a histogram of the first 12 key bits so that they hold
-// ~n/world suffixes each) and runs steps 1-3 on them; group heads and SA slots are global indices (range base + local
-// position). The rank array is block-cyclic over the members (RankView): the initial ranks and every re-ranking are
-// stored straight into the owner's memory and the gather of step 3 reads from it (NVLink peer access). Two collectives
-// per doubling round keep reads and writes of rank[] apart; the SA pieces are exchanged once at the end.
+// Sharded form (SaGroup, sa_group.h; world > 1): member r owns the suffixes whose first four symbols fall into its range of
+// level-0 bins (ranges cut from the histogram the members count together, ~n/world suffixes each) and runs steps 1-4 on
+// them; group heads and SA slots are global indices (range base + local position). The rank array is cut into contiguous
+// slices by position (RankView): every re-ranking is stored straight into the owner's memory and the gather of step 4
+// reads from it (NVLink peer access); a lazy initial rank is looked up in the sorted keys of the member that owns the
+// key's bin (RankLookup: peer pointers to every member's keys). Two collectives per doubling round keep reads and writes
+// of rank[] apart; the SA pieces are exchanged once at the end.
 // Index width is a template parameter: u32 when n < 2^32 - 1 (all BASELINE configs), u64 beyond (composite keys then
 // need 128 bits: U128). Both paths are exercised by the tests on small inputs.
 #pragma once
