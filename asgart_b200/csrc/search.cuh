@@ -1,7 +1,10 @@
 // search.cuh — text packing, 8-mer LUT, probe search (stage A) kernels.
 //   pack_text_kernel      ASCII strand -> 4-bit packed text, or its complemented / reversed / reverse-complemented
 //                         image (the needle of src/bin/asgart.rs:206-218 for every chunk at once)      HBM stream
-//   lut_build_kernel      SA interval of every 8-mer (Searcher::new, src/searcher.rs:99-143)              HBM gather
+//   lut_from_keys_kernel  SA interval of every 8-mer (Searcher::new, src/searcher.rs:99-143) and the first suffix of every ACGT
+//                         15-mer ("deep table") from the initial sort's sorted keys; deep_fill_kernel closes empty buckets   HBM stream
+//   lut_build_kernel      the 8-mer intervals from a finished suffix array (uploaded index, short keys)   HBM gather
+//   lut_literal_kernel    the same by the reference's own bisection, for --trim (sorted only where the reference looks)
 //   probe_search_kernel   one lane per probe position: LUT narrow -> literal lock-step equal range -> filtered count
 //                         (Searcher::search src/searcher.rs:145-180 + src/automaton.rs:100-117)            HBM gather
 //   emit (inside the scan's output pass): surviving matches in SA order + event list
