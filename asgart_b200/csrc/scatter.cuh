@@ -1,7 +1,7 @@
 // scatter.cuh — out[idx[i]] = val[i] for an injective idx: the inverse-permutation scatter that turns "rank by sorted
 // position" into "rank by text position" in the suffix-array build. Since round 2 the build only comes here when the lazy
-// ranks of sa_build.cuh do not apply (LSD-sorted inputs, no deep table, ASGART_B200_LAZY_RANK=0) and for the small
-// permutations of the later rounds.
+// ranks of sa_build.cuh do not apply (LSD-sorted inputs — short texts, wide alphabets —, no deep table,
+// ASGART_B200_LAZY_RANK=0).
 //
 // A plain scatter of 4-byte values to random addresses costs a DRAM read-modify-write per element (B200, measured with
 // tools/scatter_bench.cu: 30.8 G elem/s for 57 M targets, 22.7 G elem/s for 1 G). When all targets of a launch fall
