@@ -89,3 +89,33 @@ def test_emul_ingest_random_files(tmp_path):
         n = int(rng.integers(1, 3000))
         body = rng.choice(alphabet, size=n, p=weights / weights.sum()).tobytes()
         _check(tmp_path, b">r" + str(i).encode() + b" d\n" + body, bool(i & 1), f"r{i}")
+
+
+def test_random_header_heavy_files_three_ways(tmp_path):
+    """Short random files dense in '>' and blanks (empty records, blank headers, refusals): the oracle, the host-side
+    prepare_files and the emulated device passes must agree on strand, map, chunks and on which files are refused."""
+    rng = np.random.default_rng(5)
+    alphabet = np.frombuffer(b"ACGTacgtNn \t\r\n\n\n>xX-", dtype=np.uint8)
+    weights = np.array([8, 8, 8, 8, 2, 2, 2, 2, 3, 1, 1, 1, 1, 2, 2, 6, 1, 1, 1, 1], dtype=float)
+    refused = stopped_early = 0
+    for i in range(400):
+        body = rng.choice(alphabet, size=int(rng.integers(0, 400)), p=weights / weights.sum()).tobytes()
+        blob = (b">" if rng.random() < 0.9 else b"") + body
+        p = tmp_path / "r.fa"
+        p.write_bytes(blob)
+        sm = bool(i & 1)
+        try:
+            want = oracle.Prepared.from_files([str(p)], sm)
+        except IOError:
+            refused += 1
+            with pytest.raises(IOError):
+                emul_harness.ingest(blob, sm)
+            with pytest.raises(IOError):
+                ab.Prepared.from_files([str(p)], sm)
+            continue
+        strand, frags, chunks = emul_harness.ingest(blob, sm)
+        assert np.array_equal(strand, want.strand[:-1]) and frags == want.map and chunks == want.chunks, blob
+        host = ab.Prepared.from_files([str(p)], sm)
+        assert np.array_equal(host.strand, want.strand) and host.map == want.map and host.chunks == want.chunks, blob
+        stopped_early += len(want.map) < blob.count(b"\n>") + 1
+    assert refused > 10 and stopped_early > 3

@@ -47,6 +47,30 @@ def test_emul_stress(seed, label, kw):
     assert ctr["matches"] > 0
 
 
+def test_emul_random_settings_sweep():
+    """Random texts (size, duplication density, N-runs, tandem repeats, one or two fragments) under random settings: probe
+    sizes around the 16 / 32 / 64-symbol window borders, gaps from 0 to 1000, cardinality caps from 1 up, all four
+    orientations. (An offline run of 8000 such cases found no difference; this keeps 60 of them in the suite.)"""
+    for seed in range(3000, 3015):
+        rng = np.random.default_rng(seed)
+        text = cases.stress_text(seed, n=int(rng.integers(20000, 60000)), n_dups=int(rng.integers(1, 30)), with_n=bool(rng.integers(0, 2)),
+                                 tandem=bool(rng.integers(0, 2)))
+        cut = int(rng.integers(1, len(text) - 1))
+        frags = [("a", 0, cut), ("b", cut, len(text) - cut)] if rng.random() < 0.7 else [("a", 0, len(text))]
+        prep = oracle.Prepared.from_memory(text, frags)
+        sa = oracle.best_suffix_array(prep.strand)
+        for _ in range(4):
+            kw = dict(probe_size=int(rng.choice([8, 9, 10, 12, 15, 16, 17, 20, 24, 31, 32, 33, 40, 48, 64, 65])),
+                      gap_size=int(rng.choice([0, 1, 5, 10, 30, 100, 250, 1000])), min_length=int(rng.choice([50, 100, 300, 1000, 2000])),
+                      max_cardinality=int(rng.choice([1, 2, 8, 50, 500, 100000])), reverse=bool(rng.integers(0, 2)),
+                      complement=bool(rng.integers(0, 2)))
+            so, sc = _settings_pair(kw)
+            want = oracle.search(prep.strand, sa, prep.chunks, so, 0, threads=2)
+            got, ctr = emul_harness.search(prep.strand, sa, prep.chunks, sc)
+            assert got == _strip(want.families.as_lists()), (seed, kw)
+            assert ctr == want.counters, (seed, kw)
+
+
 def test_branch_free_byte_codes_equal_the_switches():
     """pack_text_kernel's table-driven byte -> 4-bit code map (kmer_core.h code_of_byte_tab), direct and complemented, on all
     256 byte values; the packing emulation below also runs it next to the plain switch on every byte it packs."""
